@@ -1,0 +1,449 @@
+"""PyTorch-CPU restatement of the cope-nerf NeuS render/train hot path.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Every function cites the
+reference lines it follows (paths relative to /root/reference).  State is kept
+in plain dicts of tensors keyed like the reference's state_dict
+(`lin{l}.weight_g`, `lin{l}.weight_v`, `lin{l}.bias`, `variance`, `r`, `t`), so
+checkpoints and fixtures are interchangeable with the reference modules.
+
+Parity status: PINNED against the imported reference (tests/golden/*.npz made by
+tests/golden/make_golden.py; checked by tests/test_oracle_golden.py).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+__all__ = [
+    "embed", "embed_dim", "init_sdf_params", "init_color_params", "init_variance_params",
+    "wn_weight", "sdf_forward", "sdf_value", "sdf_gradient", "color_forward", "inv_s_from_variance",
+    "cdf_from_weights", "search_cdf", "sample_pdf", "up_sample", "cat_z_vals", "coarse_z", "render_core",
+    "render",
+    "vec2skew", "so3_exp", "make_c2w", "pose_forward", "camera_matrix", "pixel_grid", "patch_indices",
+    "ray_generation", "near_far", "cos_anneal_ratio", "eikonal_loss", "rgb_l1_loss", "sdf_flow_loss",
+    "train_step", "DEFAULT_CFG",
+]
+
+# configs/default.yaml:103-156 (no scene config overrides any of these shapes)
+DEFAULT_CFG = dict(
+    sdf=dict(d_out=257, d_in=4, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, bias=0.5,
+             scale=1.0, geometric_init=True, weight_norm=True),
+    color=dict(d_feature=256, mode="idr", d_in=11, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
+               multires_view=4, squeeze_out=True),
+    variance=dict(init_val=0.3),
+    renderer=dict(n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4, perturb=1.0),
+)
+
+
+# --------------------------------------------------------------------------- embedder
+def embed_dim(d, n_freqs):
+    return d * (1 + 2 * n_freqs)
+
+
+def embed(x, n_freqs):
+    """model/neus_embedder.py:6-51 — [x | sin(2^0 x) | cos(2^0 x) | ... ], blocks d wide."""
+    if n_freqs <= 0:
+        return x
+    cols = [x]
+    for k in range(n_freqs):
+        f = float(2 ** k)
+        cols.append(torch.sin(x * f))
+        cols.append(torch.cos(x * f))
+    return torch.cat(cols, dim=-1)
+
+
+# --------------------------------------------------------------------------- parameters
+def _wn_split(weight):
+    """nn.utils.weight_norm(dim=0): g = row norms (out,1), v = weight (neus_fields.py:261-262)."""
+    return weight.norm(dim=1, keepdim=True).clone(), weight.clone()
+
+
+def init_sdf_params(d_in=4, d_out=257, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, bias=0.5,
+                    scale=1.0, geometric_init=True, weight_norm=True, inside_outside=False):
+    """model/neus_fields.py:205-264.  Consumes the global torch RNG in the same order as the
+    reference constructor (one nn.Linear per layer, then the geometric re-initialisation)."""
+    dims = [d_in] + [d_hidden] * n_layers + [d_out]
+    if multires > 0:
+        dims[0] = embed_dim(d_in, multires)
+    n_lin = len(dims) - 1
+    p = {}
+    for l in range(n_lin):
+        out_dim = dims[l + 1] - dims[0] if (l + 1) in skip_in else dims[l + 1]
+        lin = torch.nn.Linear(dims[l], out_dim)
+        w, b = lin.weight.data, lin.bias.data
+        if geometric_init:
+            if l == n_lin - 1:
+                sign = -1.0 if inside_outside else 1.0
+                torch.nn.init.normal_(w, mean=sign * np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                torch.nn.init.constant_(b, -sign * bias)
+            elif multires > 0 and l == 0:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.constant_(w[:, 4:], 0.0)
+                torch.nn.init.normal_(w[:, :4], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            elif multires > 0 and l in skip_in:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                torch.nn.init.constant_(w[:, -(dims[0] - 4):], 0.0)
+            else:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+        g, v = _wn_split(w)
+        p[f"lin{l}.bias"] = b.clone()
+        p[f"lin{l}.weight_g"] = g
+        p[f"lin{l}.weight_v"] = v
+    return p
+
+
+def init_color_params(d_feature=256, mode="idr", d_in=11, d_out=3, d_hidden=256, n_layers=4,
+                      weight_norm=True, multires_view=4, squeeze_out=True, use_negative_ray_vector=False):
+    """model/neus_fields.py:307-344 (default nn.Linear init, then weight_norm)."""
+    dims = [d_in + d_feature] + [d_hidden] * n_layers + [d_out]
+    if multires_view > 0:
+        dims[0] += embed_dim(3, multires_view) - 3
+    p = {}
+    for l in range(len(dims) - 1):
+        lin = torch.nn.Linear(dims[l], dims[l + 1])
+        g, v = _wn_split(lin.weight.data)
+        p[f"lin{l}.bias"] = lin.bias.data.clone()
+        p[f"lin{l}.weight_g"] = g
+        p[f"lin{l}.weight_v"] = v
+    return p
+
+
+def init_variance_params(init_val=0.3):
+    """model/neus_fields.py:459-462."""
+    return {"variance": torch.tensor(init_val)}
+
+
+def wn_weight(p, l):
+    """torch._weight_norm(v, g, dim=0) = v * (g / ||v||_row)."""
+    v = p[f"lin{l}.weight_v"]
+    return v * (p[f"lin{l}.weight_g"] / v.norm(dim=1, keepdim=True))
+
+
+def _n_lin(p):
+    return len([k for k in p if k.endswith(".bias")])
+
+
+# --------------------------------------------------------------------------- fields
+def sdf_forward(p, x, multires=6, skip_in=(4,), scale=1.0):
+    """model/neus_fields.py:268-283 — PE, 9 weight-normed linears, softplus(beta=100), skip concat/sqrt2."""
+    x = x * scale
+    e = embed(x, multires)
+    h = e
+    n = _n_lin(p)
+    for l in range(n):
+        if l in skip_in:
+            h = torch.cat([h, e], dim=1) / np.sqrt(2)
+        h = F.linear(h, wn_weight(p, l), p[f"lin{l}.bias"])
+        if l < n - 1:
+            h = F.softplus(h, beta=100)
+    return torch.cat([h[:, :1] / scale, h[:, 1:]], dim=-1)
+
+
+def sdf_value(p, x, **kw):
+    """model/neus_fields.py:285-286."""
+    return sdf_forward(p, x, **kw)[:, :1]
+
+
+def sdf_gradient(p, x, create_graph=True, **kw):
+    """model/neus_fields.py:291-303 — d sdf / d(x,y,z,t) by autograd on a fresh forward; (P,1,4)."""
+    with torch.enable_grad():
+        x.requires_grad_(True)
+        y = sdf_value(p, x, **kw)
+        (g,) = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=create_graph, retain_graph=True)
+    return g.unsqueeze(1)
+
+
+def color_forward(p, points, normals, view_dirs, features, multires_view=4, squeeze_out=True):
+    """model/neus_fields.py:346-374, mode 'idr': cat[points, PE(view), normals, feature] -> ReLU MLP -> sigmoid."""
+    h = torch.cat([points, embed(view_dirs, multires_view), normals, features], dim=-1)
+    n = _n_lin(p)
+    for l in range(n):
+        h = F.linear(h, wn_weight(p, l), p[f"lin{l}.bias"])
+        if l < n - 1:
+            h = F.relu(h)
+    return torch.sigmoid(h) if squeeze_out else h
+
+
+def inv_s_from_variance(pv):
+    """model/neus_fields.py:464-465 + model/neus_renderer.py:360: exp(10 v) clipped to [1e-3, 1e3]; (1,1)."""
+    return (torch.ones([1, 1]) * torch.exp(pv["variance"] * 10.0)).clip(1e-3, 1e3)
+
+
+# --------------------------------------------------------------------------- sampling
+def cdf_from_weights(weights):
+    """model/neus_renderer.py:42-45."""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    c = torch.cumsum(pdf, -1)
+    return torch.cat([torch.zeros_like(c[..., :1]), c], -1)
+
+
+def search_cdf(cdf, bins, n_samples):
+    """model/neus_renderer.py:47-70 with det=True; returns (samples, inds int64)."""
+    u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples)
+    u = u.expand(list(cdf.shape[:-1]) + [n_samples]).contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    lo = (inds - 1).clamp(min=0)
+    hi = inds.clamp(max=cdf.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
+    b0, b1 = torch.gather(bins, 1, lo), torch.gather(bins, 1, hi)
+    den = c1 - c0
+    den = torch.where(den < 1e-5, torch.ones_like(den), den)
+    return b0 + (u - c0) / den * (b1 - b0), inds
+
+
+def sample_pdf(bins, weights, n_samples):
+    """model/neus_renderer.py:39-70 (det=True is the only mode up_sample uses, :223)."""
+    return search_cdf(cdf_from_weights(weights), bins, n_samples)[0]
+
+
+def up_sample(z, sdf, n_importance, inv_s, return_aux=False):
+    """model/neus_renderer.py:178-224 (inside_sphere forced to ones, :187)."""
+    n = z.shape[0]
+    s0, s1 = sdf[:, :-1], sdf[:, 1:]
+    z0, z1 = z[:, :-1], z[:, 1:]
+    mid = (s0 + s1) * 0.5
+    cos = (s1 - s0) / (z1 - z0 + 1e-5)
+    prev = torch.cat([torch.zeros([n, 1]), cos[:, :-1]], dim=-1)
+    cos = torch.minimum(prev, cos).clip(-1e3, 0.0)
+    dist = z1 - z0
+    p_cdf = torch.sigmoid((mid - cos * dist * 0.5) * inv_s)
+    n_cdf = torch.sigmoid((mid + cos * dist * 0.5) * inv_s)
+    alpha = (p_cdf - n_cdf + 1e-5) / (p_cdf + 1e-5)
+    trans = torch.cumprod(torch.cat([torch.ones([n, 1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = alpha * trans
+    cdf = cdf_from_weights(w)
+    new_z, inds = search_cdf(cdf, z, n_importance)
+    if return_aux:
+        return new_z.detach(), dict(weights=w, cdf=cdf, inds=inds)
+    return new_z.detach()
+
+
+def cat_z_vals(sdf_params, rays_o, rays_d, t, z, new_z, sdf, last, **kw):
+    """model/neus_renderer.py:282-298 — sort the union; unless last, query SDF at the new points."""
+    n, s = z.shape
+    k = new_z.shape[1]
+    zz, idx = torch.sort(torch.cat([z, new_z], dim=-1), dim=-1)
+    if not last:
+        pts = (rays_o[:, None, :] + rays_d[:, None, :] * new_z[..., :, None]).reshape(-1, 3)
+        x = torch.cat([pts, t.unsqueeze(0).repeat(pts.shape[0], 1)], dim=-1)
+        new_sdf = sdf_value(sdf_params, x, **kw).reshape(n, k)
+        sdf = torch.gather(torch.cat([sdf, new_sdf], dim=-1), 1, idx)
+    return zz, sdf
+
+
+# --------------------------------------------------------------------------- render_core / forward
+def render_core(P, rays_o, rays_d, rays_d_norm, t, z, sample_dist, cos_anneal=0.0, eval_mode=False,
+                sdf_kw=None, color_kw=None):
+    """model/neus_renderer.py:307-450.  P = dict(sdf=..., color=..., variance=...)."""
+    sdf_kw, color_kw = sdf_kw or {}, color_kw or {}
+    n, s = z.shape
+    tail = torch.tensor([float(torch.as_tensor(sample_dist).detach())]).expand(n, 1)
+    dists = torch.cat([z[:, 1:] - z[:, :-1], tail], -1)
+    mid_z = z + dists * 0.5
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., :, None]
+    dirs = rays_d[:, None, :].expand(pts.shape).reshape(-1, 3)
+    pts = pts.reshape(-1, 3)
+    x = torch.cat([pts, t.unsqueeze(0).repeat(pts.shape[0], 1)], dim=-1)
+
+    y = sdf_forward(P["sdf"], x, **sdf_kw)
+    sdf, feat = y[:, :1], y[:, 1:]
+    grad = sdf_gradient(P["sdf"], x.detach(), **sdf_kw).squeeze(1)         # (P,4); :356
+    normals, flows = grad[:, :3], grad[:, 3:]
+    rgb = color_forward(P["color"], x, grad, dirs, feat, **color_kw).reshape(n, s, 3)
+
+    inv_s = inv_s_from_variance(P["variance"]).expand(n * s, 1)
+    true_cos = (dirs * normals).sum(-1, keepdim=True)
+    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal) + F.relu(-true_cos) * cos_anneal)
+    d = dists.reshape(-1, 1)
+    p_cdf = torch.sigmoid((sdf - iter_cos * d * 0.5) * inv_s)
+    n_cdf = torch.sigmoid((sdf + iter_cos * d * 0.5) * inv_s)
+    alpha = ((p_cdf - n_cdf + 1e-5) / (p_cdf + 1e-5)).reshape(n, s).clip(0.0, 1.0)
+    trans = torch.cumprod(torch.cat([torch.ones([n, 1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = alpha * trans
+    color = (rgb * w[:, :, None]).sum(dim=1)
+    depth = (z * w).sum(dim=1).unsqueeze(-1)                                # z_vals, not mid (:417)
+    weighted_z = depth.detach().clone()
+    if eval_mode:
+        depth = depth / rays_d_norm
+    return dict(
+        color=color, depth_pred=depth, weighted_z_vals=weighted_z, sdf=sdf, dists=dists,
+        normals=normals.reshape(n, s, 3), sdf_flows=flows.reshape(n, s, 1),
+        sampled_points=pts.reshape(n, s, 3), s_val=1.0 / inv_s, mid_z_vals=mid_z, weights=w,
+        cdf=p_cdf.reshape(n, s), inside_sphere=torch.ones(n, s),
+        weight_inside=w.sum(-1).detach(), weight_outside=torch.zeros(n),
+        sampled_color=rgb, gradients=grad,
+    )
+
+
+def coarse_z(near, far, n_samples, t_rand=None):
+    """model/neus_renderer.py:466-483.  t_rand (N,n_samples) = the train-mode jitter, None = eval."""
+    u = torch.linspace(0.0, 1.0, n_samples)
+    z = near * (1.0 - u[None, :]) + far * u[None, :]
+    if t_rand is not None:
+        mids = 0.5 * (z[..., 1:] + z[..., :-1])
+        upper = torch.cat([mids, z[..., -1:]], -1)
+        lower = torch.cat([z[..., :1], mids], -1)
+        z = lower + (upper - lower) * t_rand
+    return z
+
+
+def render(P, rays_o, rays_d, rays_d_norm, t, near, far, cfg=None, cos_anneal=0.0, eval_mode=False,
+           t_rand=None, return_z=False):
+    """model/neus_renderer.py:453-584 (n_outside = 0, naive_render False, it >= importance_sampling_start).
+
+    Train mode draws torch.rand([N, n_samples]) from the CPU generator (:482) unless t_rand is given."""
+    cfg = cfg or DEFAULT_CFG["renderer"]
+    n = rays_o.shape[0]
+    n_samples, n_imp, steps = cfg["n_samples"], cfg["n_importance"], cfg["up_sample_steps"]
+    sample_dist = (far[0, 0] - near[0, 0]) / n_samples
+    if not eval_mode and t_rand is None:
+        t_rand = torch.rand([n, n_samples])
+    z = coarse_z(near, far, n_samples, None if eval_mode else t_rand)
+    if n_imp > 0:
+        with torch.no_grad():
+            pts = (rays_o[:, None, :] + rays_d[:, None, :] * z[..., :, None]).reshape(-1, 3)
+            x = torch.cat([pts, t.unsqueeze(0).repeat(pts.shape[0], 1)], dim=-1)
+            sdf = sdf_value(P["sdf"], x).reshape(n, n_samples)
+            for i in range(steps):
+                new_z = up_sample(z, sdf, n_imp // steps, 64 * 2 ** i)
+                z, sdf = cat_z_vals(P["sdf"], rays_o, rays_d, t, z, new_z, sdf, last=(i + 1 == steps))
+    rc = render_core(P, rays_o, rays_d, rays_d_norm, t, z, sample_dist, cos_anneal, eval_mode)
+    w = rc["weights"]
+    s_tot = z.shape[1]
+    out = dict(
+        sdf=rc["sdf"], color_fine=rc["color"], depth_pred=rc["depth_pred"],
+        weighted_z_vals=rc["weighted_z_vals"],
+        s_val=rc["s_val"].reshape(n, s_tot).mean(dim=-1, keepdim=True), cdf_fine=rc["cdf"],
+        weight_sum=w.sum(dim=-1, keepdim=True), weight_max=torch.max(w, dim=-1, keepdim=True)[0],
+        normals=rc["normals"], sdf_flows=rc["sdf_flows"], sampled_points=rc["sampled_points"], weights=w,
+        inside_sphere=rc["inside_sphere"], weight_inside=rc["weight_inside"],
+        weight_outside=rc["weight_outside"],
+    )
+    if return_z:
+        out["z_vals"] = z
+    return out
+
+
+# --------------------------------------------------------------------------- poses and rays
+def vec2skew(v):
+    """model/common.py:255-265."""
+    z = torch.zeros(1, dtype=torch.float32)
+    return torch.stack([torch.cat([z, -v[2:3], v[1:2]]),
+                        torch.cat([v[2:3], z, -v[0:1]]),
+                        torch.cat([-v[1:2], v[0:1], z])], dim=0)
+
+
+def so3_exp(r):
+    """model/common.py:268-277 (Rodrigues with ||r|| + 1e-15)."""
+    k = vec2skew(r)
+    n = r.norm() + 1e-15
+    return torch.eye(3) + (torch.sin(n) / n) * k + ((1 - torch.cos(n)) / n ** 2) * (k @ k)
+
+
+def make_c2w(r, t):
+    """model/common.py:279-308 — [R | t; 0 0 0 1]; so(3) exp + raw translation."""
+    top = torch.cat([so3_exp(r), t.unsqueeze(1)], dim=1)
+    return torch.cat([top, torch.tensor([[0.0, 0.0, 0.0, 1.0]])], dim=0)
+
+
+def pose_forward(pp, cam_id):
+    """model/poses_retriever.py:25-32; pp = dict(r=(C,3), t=(C,3), init_c2w=(C,4,4))."""
+    cam_id = int(cam_id)
+    return make_c2w(pp["r"][cam_id], pp["t"][cam_id]) @ pp["init_c2w"][cam_id]
+
+
+def camera_matrix(fx, fy, w, h):
+    """dataloading/dataset.py:108-111."""
+    return torch.tensor([[2 * fx / w, 0, 0, 0], [0, -2 * fy / h, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]],
+                        dtype=torch.float32)
+
+
+def pixel_grid(h, w):
+    """model/common.py:12-39 — integer (col,row) and normalised [-1,1] coords of the full h*w grid."""
+    rows, cols = torch.meshgrid(torch.arange(0, h), torch.arange(0, w), indexing="ij")
+    loc = torch.stack([cols, rows], dim=-1).long().view(1, -1, 2)
+    sc = loc.clone().float()
+    sc[:, :, 0] = 2.0 * sc[:, :, 0] / (w - 1) - 1.0
+    sc[:, :, 1] = 2.0 * sc[:, :, 1] / (h - 1) - 1.0
+    return loc, sc
+
+
+def patch_indices(h, w, patch_size, n_points):
+    """model/training.py:413-436 (CPU randperm)."""
+    n_patches = n_points // patch_size ** 2
+    ha, wa = h - patch_size + 1, w - patch_size + 1
+    n_patches = min(n_patches, ha * wa)
+    corners = torch.randperm(ha * wa)[:n_patches]
+    rows, cols = corners // wa, corners % wa
+    off = torch.arange(patch_size).repeat(patch_size, 1)
+    off = (off + off.t() * w).flatten()
+    return ((rows * w + cols).unsqueeze(1) + off.view(-1)).flatten()
+
+
+def ray_generation(pixels, camera_mat, world_mat, scale_mat):
+    """model/training.py:474-487 + model/common.py:175-215.
+    pixels (1,N,2) normalised; camera/scale (1,4,4); world (4,4).  Returns o (N,3), d (N,3), |d| (N,1)."""
+    n = pixels.shape[1]
+    m = torch.inverse(scale_mat) @ torch.inverse(world_mat) @ torch.inverse(camera_mat)
+    origin = torch.zeros(1, 4, n)
+    origin[:, -1] = 1.0
+    cam_w = (m @ origin)[:, :3].permute(0, 2, 1)
+    px = pixels.permute(0, 2, 1)
+    px = torch.cat([px, torch.ones_like(px)], dim=1)            # (x, y, 1, 1): depth = 1
+    pix_w = (m @ px)[:, :3].permute(0, 2, 1)
+    v = pix_w - cam_w
+    nv = v.norm(2, 2)
+    return cam_w.reshape(-1, 3), (v / nv.unsqueeze(-1)).reshape(-1, 3), nv.view(-1, 1)
+
+
+def near_far(rays_o, rays_d, depth_range):
+    """model/training.py:101-118 — the sphere bounds are overwritten by constants (kept on-graph)."""
+    a = torch.sum(rays_d ** 2, dim=-1, keepdim=True)
+    b = 2.0 * torch.sum(rays_o * rays_d, dim=-1, keepdim=True)
+    mid = 0.5 * (-b) / a
+    return (mid - 1.0) * 0 + depth_range[0], (mid + 1.0) * 0 + depth_range[1]
+
+
+def cos_anneal_ratio(it, anneal_end):
+    """model/training.py:120-124."""
+    return 1.0 if anneal_end == 0.0 else float(min(1.0, it / anneal_end))
+
+
+# --------------------------------------------------------------------------- losses / step
+def eikonal_loss(normals):
+    """train.py:526."""
+    return torch.mean((torch.linalg.norm(normals.reshape(-1, 3), ord=2, dim=-1) - 1.0) ** 2)
+
+
+def rgb_l1_loss(rgb, rgb_gt):
+    """model/training.py:508."""
+    return torch.sum(torch.abs(rgb - rgb_gt)) / float(rgb.shape[0])
+
+
+def sdf_flow_loss(out, ang_vel, vel):
+    """train.py:467-477 — |(w x p + v).n + d sdf/dt| weighted by detached render weights."""
+    pts = out["sampled_points"].reshape(-1, 3)
+    nrm = out["normals"].reshape(-1, 3)
+    fl = out["sdf_flows"].reshape(-1)
+    w = out["weights"].reshape(-1).detach()
+    flow = torch.linalg.cross(ang_vel.expand_as(pts), pts) + vel
+    return torch.sum(torch.abs(torch.sum(flow * nrm, dim=-1) + fl) * w) / (torch.sum(w) + 1e-10)
+
+
+def train_step(P, pose, pixels, camera_mat, scale_mat, rgb_gt, t, depth_range, cam_id=0, cos_anneal=0.5,
+               rgb_weight=0.33333, eikonal_weight=0.1, t_rand=None, eval_mode=False, cfg=None):
+    """One reference training iteration without the optimiser (train.py:425-532 restricted to the rgb +
+    eikonal terms): pose -> rays -> near/far -> NeuSRenderer.forward -> loss.  Caller runs .backward()."""
+    world = pose_forward(pose, cam_id)
+    o, d, dn = ray_generation(pixels, camera_mat, world, scale_mat)
+    near, far = near_far(o, d, depth_range)
+    out = render(P, o, d, dn, t, near, far, cfg=cfg, cos_anneal=cos_anneal, eval_mode=eval_mode,
+                 t_rand=t_rand, return_z=True)
+    l_rgb = rgb_l1_loss(out["color_fine"], rgb_gt)
+    l_eik = eikonal_loss(out["normals"])
+    loss = rgb_weight * l_rgb + eikonal_weight * l_eik
+    return loss, dict(out=out, rays_o=o, rays_d=d, rays_d_norm=dn, loss_rgb=l_rgb, loss_eikonal=l_eik)

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Generate golden vectors by importing the UNMODIFIED reference (mounted at /root/reference in the
+build container) and, in the same run, check the oracle restatement against it.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference is imported with the four shims of SURVEY.md §8c (stub mcubes/icecream/imageio/matplotlib,
+bypass model/__init__.py, Tensor.cuda -> identity on CPU).  None of them touches arithmetic.
+The fixtures hold inputs + the reference's outputs only; tests/test_oracle_golden.py replays them through
+`oracle/` without the reference present (the GPU box has no /root/reference).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("COPE_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    for n in ("mcubes", "icecream", "imageio", "cv2"):
+        m = types.ModuleType(n)
+        m.ic = lambda *a, **k: None
+        sys.modules.setdefault(n, m)
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
+    sys.path.insert(0, REF)
+    pkg = types.ModuleType("model")
+    pkg.__path__ = [os.path.join(REF, "model")]
+    sys.modules["model"] = pkg
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import warnings
+    warnings.filterwarnings("ignore")
+    from model import neus_fields, neus_renderer, neus_embedder, poses_retriever, common
+    try:
+        from model import training
+    except Exception as e:  # PIL / torchvision missing etc.
+        print("model.training import failed:", e)
+        training = None
+    return types.SimpleNamespace(fields=neus_fields, renderer=neus_renderer, embedder=neus_embedder,
+                                 poses=poses_retriever, common=common, training=training)
+
+
+def npd(d):
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+def sd_to_np(sd, prefix):
+    return {f"{prefix}{k}": v.detach().numpy() for k, v in sd.items()}
+
+
+def close(a, b, tol=1e-6, name=""):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    scale = max(1.0, b.abs().max().item() if b.numel() else 1.0)
+    assert err <= tol * scale, f"oracle != reference for {name}: max err {err:.3e}"
+    return err
+
+
+SMALL_SDF = dict(d_out=65, d_in=4, d_hidden=64, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1.0,
+                 geometric_init=True, weight_norm=True)
+SMALL_COL = dict(d_feature=64, mode="idr", d_in=11, d_out=3, d_hidden=64, n_layers=4, weight_norm=True,
+                 multires_view=4, squeeze_out=True)
+
+
+def main():
+    R = import_reference()
+    import oracle as O
+    G = {}
+
+    # ---------------------------------------------------------------- embedder
+    torch.manual_seed(1)
+    x4, x3 = torch.randn(7, 4), torch.randn(5, 3)
+    f6, d6 = R.embedder.get_embedder(6, input_dims=4)
+    f4, d4 = R.embedder.get_embedder(4)
+    e6, e4 = f6(x4), f4(x3)
+    assert d6 == 52 and d4 == 27
+    close(O.embed(x4, 6), e6, 0, "embed6"); close(O.embed(x3, 4), e4, 0, "embed4")
+    G["embed"] = npd(dict(x4=x4, x3=x3, e6=e6, e4=e4))
+
+    # ---------------------------------------------------------------- constructors: same RNG stream
+    cfg = O.DEFAULT_CFG
+    torch.manual_seed(678)
+    ref_sdf = R.fields.SDFNetwork(**cfg["sdf"])
+    ref_col = R.fields.RenderingNetwork(**cfg["color"])
+    ref_var = R.fields.SingleVarianceNetwork(**cfg["variance"])
+    torch.manual_seed(678)
+    o_sdf = O.init_sdf_params(**cfg["sdf"])
+    o_col = O.init_color_params(**cfg["color"])
+    o_var = O.init_variance_params(**cfg["variance"])
+    sums = {}
+    for tag, ref, mine in (("sdf", ref_sdf, o_sdf), ("color", ref_col, o_col), ("variance", ref_var, o_var)):
+        sd = ref.state_dict()
+        assert set(sd.keys()) == set(mine.keys()), (tag, sorted(sd.keys()), sorted(mine.keys()))
+        for k, v in sd.items():
+            close(mine[k], v, 0, f"init {tag}.{k}")
+            sums[f"{tag}.{k}.sum"] = v.double().sum().item()
+            sums[f"{tag}.{k}.head"] = v.flatten()[:4].numpy()
+    G["init_seed678"] = npd(sums)
+
+    # full-size nets (weights come from the seed, not from the fixture): forward + gradient on 16 points
+    torch.manual_seed(5)
+    xs = torch.cat([torch.randn(16, 3) * 0.7, torch.zeros(16, 1)], -1)
+    dirs = torch.nn.functional.normalize(torch.randn(16, 3), dim=-1)
+    y = ref_sdf(xs)
+    g = ref_sdf.gradient(xs.clone()).squeeze(1)
+    c = ref_col(xs, g, dirs, y[:, 1:])
+    close(O.sdf_forward(o_sdf, xs), y, 1e-6, "full sdf fwd")
+    close(O.sdf_gradient(o_sdf, xs.clone()).squeeze(1), g, 1e-5, "full sdf grad")
+    close(O.color_forward(o_col, xs, g.detach(), dirs, y[:, 1:].detach()), c, 1e-6, "full color")
+    G["full_fields_seed678"] = npd(dict(x=xs, dirs=dirs, y=y, grad=g, rgb=c))
+
+    # ---------------------------------------------------------------- small nets, weights in fixture
+    torch.manual_seed(11)
+    s_sdf = R.fields.SDFNetwork(**SMALL_SDF)
+    s_col = R.fields.RenderingNetwork(**SMALL_COL)
+    s_var = R.fields.SingleVarianceNetwork(0.3)
+    with torch.no_grad():  # de-trivialise: geometric init zeroes PE columns, perturb everything a bit
+        for p in list(s_sdf.parameters()) + list(s_col.parameters()):
+            p.add_(0.05 * torch.randn_like(p))
+    P = dict(sdf={k: v.detach().clone() for k, v in s_sdf.state_dict().items()},
+             color={k: v.detach().clone() for k, v in s_col.state_dict().items()},
+             variance={k: v.detach().clone() for k, v in s_var.state_dict().items()})
+    wts = {}
+    wts.update(sd_to_np(s_sdf.state_dict(), "sdf."))
+    wts.update(sd_to_np(s_col.state_dict(), "color."))
+    wts.update(sd_to_np(s_var.state_dict(), "variance."))
+    G["small_weights"] = wts
+
+    xs = torch.cat([torch.randn(24, 3) * 0.5, torch.full((24, 1), 0.25)], -1)
+    dirs = torch.nn.functional.normalize(torch.randn(24, 3), dim=-1)
+    y = s_sdf(xs)
+    g = s_sdf.gradient(xs.clone()).squeeze(1)
+    c = s_col(xs, g, dirs, y[:, 1:])
+    close(O.sdf_forward(P["sdf"], xs), y, 1e-6, "small sdf fwd")
+    close(O.sdf_gradient(P["sdf"], xs.clone()).squeeze(1), g, 1e-5, "small sdf grad")
+    close(O.color_forward(P["color"], xs, g.detach(), dirs, y[:, 1:].detach()), c, 1e-6, "small color")
+    # second-order: d/dtheta of sum(g^2) — exercises the double backward the eikonal loss needs
+    s_sdf.zero_grad()
+    (s_sdf.gradient(xs.clone()).squeeze(1)[:, :3].norm(dim=-1) - 1).pow(2).mean().backward()
+    eik = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in s_sdf.named_parameters()}
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P["sdf"].items()}
+    (O.sdf_gradient(Pg, xs.clone()).squeeze(1)[:, :3].norm(dim=-1) - 1).pow(2).mean().backward()
+    for k in eik:
+        close(Pg[k].grad if Pg[k].grad is not None else torch.zeros_like(Pg[k]), eik[k], 1e-5, f"eikonal grad {k}")
+    G["small_fields"] = npd(dict(x=xs, dirs=dirs, y=y, grad=g, rgb=c,
+                                 **{f"eik.{k}": v for k, v in eik.items()}))
+
+    # ---------------------------------------------------------------- sample_pdf (capture inds + cdf)
+    cap = {}
+    real_ss = torch.searchsorted
+
+    def spy(cdf, u, right=False, **kw):
+        out = real_ss(cdf, u, right=right, **kw)
+        cap["cdf"], cap["u"], cap["inds"] = cdf.clone(), u.clone(), out.clone()
+        return out
+
+    torch.manual_seed(3)
+    bins = torch.sort(torch.rand(9, 80) * 4 + 0.01, dim=-1)[0]
+    w = torch.rand(9, 79) ** 6
+    w[0] = 0.0                     # all-equal pdf
+    w[1, :40] = 0.0; w[1, 41:] = 0.0   # one spike: exercises denom < 1e-5
+    torch.searchsorted = spy
+    smp = R.renderer.sample_pdf(bins, w, 16, det=True)
+    torch.searchsorted = real_ss
+    o_cdf = O.cdf_from_weights(w)
+    close(o_cdf, cap["cdf"], 0, "cdf")
+    o_smp, o_inds = O.search_cdf(o_cdf, bins, 16)
+    assert torch.equal(o_inds, cap["inds"]); close(o_smp, smp, 0, "sample_pdf")
+    G["sample_pdf"] = npd(dict(bins=bins, weights=w, cdf=cap["cdf"], inds=cap["inds"], samples=smp))
+
+    # ---------------------------------------------------------------- up_sample / cat_z_vals
+    dummy = types.SimpleNamespace()
+    rnd = R.renderer.NeuSRenderer(None, s_sdf, s_var, s_col, None, 64, 64, 0, 4, 1.0, 64000, 0, False)
+    torch.manual_seed(4)
+    n = 12
+    ro = torch.randn(n, 3) * 0.1
+    rd = torch.nn.functional.normalize(torch.randn(n, 3) - torch.tensor([0, 0, 2.0]), dim=-1)
+    ups = {}
+    for S, inv_s in ((64, 64), (80, 128), (96, 256), (112, 512)):
+        z = torch.sort(torch.rand(n, S) * 4.9 + 0.01, dim=-1)[0]
+        sdf = (1.5 - z) * torch.rand(n, 1) + 0.05 * torch.randn(n, S)
+        torch.searchsorted = spy
+        nz = rnd.up_sample(ro, rd, z, sdf, 16, inv_s)
+        torch.searchsorted = real_ss
+        onz, aux = O.up_sample(z, sdf, 16, inv_s, return_aux=True)
+        close(onz, nz, 0, f"up_sample {S}"); assert torch.equal(aux["inds"], cap["inds"])
+        ups.update({f"z{S}": z, f"sdf{S}": sdf, f"new_z{S}": nz, f"inds{S}": cap["inds"], f"cdf{S}": cap["cdf"]})
+        if S == 64:
+            tt = torch.tensor([0.25])
+            with torch.no_grad():
+                z2, sdf2 = rnd.cat_z_vals(ro, rd, tt, z, nz, sdf, last=False)
+                z3, _ = rnd.cat_z_vals(ro, rd, tt, z, nz, sdf, last=True)
+                oz2, osdf2 = O.cat_z_vals(P["sdf"], ro, rd, tt, z, nz, sdf, last=False)
+            close(oz2, z2, 0, "cat z"); close(osdf2, sdf2, 1e-6, "cat sdf"); close(z3, z2, 0, "cat z last")
+            ups.update(dict(cat_z=z2, cat_sdf=sdf2, t=tt))
+    ups.update(dict(rays_o=ro, rays_d=rd))
+    G["up_sample"] = npd(ups)
+
+    # ---------------------------------------------------------------- NeuSRenderer.forward eval + train
+    KEYS = ["sdf", "color_fine", "depth_pred", "weighted_z_vals", "s_val", "cdf_fine", "weight_sum", "weight_max",
+            "normals", "sdf_flows", "sampled_points", "weights", "inside_sphere", "weight_inside", "weight_outside"]
+    n = 6
+    torch.manual_seed(6)
+    ro = torch.randn(n, 3) * 0.05
+    rd = torch.nn.functional.normalize(torch.randn(n, 3) * 0.3 - torch.tensor([0, 0, 1.0]), dim=-1)
+    dn = 1.0 + torch.rand(n, 1)
+    near, far = torch.full((n, 1), 0.01), torch.full((n, 1), 5.0)
+    tt = torch.tensor([0.25])
+    fw = dict(rays_o=ro, rays_d=rd, rays_d_norm=dn, t=tt, near=near, far=far)
+    out_e = rnd(ro, rd, dn, tt, near, far, cos_anneal_ratio=0.5, it=1, eval=True)
+    o_e = O.render(P, ro, rd, dn, tt, near, far, cos_anneal=0.5, eval_mode=True)
+    assert list(out_e.keys()) == KEYS, list(out_e.keys())
+    for k in KEYS:
+        close(o_e[k], out_e[k], 2e-5, f"render eval {k}")
+        fw[f"eval.{k}"] = out_e[k]
+    torch.manual_seed(77)
+    t_rand = torch.rand([n, 64])
+    torch.manual_seed(77)
+    out_t = rnd(ro, rd, dn, tt, near, far, cos_anneal_ratio=0.3, it=1, eval=False)
+    o_t = O.render(P, ro, rd, dn, tt, near, far, cos_anneal=0.3, eval_mode=False, t_rand=t_rand)
+    for k in KEYS:
+        close(o_t[k], out_t[k], 2e-5, f"render train {k}")
+        fw[f"train.{k}"] = out_t[k]
+    fw["t_rand"] = t_rand
+    G["render_small"] = npd(fw)
+
+    # ---------------------------------------------------------------- poses / rays
+    torch.manual_seed(8)
+    pr = R.poses.PoseRetriever(3)
+    with torch.no_grad():
+        pr.r[1] = torch.randn(3) * 0.05; pr.t[1] = torch.randn(3) * 0.05
+        pr.r[2] = torch.randn(3) * 0.8; pr.t[2] = torch.randn(3)
+        pr.init_c2w[2] = R.common.make_c2w(torch.randn(3) * 0.3, torch.randn(3))
+    pose = {k: v.detach().clone() for k, v in pr.state_dict().items()}
+    ps = {}
+    for cam in range(3):
+        c2w = pr(cam)
+        close(O.pose_forward(pose, cam), c2w, 1e-7, f"pose {cam}")
+        ps[f"c2w{cam}"] = c2w
+    ps.update({k: v for k, v in pose.items()})
+    H, W = 60, 80
+    Kc = O.camera_matrix(0.8 * W, 0.8 * W, W, H).unsqueeze(0)
+    Sc = torch.eye(4).unsqueeze(0)
+    if R.training is not None:
+        TT = R.training.Trainer
+        torch.manual_seed(9)
+        idx = TT.get_patch_indices(None, H, W, 4, 64)
+        torch.manual_seed(9)
+        close(O.patch_indices(H, W, 4, 64), idx, 0, "patch idx")
+        _, pix = R.common.arange_pixels((H, W), 1)
+        close(O.pixel_grid(H, W)[1], pix, 0, "pixel grid")
+        pn = pix[:, idx]
+        o, d, nn_ = TT.get_world_cameraOrigin_cameraRay(None, pn, Kc, pr(2), Sc)
+        oo, od, on = O.ray_generation(pn, Kc, O.pose_forward(pose, 2), Sc)
+        close(oo, o, 1e-6, "ray o"); close(od, d, 1e-6, "ray d"); close(on, nn_, 1e-6, "ray n")
+        nf = TT.near_far_from_sphere(types.SimpleNamespace(depth_range=[0.01, 5.0]), o, d)
+        onf = O.near_far(oo, od, [0.01, 5.0])
+        close(onf[0], nf[0], 0, "near"); close(onf[1], nf[1], 0, "far")
+        # pose gradients through the rays
+        pr.zero_grad()
+        o, d, nn_ = TT.get_world_cameraOrigin_cameraRay(None, pn, Kc, pr(1), Sc)
+        wgt_o, wgt_d = torch.randn_like(o), torch.randn_like(d)
+        ((o * wgt_o).sum() + (d * wgt_d).sum()).backward()
+        ps.update(dict(idx=idx, pix=pn, ray_o2=oo, ray_d2=od, ray_n2=on, wgt_o=wgt_o, wgt_d=wgt_d,
+                       ray_o1=o, ray_d1=d, dr1=pr.r.grad.clone(), dt1=pr.t.grad.clone(), K=Kc, H=H, W=W))
+        pg = {k: v.clone().requires_grad_(k in ("r", "t")) for k, v in pose.items()}
+        oo, od, _ = O.ray_generation(pn, Kc, O.pose_forward(pg, 1), Sc)
+        ((oo * wgt_o).sum() + (od * wgt_d).sum()).backward()
+        close(pg["r"].grad, pr.r.grad, 1e-5, "dr"); close(pg["t"].grad, pr.t.grad, 1e-5, "dt")
+    G["poses_rays"] = npd(ps)
+
+    # ---------------------------------------------------------------- one full step: all parameter gradients
+    n = 8
+    torch.manual_seed(10)
+    pn = (torch.rand(1, n, 2) * 2 - 1) * 0.9
+    rgb_gt = torch.rand(n, 3)
+    pr2 = R.poses.PoseRetriever(1)
+    with torch.no_grad():
+        pr2.r[0] = torch.randn(3) * 0.05; pr2.t[0] = torch.randn(3) * 0.05
+    for m in (s_sdf, s_col, s_var):
+        m.zero_grad()
+    TT = R.training.Trainer
+    world = pr2(0)
+    o, d, dnorm = TT.get_world_cameraOrigin_cameraRay(None, pn, Kc, world, Sc)
+    near, far = TT.near_far_from_sphere(types.SimpleNamespace(depth_range=[0.01, 5.0]), o, d)
+    torch.manual_seed(123)
+    t_rand = torch.rand([n, 64])
+    torch.manual_seed(123)
+    out = rnd(o, d, dnorm, tt, near, far, cos_anneal_ratio=0.5, it=1, eval=False)
+    l_rgb = torch.sum(torch.abs(out["color_fine"] - rgb_gt)) / float(n)
+    l_eik = torch.mean((torch.linalg.norm(out["normals"].reshape(-1, 3), ord=2, dim=-1) - 1.0) ** 2)
+    loss = 0.33333 * l_rgb + 0.1 * l_eik
+    loss.backward()
+    st = dict(pix=pn, rgb_gt=rgb_gt, t=tt, t_rand=t_rand, r=pr2.r.detach(), tr=pr2.t.detach(), loss=loss.detach(),
+              loss_rgb=l_rgb.detach(), loss_eik=l_eik.detach(), color=out["color_fine"], depth=out["depth_pred"],
+              dr=pr2.r.grad, dt=pr2.t.grad)
+    for tag, m in (("sdf", s_sdf), ("color", s_col), ("variance", s_var)):
+        for k, v in m.named_parameters():
+            st[f"grad.{tag}.{k}"] = v.grad.clone()
+    # oracle replay
+    Pg = {t_: {k: v.clone().requires_grad_(True) for k, v in P[t_].items()} for t_ in P}
+    pose2 = dict(r=pr2.r.detach().clone().requires_grad_(True), t=pr2.t.detach().clone().requires_grad_(True),
+                 init_c2w=pr2.init_c2w.detach().clone())
+    ol, oaux = O.train_step(Pg, pose2, pn, Kc, Sc, rgb_gt, tt, [0.01, 5.0], cos_anneal=0.5, t_rand=t_rand)
+    ol.backward()
+    close(ol, loss, 1e-6, "step loss")
+    for tag in ("sdf", "color", "variance"):
+        for k, v in Pg[tag].items():
+            ref = st[f"grad.{tag}.{k}"]
+            close(v.grad, ref, 2e-4, f"step grad {tag}.{k}")
+    close(pose2["r"].grad, pr2.r.grad, 2e-4, "step dr"); close(pose2["t"].grad, pr2.t.grad, 2e-4, "step dt")
+    G["step_small"] = npd(st)
+
+    for name, d in G.items():
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **d)
+        print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB, {len(d)} arrays)")
+    print("oracle == reference on every case")
+
+
+if __name__ == "__main__":
+    main()

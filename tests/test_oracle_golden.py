@@ -1,0 +1,137 @@
+"""Pins the oracle (oracle/neus_oracle.py) to the reference: replays the fixtures that
+tests/golden/make_golden.py produced from the imported reference.  CPU only."""
+import torch
+
+import oracle as O
+from conftest import assert_close, load_golden, unflatten
+
+KEYS = ["sdf", "color_fine", "depth_pred", "weighted_z_vals", "s_val", "cdf_fine", "weight_sum", "weight_max",
+        "normals", "sdf_flows", "sampled_points", "weights", "inside_sphere", "weight_inside", "weight_outside"]
+
+
+def test_embedder():
+    g = load_golden("embed")
+    assert torch.equal(O.embed(g["x4"], 6), g["e6"])
+    assert torch.equal(O.embed(g["x3"], 4), g["e4"])
+
+
+def test_constructor_rng_stream():
+    """Reference constructors under seed 678 (configs/default.yaml:51) == oracle init under the same seed."""
+    g = load_golden("init_seed678")
+    torch.manual_seed(678)
+    P = dict(sdf=O.init_sdf_params(**O.DEFAULT_CFG["sdf"]), color=O.init_color_params(**O.DEFAULT_CFG["color"]),
+             variance=O.init_variance_params(**O.DEFAULT_CFG["variance"]))
+    n = 0
+    for tag, p in P.items():
+        for k, v in p.items():
+            assert_close(v.double().sum(), g[f"{tag}.{k}.sum"], 1e-12, f"{tag}.{k}.sum")
+            assert torch.equal(v.flatten()[:4], g[f"{tag}.{k}.head"].flatten())
+            n += 1
+    assert n == 27 + 15 + 1
+    assert sum(v.numel() for v in P["sdf"].values()) == 529050
+    assert sum(v.numel() for v in P["color"].values()) == 273926
+
+
+def test_full_size_fields():
+    g = load_golden("full_fields_seed678")
+    torch.manual_seed(678)
+    sdf = O.init_sdf_params(**O.DEFAULT_CFG["sdf"])
+    col = O.init_color_params(**O.DEFAULT_CFG["color"])
+    y = O.sdf_forward(sdf, g["x"])
+    grad = O.sdf_gradient(sdf, g["x"].clone()).squeeze(1)
+    assert_close(y, g["y"], 1e-6, "y")
+    assert_close(grad, g["grad"], 1e-5, "grad")
+    assert_close(O.color_forward(col, g["x"], grad.detach(), g["dirs"], y[:, 1:].detach()), g["rgb"], 1e-6, "rgb")
+
+
+def test_small_fields_and_eikonal_double_backward(small_params):
+    g = load_golden("small_fields")
+    P = small_params
+    y = O.sdf_forward(P["sdf"], g["x"])
+    grad = O.sdf_gradient(P["sdf"], g["x"].clone()).squeeze(1)
+    assert_close(y, g["y"], 1e-6, "y")
+    assert_close(grad, g["grad"], 1e-5, "grad")
+    assert_close(O.color_forward(P["color"], g["x"], grad.detach(), g["dirs"], y[:, 1:].detach()), g["rgb"], 1e-6)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P["sdf"].items()}
+    (O.sdf_gradient(Pg, g["x"].clone()).squeeze(1)[:, :3].norm(dim=-1) - 1).pow(2).mean().backward()
+    for k, v in Pg.items():
+        got = v.grad if v.grad is not None else torch.zeros_like(v)
+        assert_close(got, g[f"eik.{k}"], 1e-5, k)
+
+
+def test_sample_pdf_bit_exact():
+    g = load_golden("sample_pdf")
+    cdf = O.cdf_from_weights(g["weights"])
+    assert torch.equal(cdf, g["cdf"])
+    smp, inds = O.search_cdf(g["cdf"], g["bins"], 16)
+    assert torch.equal(inds, g["inds"]) and inds.dtype == torch.int64
+    assert torch.equal(smp, g["samples"])
+    assert torch.equal(O.sample_pdf(g["bins"], g["weights"], 16), g["samples"])
+
+
+def test_up_sample_and_cat(small_params):
+    g = load_golden("up_sample")
+    for S, inv_s in ((64, 64), (80, 128), (96, 256), (112, 512)):
+        nz, aux = O.up_sample(g[f"z{S}"], g[f"sdf{S}"], 16, inv_s, return_aux=True)
+        assert torch.equal(aux["inds"], g[f"inds{S}"])
+        assert torch.equal(aux["cdf"], g[f"cdf{S}"])
+        assert torch.equal(nz, g[f"new_z{S}"])
+    with torch.no_grad():
+        z2, s2 = O.cat_z_vals(small_params["sdf"], g["rays_o"], g["rays_d"], g["t"], g["z64"], g["new_z64"],
+                              g["sdf64"], last=False)
+    assert torch.equal(z2, g["cat_z"])
+    assert_close(s2, g["cat_sdf"], 1e-6)
+    assert (z2[:, 1:] > z2[:, :-1]).all(), "fixture must have no exact ties (SURVEY gotcha 10)"
+
+
+def test_renderer_forward_eval_and_train(small_params):
+    g = load_golden("render_small")
+    a = (g["rays_o"], g["rays_d"], g["rays_d_norm"], g["t"], g["near"], g["far"])
+    oe = O.render(small_params, *a, cos_anneal=0.5, eval_mode=True)
+    ot = O.render(small_params, *a, cos_anneal=0.3, eval_mode=False, t_rand=g["t_rand"])
+    assert [k for k in oe.keys()] == KEYS
+    for k in KEYS:
+        assert_close(oe[k], g[f"eval.{k}"], 2e-5, f"eval.{k}")
+        assert_close(ot[k], g[f"train.{k}"], 2e-5, f"train.{k}")
+    # the train-mode jitter comes from the CPU generator (neus_renderer.py:482)
+    torch.manual_seed(77)
+    o2 = O.render(small_params, *a, cos_anneal=0.3, eval_mode=False)
+    assert_close(o2["color_fine"], g["train.color_fine"], 2e-5)
+
+
+def test_poses_and_rays():
+    g = load_golden("poses_rays")
+    pose = dict(r=g["r"], t=g["t"], init_c2w=g["init_c2w"])
+    for cam in range(3):
+        assert_close(O.pose_forward(pose, cam), g[f"c2w{cam}"], 1e-7, f"c2w{cam}")
+    H, W = int(g["H"]), int(g["W"])
+    torch.manual_seed(9)
+    assert torch.equal(O.patch_indices(H, W, 4, 64), g["idx"])
+    assert torch.equal(O.pixel_grid(H, W)[1][:, g["idx"]], g["pix"])
+    S = torch.eye(4).unsqueeze(0)
+    o, d, n = O.ray_generation(g["pix"], g["K"], O.pose_forward(pose, 2), S)
+    assert_close(o, g["ray_o2"], 1e-6); assert_close(d, g["ray_d2"], 1e-6); assert_close(n, g["ray_n2"], 1e-6)
+    pg = {k: v.clone().requires_grad_(k in ("r", "t")) for k, v in pose.items()}
+    o, d, _ = O.ray_generation(g["pix"], g["K"], O.pose_forward(pg, 1), S)
+    ((o * g["wgt_o"]).sum() + (d * g["wgt_d"]).sum()).backward()
+    assert_close(pg["r"].grad, g["dr1"], 1e-5, "dr"); assert_close(pg["t"].grad, g["dt1"], 1e-5, "dt")
+    # r = 0 (the zero-initialised common case, SURVEY gotcha 15): R = I exactly
+    assert torch.equal(O.so3_exp(torch.zeros(3)), torch.eye(3))
+
+
+def test_full_step_parameter_gradients(small_params):
+    g = load_golden("step_small")
+    P = {t: {k: v.clone().requires_grad_(True) for k, v in small_params[t].items()} for t in small_params}
+    pose = dict(r=g["r"].clone().requires_grad_(True), t=g["tr"].clone().requires_grad_(True),
+                init_c2w=torch.eye(4).unsqueeze(0))
+    H, W = 60, 80
+    K = O.camera_matrix(0.8 * W, 0.8 * W, W, H).unsqueeze(0)
+    loss, aux = O.train_step(P, pose, g["pix"], K, torch.eye(4).unsqueeze(0), g["rgb_gt"], g["t"], [0.01, 5.0],
+                             cos_anneal=0.5, t_rand=g["t_rand"])
+    loss.backward()
+    assert_close(loss, g["loss"], 1e-6, "loss")
+    assert_close(aux["out"]["color_fine"], g["color"], 1e-5); assert_close(aux["out"]["depth_pred"], g["depth"], 1e-5)
+    for tag in ("sdf", "color", "variance"):
+        for k, v in P[tag].items():
+            assert_close(v.grad, g[f"grad.{tag}.{k}"], 2e-4, f"{tag}.{k}")
+    assert_close(pose["r"].grad, g["dr"], 2e-4, "dr"); assert_close(pose["t"].grad, g["dt"], 2e-4, "dt")
