@@ -1,0 +1,131 @@
+"""ctypes binding of libcope_b200.so (include/cope_b200.h).
+
+There is NO fallback: if the library is missing, or a kernel entry point is called without a CUDA device,
+this raises.  Building: `python -m cope_nerf_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcope_b200.so")
+MAX_LIN = 12
+PREC_FP32, PREC_BF16 = 0, 1
+
+_f = C.c_void_p      # device pointers travel as integers
+_i, _l, _fl = C.c_int, C.c_int64, C.c_float
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("n_lin", C.c_int32), ("d_in", C.c_int32), ("multires", C.c_int32), ("skip_layer", C.c_int32),
+                ("dims_in", C.c_int32 * MAX_LIN), ("dims_out", C.c_int32 * MAX_LIN)]
+
+    @staticmethod
+    def make(dims_in, dims_out, d_in, multires, skip_layer):
+        d = MlpDesc()
+        d.n_lin, d.d_in, d.multires, d.skip_layer = len(dims_in), d_in, multires, skip_layer
+        for k, (a, b) in enumerate(zip(dims_in, dims_out)):
+            d.dims_in[k], d.dims_out[k] = a, b
+        return d
+
+
+_D = C.POINTER(MlpDesc)
+_SIGS = {
+    "cope_version": (C.c_int, []),
+    "cope_last_error": (C.c_char_p, []),
+    "cope_launch_count": (C.c_uint64, []),
+    "cope_mlp_flat_floats": (_l, [_D]),
+    "cope_weightnorm_fwd": (_i, [_f, _f, _f, _i, _i, _f]),
+    "cope_weightnorm_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _f]),
+    "cope_embed_fwd": (_i, [_f, _l, _i, _i, _f, _f]),
+    "cope_sdf_saved_floats": (_l, [_D, _l, _i, _i]),
+    "cope_sdf_ws_floats": (_l, [_D, _l, _i]),
+    "cope_sdf_query": (_i, [_D, _f, _f, _l, _f, _f, _i, _f]),
+    "cope_sdf_fwd": (_i, [_D, _f, _f, _l, _f, _i, _f, _i, _f, _f, _f, _i, _f]),
+    "cope_sdf_bwd": (_i, [_D, _f, _f, _l, _f, _f, _i, _f, _i, _f, _f, _f, _i, _f, _i, _f]),
+    "cope_color_saved_floats": (_l, [_D, _l, _i]),
+    "cope_color_ws_floats": (_l, [_D, _l, _i]),
+    "cope_color_fwd": (_i, [_D, _f, _f, _f, _i, _i, _f, _f, _i, _l, _f, _f, _f, _i, _f]),
+    "cope_color_bwd": (_i, [_D, _f, _f, _i, _i, _l, _f, _f, _f, _f, _f, _f, _f, _i, _f, _i, _f]),
+    "cope_ray_points": (_i, [_f, _f, _f, _f, _f, _f, _i, _l, _i, _i, _f, _f, _f, _f]),
+    "cope_ray_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),
+    "cope_coarse_z": (_i, [_f, _f, _f, _l, _i, _f, _f]),
+    "cope_sample_cdf": (_i, [_f, _f, _l, _i, _i, _f, _f, _f]),
+    "cope_upsample": (_i, [_f, _f, _l, _i, _i, _fl, _f, _f, _f, _f]),
+    "cope_merge_z": (_i, [_f, _f, _f, _f, _l, _i, _i, _f, _f, _f]),
+    "cope_composite_fwd": (_i, [_f] * 8 + [_fl, _i, _l, _i] + [_f] * 8 + [_f]),
+    "cope_composite_bwd": (_i, [_f] * 8 + [_fl, _i, _l, _i] + [_f] * 8 + [_f]),
+    "cope_pose_fwd": (_i, [_f, _f, _f, _f, _f]),
+    "cope_pose_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f]),
+    "cope_raygen_fwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f]),
+    "cope_raygen_bwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f, _f, _f]),
+    "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+class CopeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (no GPU needed for this); raises loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CopeError(f"{LIB_PATH} is missing: run `python -m cope_nerf_b200.build`. "
+                            "cope_nerf_b200 has no CPU / PyTorch fallback path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA fp32/int64 and dense enough for
+    the callee's stated layout; contiguity is the caller's contract."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CopeError("cope_nerf_b200 kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
+    return t.data_ptr()
+
+
+def stream():
+    if not torch.cuda.is_available():
+        raise CopeError("cope_nerf_b200 kernels need a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise CopeError(f"{name} failed ({rc}): {lib.cope_last_error().decode()}")
+
+
+def query(name, *args):
+    n = getattr(load(), name)(*args)
+    if n < 0:
+        raise CopeError(f"{name} failed: {load().cope_last_error().decode()}")
+    return n
+
+
+_scratch = {}
+
+
+def scratch(n_floats, device):
+    """Grow-only per-device fp32 scratch (stream-ordered reuse on the current stream)."""
+    if not torch.cuda.is_available():
+        raise CopeError("cope_nerf_b200 kernels need a CUDA device (sm_100a); there is no CPU fallback")
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < n_floats:
+        buf = torch.empty(int(n_floats * 1.25) + 1024, dtype=torch.float32, device=device)
+        _scratch[key] = buf
+    return buf

@@ -1,0 +1,276 @@
+"""Drop-in NeuSRenderer (reference: model/neus_renderer.py:107-584) on libcope_b200.
+
+`forward` keeps the reference signature and the 15 output keys.  Internally:
+  coarse z (cope_coarse_z) -> [no grad] SDF queries + 4x (cope_upsample, cope_merge_z) -> one fused autograd
+  node for render_core: cope_ray_points -> cope_sdf_fwd (value + analytic gradient in one pass) -> cope_color_fwd
+  -> cope_composite_fwd, with a hand-written backward (composite -> colour -> SDF first+second order -> rays).
+No host synchronisation happens inside forward/backward (sample_dist is read on the device).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+__all__ = ["NeuSRenderer", "sample_pdf"]
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+def sample_pdf(bins, weights, n_samples, det=True, return_inds=False):
+    """model/neus_renderer.py:39-70 (det=True).  The CDF is built with torch ops (as the reference does) and the
+    inverse-CDF step runs in cope_sample_cdf; indices are bit-exact w.r.t. torch.searchsorted(right=True)."""
+    if not det:
+        raise NotImplementedError("up_sample only ever uses det=True (model/neus_renderer.py:223)")
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1).contiguous()
+    return sample_cdf(cdf, bins, n_samples, return_inds)
+
+
+def sample_cdf(cdf, bins, n_samples, return_inds=False):
+    n, s = cdf.shape
+    out = _f32(n, n_samples, device=cdf.device)
+    inds = torch.empty(n, n_samples, dtype=torch.int64, device=cdf.device) if return_inds else None
+    L.call("cope_sample_cdf", L.ptr(cdf.contiguous()), L.ptr(bins.contiguous()), n, s, n_samples, L.ptr(out),
+           L.ptr(inds), L.stream())
+    return (out, inds) if return_inds else out
+
+
+class _RenderCoreFn(torch.autograd.Function):
+    """render_core (model/neus_renderer.py:307-450) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
+                n_coarse, cos_anneal, eval_mode):
+        sdf_net, col_net = rnd.sdf_network, rnd.color_network
+        dev = z.device
+        N, S = z.shape
+        P = N * S
+        s = L.stream()
+        rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+        rays_d_norm = rays_d_norm.contiguous().float()
+        z = z.contiguous()
+        near, far = near.contiguous().float(), far.contiguous().float()
+        tstep = time_step.reshape(-1)[:1].contiguous().float()
+        prec_s, prec_c = sdf_net.precision, col_net.precision
+        d_feat = sdf_net._dims_out[-1] - 1
+
+        pts = _f32(P, 4, device=dev)
+        dists, mid_z = _f32(N, S, device=dev), _f32(N, S, device=dev)
+        L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
+               n_coarse, N, S, 1, L.ptr(pts), L.ptr(dists), L.ptr(mid_z), s)
+
+        sdf, feat, grad = _f32(P, 1, device=dev), _f32(P, d_feat, device=dev), _f32(P, 4, device=dev)
+        sdf_saved = _f32(L.query("cope_sdf_saved_floats", sdf_net.desc, P, 1, prec_s), device=dev)
+        ws = L.scratch(max(L.query("cope_sdf_ws_floats", sdf_net.desc, P, prec_s),
+                           L.query("cope_color_ws_floats", col_net.desc, P, prec_c)), dev)
+        L.call("cope_sdf_fwd", sdf_net.desc, L.ptr(sdf_flat), L.ptr(pts), P, L.ptr(sdf), 1, L.ptr(feat), d_feat,
+               L.ptr(grad), L.ptr(sdf_saved), L.ptr(ws), prec_s, s)
+
+        rgb = _f32(P, 3, device=dev)
+        col_saved = _f32(L.query("cope_color_saved_floats", col_net.desc, P, prec_c), device=dev)
+        L.call("cope_color_fwd", col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S, col_net.multires_view,
+               L.ptr(grad), L.ptr(feat), d_feat, P, L.ptr(rgb), L.ptr(col_saved), L.ptr(ws), prec_c, s)
+
+        weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
+        color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
+        wsum, wmax, inv_s = _f32(N, 1, device=dev), _f32(N, 1, device=dev), _f32(1, device=dev)
+        L.call("cope_composite_fwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
+               L.ptr(rays_d_norm), L.ptr(variance), float(cos_anneal), int(eval_mode), N, S, L.ptr(weights),
+               L.ptr(color), L.ptr(depth), L.ptr(wz), L.ptr(cdf), L.ptr(wsum), L.ptr(wmax), L.ptr(inv_s), s)
+
+        ctx.rnd, ctx.cfg = rnd, (N, S, n_coarse, float(cos_anneal), int(eval_mode))
+        ctx.save_for_backward(sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb,
+                              sdf_saved, col_saved)
+        normals = grad[:, :3].reshape(N, S, 3).contiguous()
+        flows = grad[:, 3:].clone().reshape(N, S, 1)
+        points = pts[:, :3].reshape(N, S, 3).contiguous()
+        ctx.mark_non_differentiable(wz, cdf, wsum, wmax, inv_s, dists, mid_z)
+        return color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z
+
+    @staticmethod
+    def backward(ctx, d_color, d_depth, d_normals, d_flows, d_weights, d_sdf_up, d_points, *unused):
+        (sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb, sdf_saved,
+         col_saved) = ctx.saved_tensors
+        rnd = ctx.rnd
+        sdf_net, col_net = rnd.sdf_network, rnd.color_network
+        N, S, n_coarse, cos_anneal, eval_mode = ctx.cfg
+        P, dev, s = N * S, z.device, L.stream()
+        prec_s, prec_c = sdf_net.precision, col_net.precision
+        d_feat_w = sdf_net._dims_out[-1] - 1
+        need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+
+        # upstream of the analytic gradient (normals | sdf_flow), accumulated into by compositing + colour net
+        d_grad = torch.zeros(P, 4, dtype=torch.float32, device=dev)
+        if d_normals is not None:
+            d_grad[:, :3] = d_normals.reshape(P, 3)
+        if d_flows is not None:
+            d_grad[:, 3:] = d_flows.reshape(P, 1)
+        d_sdf, d_rgb = _f32(P, 1, device=dev), _f32(P, 3, device=dev)
+        d_var = torch.zeros(1, dtype=torch.float32, device=dev)
+        d_rays_d = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+        cg = lambda t: L.ptr(t.contiguous()) if t is not None else None
+        L.call("cope_composite_bwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
+               L.ptr(rays_d_norm), L.ptr(variance), cos_anneal, eval_mode, N, S, cg(d_color),
+               cg(d_depth), cg(d_weights), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb), L.ptr(d_var), L.ptr(d_rays_d), s)
+        if d_sdf_up is not None:
+            d_sdf = d_sdf + d_sdf_up.reshape(P, 1)
+
+        ws = L.scratch(max(L.query("cope_sdf_ws_floats", sdf_net.desc, P, prec_s),
+                           L.query("cope_color_ws_floats", col_net.desc, P, prec_c)), dev)
+        d_col_flat = torch.zeros_like(col_flat)
+        d_sdf_flat = torch.zeros_like(sdf_flat)
+        d_feat = _f32(P, d_feat_w, device=dev)
+        d_pts = d_dirs_pp = None
+        if need_rays:
+            d_pts = torch.zeros(P, 4, dtype=torch.float32, device=dev)
+            if d_points is not None:
+                d_pts[:, :3] = d_points.reshape(P, 3)
+            d_dirs_pp = _f32(P, 3, device=dev)
+        L.call("cope_color_bwd", col_net.desc, L.ptr(col_flat), L.ptr(rays_d), S, col_net.multires_view, P,
+               L.ptr(col_saved), L.ptr(d_rgb), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(d_grad),
+               L.ptr(d_feat), d_feat_w, L.ptr(ws), prec_c, s)
+        L.call("cope_sdf_bwd", sdf_net.desc, L.ptr(sdf_flat), L.ptr(pts), P, L.ptr(sdf_saved), L.ptr(d_sdf), 1,
+               L.ptr(d_feat), d_feat_w, L.ptr(d_grad), L.ptr(d_sdf_flat), L.ptr(d_pts), 1, L.ptr(ws), prec_s, s)
+        d_rays_o = None
+        if need_rays:
+            d_rays_o = _f32(N, 3, device=dev)
+            L.call("cope_ray_points_bwd", L.ptr(d_pts), L.ptr(mid_z), L.ptr(d_dirs_pp), N, S, L.ptr(d_rays_o),
+                   L.ptr(d_rays_d), s)
+        else:
+            d_rays_d = None
+        d_variance = d_var.reshape(variance.shape) if ctx.needs_input_grad[3] else None
+        return (None, d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d, None, None, None, None, None, None,
+                None, None)
+
+
+class NeuSRenderer(nn.Module):
+    """model/neus_renderer.py:107-584.  Constructor kwargs = the `neus_renderer` config section plus the five
+    networks, as train.py:46-52 passes them."""
+
+    def __init__(self, nerf, sdf_network, deviation_network, color_network, motion_network, n_samples, n_importance,
+                 n_outside, up_sample_steps, perturb, n_max_network_queries, importance_sampling_start, naive_render):
+        super().__init__()
+        self.nerf = nerf
+        self.sdf_network = sdf_network
+        self.deviation_network = deviation_network
+        self.color_network = color_network
+        self.motion_network = motion_network
+        self.n_samples = n_samples
+        self.n_importance = n_importance
+        self.n_outside = n_outside
+        self.up_sample_steps = up_sample_steps
+        self.perturb = perturb
+        self.n_max_network_queries = n_max_network_queries
+        self.importance_sampling_start = importance_sampling_start
+        self.naive_render = naive_render
+        if n_outside > 0 or naive_render:
+            raise NotImplementedError("n_outside > 0 / naive_render are dead paths at every shipped config "
+                                      "(configs/default.yaml:151,156) and are out of scope (SURVEY.md §8)")
+        self.t_rand_override = None     # tests inject the CPU-RNG jitter the reference would draw
+
+    # -- pieces, exposed for the parity tests ------------------------------------------------------------
+    def coarse_z(self, near, far, n_samples, t_rand):
+        n = near.shape[0]
+        z = _f32(n, n_samples, device=near.device)
+        L.call("cope_coarse_z", L.ptr(near.contiguous().float()), L.ptr(far.contiguous().float()), L.ptr(t_rand),
+               n, n_samples, L.ptr(z), L.stream())
+        return z
+
+    def _points(self, rays_o, rays_d, z, tstep, near, far):
+        n, s = z.shape
+        pts = _f32(n * s, 4, device=z.device)
+        L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
+               self.n_samples, n, s, 0, L.ptr(pts), None, None, L.stream())
+        return pts
+
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s, return_aux=False):
+        """model/neus_renderer.py:178-224."""
+        n, s = z_vals.shape
+        new_z = _f32(n, n_importance, device=z_vals.device)
+        cdf = _f32(n, s, device=z_vals.device) if return_aux else None
+        inds = torch.empty(n, n_importance, dtype=torch.int64, device=z_vals.device) if return_aux else None
+        L.call("cope_upsample", L.ptr(z_vals.contiguous()), L.ptr(sdf.reshape(n, s).contiguous()), n, s, n_importance,
+               float(inv_s), L.ptr(new_z), L.ptr(cdf), L.ptr(inds), L.stream())
+        return (new_z, cdf, inds) if return_aux else new_z
+
+    def merge_z(self, z_vals, new_z, sdf=None, new_sdf=None):
+        n, s = z_vals.shape
+        k = new_z.shape[1]
+        z_out = _f32(n, s + k, device=z_vals.device)
+        sdf_out = _f32(n, s + k, device=z_vals.device) if sdf is not None else None
+        L.call("cope_merge_z", L.ptr(z_vals.contiguous()), L.ptr(new_z.contiguous()),
+               L.ptr(sdf.contiguous()) if sdf is not None else None,
+               L.ptr(new_sdf.contiguous()) if new_sdf is not None else None, n, s, k, L.ptr(z_out), L.ptr(sdf_out),
+               L.stream())
+        return z_out, sdf_out
+
+    def cat_z_vals(self, rays_o, rays_d, time_step, z_vals, new_z_vals, sdf, last=False, sdf_flat=None):
+        """model/neus_renderer.py:282-298 (sorted merge instead of a full sort)."""
+        if last:
+            return self.merge_z(z_vals, new_z_vals)[0], sdf
+        n, k = new_z_vals.shape
+        flat = sdf_flat if sdf_flat is not None else self.sdf_network.flat_weights().detach()
+        tstep = time_step.reshape(-1)[:1].contiguous().float()
+        near = far = tstep   # unused when use_mid = 0
+        pts = self._points(rays_o.contiguous(), rays_d.contiguous(), new_z_vals, tstep, near, far)
+        new_sdf = self.sdf_network.query_flat(flat, pts).reshape(n, k)
+        return self.merge_z(z_vals, new_z_vals, sdf.reshape(z_vals.shape), new_sdf)
+
+    def sample_z(self, rays_o, rays_d, time_step, near, far, eval, sdf_flat, it=0):
+        """Coarse + hierarchical depths of model/neus_renderer.py:456-525 (no gradients)."""
+        n = rays_o.shape[0]
+        use_imp = it >= self.importance_sampling_start and self.n_importance > 0
+        n_samples = self.n_samples if use_imp else self.n_samples + self.n_importance
+        t_rand = None
+        if not eval:
+            t_rand = self.t_rand_override
+            if t_rand is None:
+                t_rand = torch.rand([n, n_samples])            # CPU generator, as neus_renderer.py:482
+            t_rand = t_rand.to(rays_o.device, torch.float32).contiguous()
+        with torch.no_grad():
+            tstep = time_step.reshape(-1)[:1].contiguous().float()
+            near_c, far_c = near.contiguous().float(), far.contiguous().float()
+            ro, rd = rays_o.detach().contiguous().float(), rays_d.detach().contiguous().float()
+            z = self.coarse_z(near_c, far_c, n_samples, t_rand)
+            if use_imp:
+                flat = sdf_flat.detach()
+                sdf = self.sdf_network.query_flat(flat, self._points(ro, rd, z, tstep, near_c, far_c)).reshape(n, n_samples)
+                k = self.n_importance // self.up_sample_steps
+                for i in range(self.up_sample_steps):
+                    new_z = self.up_sample(ro, rd, z, sdf, k, 64 * 2 ** i)
+                    z, sdf = self.cat_z_vals(ro, rd, tstep, z, new_z, sdf, last=(i + 1 == self.up_sample_steps),
+                                             sdf_flat=flat)
+        return z, n_samples
+
+    def forward(self, rays_o, rays_d, ray_d_norm, time_step, near, far, perturb_overwrite=-1, background_rgb=None,
+                cos_anneal_ratio=0.0, it=-1, eval=False):
+        if background_rgb is not None:
+            raise NotImplementedError("background_rgb is always None in the reference's callers")
+        n = len(rays_o)
+        sdf_flat = self.sdf_network.flat_weights()
+        col_flat = self.color_network.flat_weights()
+        z, n_coarse = self.sample_z(rays_o, rays_d, time_step, near, far, eval, sdf_flat, it)
+        (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
+            _RenderCoreFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
+                                time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
+        return {
+            'sdf': sdf,
+            'color_fine': color,
+            'depth_pred': depth,
+            'weighted_z_vals': wz,
+            's_val': (1.0 / inv_s).expand(n, 1).clone(),
+            'cdf_fine': cdf,
+            'weight_sum': wsum,
+            'weight_max': wmax,
+            'normals': normals,
+            'sdf_flows': flows,
+            'sampled_points': points,
+            'weights': weights,
+            'inside_sphere': torch.ones_like(weights),
+            'weight_inside': wsum.reshape(n).detach(),
+            'weight_outside': torch.zeros(n, dtype=torch.float32, device=weights.device),
+        }

@@ -1,0 +1,105 @@
+"""Step glue of the reference's `mdl.Trainer` that sits on the hot path (model/training.py:101-124, 413-487,
+490-558) plus the loss lines of train.py:472-477, 526 — restricted to what the NeuS render/train step needs.
+Everything here is thin host code over the CUDA kernels; dataset I/O, logging and visualisation are out of scope.
+"""
+import numpy as np
+import torch
+
+from .common import get_world_cameraOrigin_cameraRay, pixels_from_indices
+
+__all__ = ["near_far_from_sphere", "get_cos_anneal_ratio", "get_patch_indices", "sample_rays", "eikonal_loss",
+           "rgb_l1_loss", "sdf_flow_loss", "neus_losses", "render_train_step", "build_networks", "DEFAULT_CFG"]
+
+# configs/default.yaml:103-156
+DEFAULT_CFG = dict(
+    neus_sdf_network=dict(d_out=257, d_in=4, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                          geometric_init=True, weight_norm=True),
+    neus_variance_network=dict(init_val=0.3),
+    neus_rendering_network=dict(d_feature=256, mode="idr", d_in=11, d_out=3, d_hidden=256, n_layers=4,
+                                weight_norm=True, multires_view=4, squeeze_out=True, use_negative_ray_vector=False),
+    neus_renderer=dict(n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4, perturb=1.0,
+                       n_max_network_queries=64000, importance_sampling_start=0, naive_render=False),
+)
+
+
+def build_networks(cfg=None, device="cuda", precision=None):
+    """train.py:39-52 — construct the networks from config sections (same kwargs) and wrap them in NeuSRenderer."""
+    from .fields import SDFNetwork, RenderingNetwork, SingleVarianceNetwork
+    from .renderer import NeuSRenderer
+    cfg = cfg or DEFAULT_CFG
+    sdf = SDFNetwork(**cfg["neus_sdf_network"]).to(device)
+    var = SingleVarianceNetwork(**cfg["neus_variance_network"]).to(device)
+    col = RenderingNetwork(**cfg["neus_rendering_network"]).to(device)
+    if precision is not None:
+        sdf.precision = col.precision = precision
+    return NeuSRenderer(None, sdf, var, col, None, **cfg["neus_renderer"]).to(device)
+
+
+def near_far_from_sphere(rays_o, rays_d, depth_range):
+    """model/training.py:101-118: the sphere bounds are overwritten by the constant depth range."""
+    near = torch.full((rays_o.shape[0], 1), float(depth_range[0]), dtype=torch.float32, device=rays_o.device)
+    far = torch.full((rays_o.shape[0], 1), float(depth_range[1]), dtype=torch.float32, device=rays_o.device)
+    return near, far
+
+
+def get_cos_anneal_ratio(iter_step, anneal_end):
+    """model/training.py:120-124."""
+    return 1.0 if anneal_end == 0.0 else float(np.min([1.0, iter_step / anneal_end]))
+
+
+def get_patch_indices(h, w, patch_size, n_points):
+    """model/training.py:413-436 — CPU randperm of top-left corners, row-major pixel ids inside each patch."""
+    n_patches = n_points // (patch_size ** 2)
+    ha, wa = h - patch_size + 1, w - patch_size + 1
+    n_patches = min(n_patches, ha * wa)
+    corners = torch.randperm(ha * wa)[:n_patches]
+    rows, cols = corners // wa, corners % wa
+    off = torch.arange(patch_size).repeat(patch_size, 1)
+    off = (off + off.t() * w).flatten()
+    return ((rows * w + cols).unsqueeze(1) + off.view(-1)).flatten()
+
+
+def sample_rays(ray_idx, h, w, camera_mat, world_mat, scale_mat):
+    """process_data's ray part (model/training.py:439-471): pixel ids -> normalised pixels -> world rays."""
+    pix = pixels_from_indices(ray_idx.to(camera_mat.device), h, w)
+    return (pix,) + tuple(get_world_cameraOrigin_cameraRay(pix, camera_mat, world_mat, scale_mat))
+
+
+def eikonal_loss(normals):
+    """train.py:526."""
+    return torch.mean((torch.linalg.norm(normals.reshape(-1, 3), ord=2, dim=-1) - 1.0) ** 2)
+
+
+def rgb_l1_loss(rgb, rgb_gt):
+    """model/training.py:508."""
+    return torch.sum(torch.abs(rgb - rgb_gt)) / float(rgb.shape[0])
+
+
+def sdf_flow_loss(out, ang_vel, vel):
+    """train.py:467-477."""
+    pts = out["sampled_points"].reshape(-1, 3)
+    nrm = out["normals"].reshape(-1, 3)
+    fl = out["sdf_flows"].reshape(-1)
+    w = out["weights"].reshape(-1).detach()
+    flow = torch.linalg.cross(ang_vel.expand_as(pts), pts) + vel
+    return torch.sum(torch.abs(torch.sum(flow * nrm, dim=-1) + fl) * w) / (torch.sum(w) + 1e-10)
+
+
+def neus_losses(out, rgb_gt, rgb_weight=0.33333, eikonal_weight=0.1):
+    """compute_loss (model/training.py:490-549) restricted to the rgb + eikonal terms of BASELINE.json's metric."""
+    l_rgb = rgb_l1_loss(out["color_fine"], rgb_gt)
+    l_eik = eikonal_loss(out["normals"])
+    return rgb_weight * l_rgb + eikonal_weight * l_eik, dict(loss_rgb=l_rgb, loss_eikonal=l_eik)
+
+
+def render_train_step(renderer, pose, cam_id, pixels, camera_mat, scale_mat, rgb_gt, time_step, depth_range,
+                      cos_anneal_ratio=0.5, it=1, rgb_weight=0.33333, eikonal_weight=0.1, loss_scale=1.0):
+    """One training iteration without the optimiser: pose -> rays -> near/far -> NeuSRenderer.forward -> loss ->
+    backward (train.py:425-532 with the rgb + eikonal terms).  Returns (loss, outputs, rays)."""
+    world = pose(cam_id)
+    o, d, dn = get_world_cameraOrigin_cameraRay(pixels, camera_mat, world, scale_mat)
+    near, far = near_far_from_sphere(o, d, depth_range)
+    out = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=False)
+    loss, parts = neus_losses(out, rgb_gt, rgb_weight, eikonal_weight)
+    (loss * loss_scale).backward()
+    return loss.detach(), out, (o, d, dn)

@@ -1,0 +1,178 @@
+/*
+ * cope_b200.h — C ABI of libcope_b200.so: the B200 (sm_100a) kernels behind the cope-nerf NeuS
+ * render/train hot path.
+ *
+ * The reference (HoangChuongNguyen/cope-nerf) has NO native boundary: its hot path is eager PyTorch
+ * inside model/neus_renderer.py, model/neus_fields.py, model/neus_embedder.py, model/poses_retriever.py,
+ * model/common.py and model/training.py.  This ABI is therefore ours to define; each entry point names
+ * the reference lines it replaces.  The host side (cope_nerf_b200/*.py) keeps the reference's nn.Module
+ * API and calls these functions from torch.autograd.Function.forward/backward via ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; row-major, fp32, contiguous unless a stride is given
+ *   - the caller allocates every buffer (including workspaces, sized by the *_floats queries)
+ *   - the callee never allocates, frees or synchronises; all work is enqueued on `stream`
+ *   - return 0 on success, negative on error; cope_last_error() gives the text (thread-local)
+ *   - `cope_stream_t` is a cudaStream_t
+ */
+#ifndef COPE_B200_H
+#define COPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cope_stream_t;
+
+#define COPE_MAX_LIN 12
+
+/* precision of the MLP paths */
+#define COPE_PREC_FP32 0 /* fp32 SIMT GEMMs: strict-parity mode (<= 1e-3 rel vs the reference)          */
+#define COPE_PREC_BF16 1 /* bf16 tcgen05 tensor-core path, fp32 accumulate (cos-sim > 0.999 contract)    */
+
+/* Shape of a weight-normalised MLP (SDFNetwork / RenderingNetwork, model/neus_fields.py:205-374).
+ * Flat parameter layout (floats): for l in 0..n_lin-1: W_l [dims_out[l] x dims_in[l]] row-major, then
+ * b_l [dims_out[l]].  Gradients use the same layout. */
+typedef struct {
+  int32_t n_lin;                 /* number of linear layers: 9 (SDF) or 5 (colour)                       */
+  int32_t d_in;                  /* raw input width before PE: 4 = (x,y,z,t)                              */
+  int32_t multires;              /* PE frequencies L (6 for SDF); PE width = d_in*(1+2L)                  */
+  int32_t skip_layer;            /* layer whose input is cat([h, pe])/sqrt(2) (4 for SDF), -1 = none     */
+  int32_t dims_in[COPE_MAX_LIN]; /* K of each layer                                                      */
+  int32_t dims_out[COPE_MAX_LIN];/* N of each layer (layer skip_layer-1 emits dims_in[skip]-pe_width)    */
+} cope_mlp_desc;
+
+int cope_version(void);
+const char* cope_last_error(void);
+/* kernels launched by this library since load (monotonic; bench.py reports the per-run delta) */
+uint64_t cope_launch_count(void);
+/* number of floats in the flat [W_l | b_l]* buffer of an MLP */
+int64_t cope_mlp_flat_floats(const cope_mlp_desc* d);
+
+/* ---- weight norm: W = g * v / ||v||_row  (nn.utils.weight_norm, model/neus_fields.py:261-262,339-340) */
+int cope_weightnorm_fwd(const float* v, const float* g, float* W, int rows, int cols, cope_stream_t s);
+/* dv, dg are OVERWRITTEN */
+int cope_weightnorm_bwd(const float* v, const float* g, const float* dW, float* dv, float* dg, int rows,
+                        int cols, cope_stream_t s);
+
+/* ---- positional encoding (model/neus_embedder.py:6-51): out [P x d*(1+2L)] */
+int cope_embed_fwd(const float* x, int64_t P, int d, int L, float* out, cope_stream_t s);
+
+/* ---- SDF network (model/neus_fields.py:268-303) --------------------------------------------------- */
+/* floats of `saved` needed by cope_sdf_fwd (with_grad: also keeps the reverse-sweep deltas) */
+int64_t cope_sdf_saved_floats(const cope_mlp_desc* d, int64_t P, int with_grad, int prec);
+/* floats of scratch workspace needed by query / fwd / bwd */
+int64_t cope_sdf_ws_floats(const cope_mlp_desc* d, int64_t P, int prec);
+
+/* sdf only, no state kept: SDFNetwork.sdf under no_grad (neus_renderer.py:499, :292). sdf_out [P] */
+int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, int64_t P, float* sdf_out,
+                   float* ws, int prec, cope_stream_t s);
+/* SDFNetwork.forward(x): column 0 -> sdf (row stride sdf_ld), columns 1.. -> feat (row stride feat_ld); for one
+ * [P x d_out] tensor y pass (y, d_out, y+1, d_out).  grad [P x d_in] = SDFNetwork.gradient(x) (analytic reverse
+ * sweep, replaces the autograd.grad of neus_fields.py:291-303) or NULL.  `saved` keeps activations for bwd. */
+int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld,
+                 float* feat, int feat_ld, float* grad, float* saved, float* ws, int prec, cope_stream_t s);
+/* Backward of both outputs.  Upstream of forward(): d_sdf (row stride d_sdf_ld) and d_feat (row stride d_feat_ld),
+ * either may be NULL (= zero); dgrad [P x d_in] or NULL (second-order path: the double backward that the eikonal
+ * loss / colour-net normals need).  dWflat is ACCUMULATED into.
+ * dx [P x d_in] or NULL receives (ACCUMULATED if dx_accumulate) the gradient w.r.t. x THROUGH THE VALUE PATH ONLY,
+ * matching render_core where .gradient() sees pts_time.detach() (neus_renderer.py:352-356). */
+int cope_sdf_bwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int64_t P, const float* saved,
+                 const float* d_sdf, int d_sdf_ld, const float* d_feat, int d_feat_ld, const float* dgrad,
+                 float* dWflat, float* dx, int dx_accumulate, float* ws, int prec, cope_stream_t s);
+
+/* ---- colour network (model/neus_fields.py:346-374, mode 'idr') ------------------------------------ */
+int64_t cope_color_saved_floats(const cope_mlp_desc* d, int64_t P, int prec);
+int64_t cope_color_ws_floats(const cope_mlp_desc* d, int64_t P, int prec);
+/* input = cat[x(4) | PE_Lv(dirs)(3+6Lv) | normals(4) | feat(d_feat)].  dirs is [P/dirs_group x 3]: one
+ * direction per `dirs_group` consecutive points (= samples per ray; 1 for per-point dirs).
+ * feat has row stride feat_ld (257 when it aliases y[:,1:]).  rgb [P x 3] (sigmoid applied). */
+int cope_color_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, const float* dirs,
+                   int dirs_group, int Lv, const float* normals, const float* feat, int feat_ld, int64_t P,
+                   float* rgb, float* saved, float* ws, int prec, cope_stream_t s);
+/* d_rgb [P x 3].  Outputs (any may be NULL): dx [P x 4] ACCUMULATED, ddirs [P x 3] per point OVERWRITTEN,
+ * dnormals [P x 4] ACCUMULATED, dfeat (row stride dfeat_ld) OVERWRITTEN.  dWflat ACCUMULATED. */
+int cope_color_bwd(const cope_mlp_desc* d, const float* Wflat, const float* dirs, int dirs_group, int Lv,
+                   int64_t P, const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs,
+                   float* dnormals, float* dfeat, int dfeat_ld, float* ws, int prec, cope_stream_t s);
+
+/* ---- ray points (neus_renderer.py:337-350 / :495-498 / :285) --------------------------------------
+ * pts_time [N*S x 4] = (o + d * zz, t) with zz = z + dists/2 if use_mid else z.
+ * dists / mid_z [N x S] may be NULL.  The last interval is sample_dist = (far[0]-near[0])/n_coarse,
+ * read on the device (near/far are device pointers; no host sync). */
+int cope_ray_points(const float* rays_o, const float* rays_d, const float* z, const float* time_step,
+                    const float* near, const float* far, int n_coarse, int64_t N, int S, int use_mid,
+                    float* pts_time, float* dists, float* mid_z, cope_stream_t s);
+/* d_pts [N*S x 4] -> d_rays_o [N x 3] (overwritten), d_rays_d [N x 3] (ACCUMULATED: compositing adds the
+ * true_cos term first).  d_dirs_pp [N*S x 3] or NULL: per-point view-direction gradients (colour net) summed
+ * per ray into d_rays_d. */
+int cope_ray_points_bwd(const float* d_pts, const float* mid_z, const float* d_dirs_pp, int64_t N, int S,
+                        float* d_rays_o, float* d_rays_d, cope_stream_t s);
+/* coarse stratified depths (neus_renderer.py:466-483): t_rand [N x S] or NULL (eval) */
+int cope_coarse_z(const float* near, const float* far, const float* t_rand, int64_t N, int S, float* z,
+                  cope_stream_t s);
+
+/* ---- hierarchical sampling ----------------------------------------------------------------------- */
+/* sample_pdf's inverse-CDF step given a CDF (neus_renderer.py:47-70, det=True): bit-exact contract.
+ * cdf, bins [N x S]; out samples [N x K], inds int64 [N x K] (searchsorted right=True) or NULL */
+int cope_sample_cdf(const float* cdf, const float* bins, int64_t N, int S, int K, float* samples,
+                    int64_t* inds, cope_stream_t s);
+/* up_sample (neus_renderer.py:178-224) incl. sample_pdf: z, sdf [N x S] -> new_z [N x K].
+ * Optional debug outputs: cdf [N x S], inds [N x K]. */
+int cope_upsample(const float* z, const float* sdf, int64_t N, int S, int K, float inv_s, float* new_z,
+                  float* cdf_out, int64_t* inds_out, cope_stream_t s);
+/* cat_z_vals without the MLP query (neus_renderer.py:286-297): merge sorted z [N x S] with new_z [N x K];
+ * sdf/new_sdf may be NULL (last step).  Ties: old before new. */
+int cope_merge_z(const float* z, const float* new_z, const float* sdf, const float* new_sdf, int64_t N, int S,
+                 int K, float* z_out, float* sdf_out, cope_stream_t s);
+
+/* ---- compositing (neus_renderer.py:360-420, :565-575) --------------------------------------------- */
+/* Inputs per sample: sdf [P], grad [P x 4] (normal = first 3), rgb [P x 3], z/dists [N x S]; per ray: rays_d
+ * [N x 3], rays_d_norm [N] (used only if eval_mode).  variance: device scalar (SingleVarianceNetwork).
+ * Outputs: weights [N x S], color [N x 3], depth [N] (divided by |d| if eval), weighted_z [N] (never divided),
+ * cdf [N x S] (prev_cdf, logging), wsum [N], wmax [N],
+ * inv_s_out [1]. */
+int cope_composite_fwd(const float* sdf, const float* grad, const float* rgb, const float* z,
+                       const float* dists, const float* rays_d, const float* rays_d_norm,
+                       const float* variance, float cos_anneal, int eval_mode, int64_t N, int S,
+                       float* weights, float* color, float* depth, float* weighted_z, float* cdf, float* wsum,
+                       float* wmax, float* inv_s_out, cope_stream_t s);
+/* Upstream: d_color [N x 3], d_depth [N], d_weights [N x S] (any may be NULL = zero).
+ * Outputs: d_sdf [P] OVERWRITTEN, d_grad [P x 4] ACCUMULATED (caller pre-fills with the upstream grads of
+ * `normals` / `sdf_flows`), d_rgb [P x 3] OVERWRITTEN, d_variance [1] ACCUMULATED,
+ * d_rays_d [N x 3] OVERWRITTEN (the true_cos term). */
+int cope_composite_bwd(const float* sdf, const float* grad, const float* rgb, const float* z,
+                       const float* dists, const float* rays_d, const float* rays_d_norm,
+                       const float* variance, float cos_anneal, int eval_mode, int64_t N, int S,
+                       const float* d_color, const float* d_depth,
+                       const float* d_weights, float* d_sdf, float* d_grad, float* d_rgb, float* d_variance,
+                       float* d_rays_d, cope_stream_t s);
+
+/* ---- pose + ray generation (poses_retriever.py:25-32, common.py:175-215,255-308, training.py:474-487) */
+/* c2w [4x4] = make_c2w(r, t) @ init_c2w   (r, t, init_c2w: device pointers to one camera's entries) */
+int cope_pose_fwd(const float* r, const float* t, const float* init_c2w, float* c2w, cope_stream_t s);
+int cope_pose_bwd(const float* r, const float* t, const float* init_c2w, const float* d_c2w, float* dr,
+                  float* dt, cope_stream_t s);
+/* rays from normalised pixels [N x 2]: M = inv(scale) inv(world) inv(camera); o = M[:,3], d = normalise(M p - o)
+ * outputs rays_o [N x 3], rays_d [N x 3], rays_d_norm [N] */
+int cope_raygen_fwd(const float* pixels, const float* camera_mat, const float* world_mat,
+                    const float* scale_mat, int64_t N, float* rays_o, float* rays_d, float* rays_d_norm,
+                    cope_stream_t s);
+/* d_world [4x4] OVERWRITTEN with dL/d world_mat given d_rays_o, d_rays_d (d_norm may be NULL) */
+int cope_raygen_bwd(const float* pixels, const float* camera_mat, const float* world_mat,
+                    const float* scale_mat, int64_t N, const float* d_rays_o, const float* d_rays_d,
+                    const float* d_norm, float* d_world, float* ws /* >= 16 floats, zeroed by callee */,
+                    cope_stream_t s);
+
+/* ---- generic fp32 GEMM (used by the tests to exercise the kernel directly) ------------------------
+ * C[M x N] (+)= op(A) op(B); transA: A stored [K x M]; transB: B stored [N x K] */
+int cope_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+               float* C, int ldc, int accumulate, cope_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COPE_B200_H */

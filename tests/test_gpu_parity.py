@@ -1,0 +1,347 @@
+"""GPU parity: every kernel of libcope_b200 (through the Python module API -> ctypes C-ABI) against the CPU oracle
+and the committed golden vectors.  Tolerances follow BASELINE.json north_star: integer outputs bit-exact, floats
+<= 1e-3 relative for the fp32 path."""
+import numpy as np
+import pytest
+import torch
+
+import cope_nerf_b200 as C
+import oracle as O
+from cope_nerf_b200 import _lib as L
+from conftest import assert_close, cos_sim, load_golden, rel_err, unflatten
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+KEYS = ["sdf", "color_fine", "depth_pred", "weighted_z_vals", "s_val", "cdf_fine", "weight_sum", "weight_max",
+        "normals", "sdf_flows", "sampled_points", "weights", "inside_sphere", "weight_inside", "weight_outside"]
+
+SMALL_CFG = dict(
+    neus_sdf_network=dict(d_out=65, d_in=4, d_hidden=64, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                          geometric_init=True, weight_norm=True),
+    neus_variance_network=dict(init_val=0.3),
+    neus_rendering_network=dict(d_feature=64, mode="idr", d_in=11, d_out=3, d_hidden=64, n_layers=4, weight_norm=True,
+                                multires_view=4, squeeze_out=True, use_negative_ray_vector=False),
+    neus_renderer=C.training.DEFAULT_CFG["neus_renderer"],
+)
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def renderer_from(params, cfg):
+    r = C.training.build_networks(cfg, device=DEV)
+    r.sdf_network.load_state_dict(params["sdf"])
+    r.color_network.load_state_dict(params["color"])
+    r.deviation_network.load_state_dict(params["variance"])
+    return r
+
+
+def full_params(seed=678, perturb=0.0):
+    torch.manual_seed(seed)
+    P = dict(sdf=O.init_sdf_params(**O.DEFAULT_CFG["sdf"]), color=O.init_color_params(**O.DEFAULT_CFG["color"]),
+             variance=O.init_variance_params(**O.DEFAULT_CFG["variance"]))
+    if perturb:
+        for k in ("sdf", "color"):
+            for n, v in P[k].items():
+                v.add_(perturb * torch.randn_like(v))
+    return P
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(300, 257, 52), (129, 204, 291), (1, 3, 1000), (256, 256, 4099)])
+def test_sgemm(ta, tb, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), device=DEV)
+    B = torch.randn((N, K) if tb else (K, N), device=DEV)
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+    out = torch.zeros(M, N, device=DEV)
+    L.call("cope_sgemm", ta, tb, M, N, K, L.ptr(A), A.shape[1], L.ptr(B), B.shape[1], L.ptr(out), N, 0, L.stream())
+    assert rel_err(out, ref) < 1e-5
+    out2 = torch.ones(M, N, device=DEV)
+    L.call("cope_sgemm", ta, tb, M, N, K, L.ptr(A), A.shape[1], L.ptr(B), B.shape[1], L.ptr(out2), N, 1, L.stream())
+    assert rel_err(out2, ref + 1) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ primitives
+def test_embedder():
+    g = load_golden("embed")
+    f6, d6 = C.get_embedder(6, input_dims=4)
+    f4, d4 = C.get_embedder(4)
+    assert (d6, d4) == (52, 27)
+    assert_close(f6(cu(g["x4"])), g["e6"], 2e-6, "embed6")
+    assert_close(f4(cu(g["x3"])), g["e4"], 2e-6, "embed4")
+    x = torch.randn(5000, 4) * 3
+    assert_close(f6(cu(x)), O.embed(x, 6), 1e-5, "embed big")    # 2^5 * 3-sigma arguments: range reduction
+
+
+def test_weightnorm_fwd_bwd():
+    torch.manual_seed(2)
+    net = C.SDFNetwork(**C.training.DEFAULT_CFG["neus_sdf_network"]).to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    flat = net.flat_weights()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    ref = torch.cat([torch.cat([O.wn_weight(sd, l).reshape(-1), sd[f"lin{l}.bias"]]) for l in range(9)])
+    assert_close(flat, ref, 1e-6, "flat weights")
+    w = torch.randn_like(ref)
+    (flat * cu(w)).sum().backward()
+    (ref * w).sum().backward()
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad, sd[k].grad) < 1e-5, k
+
+
+def test_pose_and_raygen_golden():
+    g = load_golden("poses_rays")
+    pr = C.PoseRetriever(3).to(DEV)
+    pr.load_state_dict({k: g[k] for k in ("r", "t", "init_c2w")})
+    for cam in range(3):
+        assert_close(pr(cam), g[f"c2w{cam}"], 1e-6, f"c2w{cam}")
+    S = torch.eye(4, device=DEV).unsqueeze(0)
+    o, d, n = C.get_world_cameraOrigin_cameraRay(cu(g["pix"]), cu(g["K"]), pr(2), S)
+    assert_close(o, g["ray_o2"], 1e-5); assert_close(d, g["ray_d2"], 1e-5); assert_close(n, g["ray_n2"], 1e-5)
+    o, d, n = C.get_world_cameraOrigin_cameraRay(cu(g["pix"]), cu(g["K"]), pr(1), S)
+    ((o * cu(g["wgt_o"])).sum() + (d * cu(g["wgt_d"])).sum()).backward()
+    assert rel_err(pr.r.grad, g["dr1"]) < 1e-3 and rel_err(pr.t.grad, g["dt1"]) < 1e-3
+    # r = 0: R = I exactly, and the sub-gradient torch uses at ||r|| = 0
+    r0 = torch.zeros(3, device=DEV, requires_grad=True)
+    t0 = torch.zeros(3, device=DEV, requires_grad=True)
+    c = C.make_c2w(r0, t0)
+    assert torch.equal(c.cpu(), torch.eye(4))
+    (c * torch.arange(16., device=DEV).reshape(4, 4)).sum().backward()
+    assert_close(r0.grad, torch.tensor([3., -6., 3.]), 1e-6); assert_close(t0.grad, torch.tensor([3., 7., 11.]), 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ fields
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_sdf_forward_gradient_color(which, small_params):
+    if which == "small":
+        g, P, cfg = load_golden("small_fields"), small_params, SMALL_CFG
+    else:
+        g, P, cfg = load_golden("full_fields_seed678"), full_params(), C.training.DEFAULT_CFG
+    r = renderer_from(P, cfg)
+    x, dirs = cu(g["x"]), cu(g["dirs"])
+    y = r.sdf_network(x)
+    grad = r.sdf_network.gradient(x).squeeze(1)
+    assert_close(y, g["y"], 2e-5, "y")
+    assert_close(grad, g["grad"], 1e-4, "grad")
+    assert_close(r.sdf_network.sdf(x), g["y"][:, :1], 2e-5, "sdf()")
+    with torch.no_grad():
+        assert_close(r.sdf_network.sdf(x), g["y"][:, :1], 2e-5, "sdf() no_grad query path")
+    rgb = r.color_network(x, grad.detach(), dirs, y[:, 1:].detach())
+    assert_close(rgb, g["rgb"], 2e-5, "rgb")
+    if which == "small":   # eikonal double backward (second order) against the reference's autograd
+        (r.sdf_network.gradient(x).squeeze(1)[:, :3].norm(dim=-1) - 1).pow(2).mean().backward()
+        for k, p in r.sdf_network.named_parameters():
+            got = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert_close(got, g[f"eik.{k}"], 1e-4, f"eik.{k}")
+            if g[f"eik.{k}"].abs().max() > 0:
+                assert rel_err(got, g[f"eik.{k}"]) < 1e-3, k
+
+
+def test_sdf_and_color_backward_vs_oracle_full_size():
+    """First + second order parameter gradients and dx of the full-size nets on 777 points."""
+    P = full_params(perturb=0.02)
+    r = renderer_from(P, C.training.DEFAULT_CFG)
+    torch.manual_seed(3)
+    n = 777
+    x = torch.cat([torch.randn(n, 3) * 0.6, torch.full((n, 1), -0.3)], -1)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    wy, wg, wc = torch.randn(n, 257) * 0.1, torch.randn(n, 4), torch.randn(n, 3)
+    # oracle
+    Pg = {t: {k: v.clone().requires_grad_(True) for k, v in P[t].items()} for t in ("sdf", "color")}
+    xo = x.clone().requires_grad_(True)
+    yo = O.sdf_forward(Pg["sdf"], xo)
+    go = O.sdf_gradient(Pg["sdf"], x.clone()).squeeze(1)
+    co = O.color_forward(Pg["color"], xo, go, dirs, yo[:, 1:])
+    ((yo * wy).sum() + (go * wg).sum() + (co * wc).sum()).backward()
+    # ours
+    xc = cu(x).requires_grad_(True)
+    flat = r.sdf_network.flat_weights()
+    y, g = r.sdf_network.apply_flat(flat, xc, True)
+    c = r.color_network(xc, g, cu(dirs), y[:, 1:])
+    ((y * cu(wy)).sum() + (g * cu(wg)).sum() + (c * cu(wc)).sum()).backward()
+    assert_close(y, yo, 1e-4); assert_close(g, go, 1e-4); assert_close(c, co, 1e-4)
+    for tag, net in (("sdf", r.sdf_network), ("color", r.color_network)):
+        for k, p in net.named_parameters():
+            assert rel_err(p.grad, Pg[tag][k].grad) < 1e-3, (tag, k, rel_err(p.grad, Pg[tag][k].grad))
+    assert rel_err(xc.grad, xo.grad) < 1e-3      # value-path-only dx (gradient path saw x.detach())
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+def test_sample_cdf_bit_exact_given_reference_cdf():
+    g = load_golden("sample_pdf")
+    smp, inds = C.renderer.sample_cdf(cu(g["cdf"]), cu(g["bins"]), 16, return_inds=True)
+    assert inds.dtype == torch.int64 and torch.equal(inds.cpu(), g["inds"])
+    assert torch.equal(smp.cpu(), g["samples"])
+    u = load_golden("up_sample")
+    for S in (64, 80, 96, 112):
+        smp, inds = C.renderer.sample_cdf(cu(u[f"cdf{S}"]), cu(u[f"z{S}"]), 16, return_inds=True)
+        assert torch.equal(inds.cpu(), u[f"inds{S}"]), S
+        assert torch.equal(smp.cpu(), u[f"new_z{S}"]), S
+    # larger random case against torch.searchsorted on the same CDF
+    torch.manual_seed(1)
+    w = torch.rand(4096, 127) ** 8
+    bins = torch.sort(torch.rand(4096, 128) * 5, dim=-1)[0]
+    cdf = O.cdf_from_weights(w)
+    want, want_i = O.search_cdf(cdf, bins, 16)
+    smp, inds = C.renderer.sample_cdf(cu(cdf), cu(bins), 16, return_inds=True)
+    assert torch.equal(inds.cpu(), want_i) and torch.equal(smp.cpu(), want)
+
+
+def test_up_sample_and_merge(small_params):
+    u = load_golden("up_sample")
+    r = renderer_from(small_params, SMALL_CFG)
+    ro, rd = cu(u["rays_o"]), cu(u["rays_d"])
+    for S, inv_s in ((64, 64), (80, 128), (96, 256), (112, 512)):
+        nz, cdf, inds = r.up_sample(ro, rd, cu(u[f"z{S}"]), cu(u[f"sdf{S}"]), 16, inv_s, return_aux=True)
+        assert_close(cdf, u[f"cdf{S}"], 2e-6, f"cdf{S}")
+        assert (inds.cpu() != u[f"inds{S}"]).float().mean() < 0.02, "indices may only differ at 1-ulp CDF ties"
+        assert_close(nz, u[f"new_z{S}"], 2e-5, f"new_z{S}")
+    z2, s2 = r.cat_z_vals(ro, rd, cu(u["t"]), cu(u["z64"]), cu(u["new_z64"]), cu(u["sdf64"]), last=False)
+    assert torch.equal(z2.cpu(), u["cat_z"])
+    assert_close(s2, u["cat_sdf"], 2e-5, "cat sdf")
+    z3, _ = r.cat_z_vals(ro, rd, cu(u["t"]), cu(u["z64"]), cu(u["new_z64"]), cu(u["sdf64"]), last=True)
+    assert torch.equal(z3.cpu(), u["cat_z"])
+    # merge == sort on ragged sizes incl. ties (old before new) and unsorted new samples
+    torch.manual_seed(5)
+    for S, K in ((64, 16), (97, 7), (128, 64), (1, 1)):
+        z = torch.sort(torch.rand(333, S), dim=-1)[0]
+        nz = torch.rand(333, K)
+        nz[:, 0] = z[:, S // 2]                    # exact tie
+        a, b = torch.randn(333, S), torch.randn(333, K)
+        zo, so = r.merge_z(cu(z), cu(nz), cu(a), cu(b))
+        zs, idx = torch.sort(torch.cat([z, nz], -1), dim=-1, stable=True)
+        assert torch.equal(zo.cpu(), zs)
+        assert torch.equal(so.cpu(), torch.gather(torch.cat([a, b], -1), 1, idx))
+
+
+def test_coarse_z_matches_reference_bits():
+    near, far = torch.full((7, 1), 0.01), torch.full((7, 1), 5.0)
+    r = C.training.build_networks(SMALL_CFG, device=DEV)
+    for S in (64, 128):
+        t_rand = torch.rand(7, S)
+        assert torch.equal(r.coarse_z(cu(near), cu(far), S, None).cpu(), O.coarse_z(near, far, S, None))
+        assert_close(r.coarse_z(cu(near), cu(far), S, cu(t_rand)), O.coarse_z(near, far, S, t_rand), 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ renderer
+def test_renderer_forward_golden(small_params):
+    g = load_golden("render_small")
+    r = renderer_from(small_params, SMALL_CFG)
+    a = [cu(g[k]) for k in ("rays_o", "rays_d", "rays_d_norm", "t", "near", "far")]
+    out = r(*a, cos_anneal_ratio=0.5, it=1, eval=True)
+    assert list(out.keys()) == KEYS
+    for k in KEYS:
+        assert_close(out[k], g[f"eval.{k}"], 1e-4, f"eval.{k}")
+    r.t_rand_override = g["t_rand"]
+    out = r(*a, cos_anneal_ratio=0.3, it=1, eval=False)
+    for k in KEYS:
+        assert_close(out[k], g[f"train.{k}"], 1e-4, f"train.{k}")
+    torch.manual_seed(77)            # the CPU-generator jitter the reference would draw (neus_renderer.py:482)
+    r.t_rand_override = None
+    out = r(*a, cos_anneal_ratio=0.3, it=1, eval=False)
+    assert_close(out["color_fine"], g["train.color_fine"], 1e-4)
+
+
+def _run_step(r, pose, g, K, depth_range=(0.01, 5.0)):
+    r.t_rand_override = g["t_rand"]
+    loss, out, rays = C.training.render_train_step(r, pose, 0, cu(g["pix"]), K, torch.eye(4, device=DEV).unsqueeze(0),
+                                                   cu(g["rgb_gt"]), cu(g["t"]), depth_range, cos_anneal_ratio=0.5)
+    return loss, out
+
+
+def test_full_step_gradients_golden(small_params):
+    """One whole training iteration (pose -> rays -> sampling -> render -> rgb + eikonal -> backward): every
+    parameter gradient against the reference's autograd (fixture from the imported reference)."""
+    g = load_golden("step_small")
+    r = renderer_from(small_params, SMALL_CFG)
+    pose = C.PoseRetriever(1).to(DEV)
+    with torch.no_grad():
+        pose.r.copy_(g["r"]); pose.t.copy_(g["tr"])
+    K = cu(O.camera_matrix(0.8 * 80, 0.8 * 80, 80, 60).unsqueeze(0))
+    loss, out = _run_step(r, pose, g, K)
+    assert_close(loss, g["loss"], 1e-5, "loss")
+    assert_close(out["color_fine"], g["color"], 1e-4); assert_close(out["depth_pred"], g["depth"], 1e-4)
+    worst = 0.0
+    for tag, net in (("sdf", r.sdf_network), ("color", r.color_network), ("variance", r.deviation_network)):
+        for k, p in net.named_parameters():
+            e = rel_err(p.grad, g[f"grad.{tag}.{k}"])
+            worst = max(worst, e)
+            assert e < 1e-3, (tag, k, e)
+    assert rel_err(pose.r.grad, g["dr"]) < 1e-3 and rel_err(pose.t.grad, g["dt"]) < 1e-3
+
+
+def test_full_size_step_vs_oracle():
+    """Full-size networks (8x256 SDF, 4x256 colour), 48 rays x 64+64 samples, against the CPU oracle."""
+    P = full_params(perturb=0.01)
+    r = renderer_from(P, C.training.DEFAULT_CFG)
+    torch.manual_seed(21)
+    n = 48
+    g = dict(pix=(torch.rand(1, n, 2) * 2 - 1) * 0.8, rgb_gt=torch.rand(n, 3), t=torch.tensor([0.1]),
+             t_rand=torch.rand(n, 64))
+    r0, t0 = torch.randn(1, 3) * 0.05, torch.randn(1, 3) * 0.05
+    Kc = O.camera_matrix(0.8 * 1275, 0.8 * 1275, 1275, 717).unsqueeze(0)
+    Pg = {t: {k: v.clone().requires_grad_(True) for k, v in P[t].items()} for t in P}
+    po = dict(r=r0.clone().requires_grad_(True), t=t0.clone().requires_grad_(True), init_c2w=torch.eye(4).unsqueeze(0))
+    lo, aux = O.train_step(Pg, po, g["pix"], Kc, torch.eye(4).unsqueeze(0), g["rgb_gt"], g["t"], [0.01, 5.0],
+                           cos_anneal=0.5, t_rand=g["t_rand"])
+    lo.backward()
+    pose = C.PoseRetriever(1).to(DEV)
+    with torch.no_grad():
+        pose.r.copy_(r0); pose.t.copy_(t0)
+    loss, out = _run_step(r, pose, g, cu(Kc))
+    assert_close(out["color_fine"], aux["out"]["color_fine"], 1e-3, "rgb")
+    assert rel_err(out["depth_pred"], aux["out"]["depth_pred"]) < 1e-3
+    assert rel_err(loss, lo) < 1e-4
+    for tag, net in (("sdf", r.sdf_network), ("color", r.color_network), ("variance", r.deviation_network)):
+        for k, p in net.named_parameters():
+            e = rel_err(p.grad, Pg[tag][k].grad)
+            assert e < 1e-3, (tag, k, e)
+    assert rel_err(pose.r.grad, po["r"].grad) < 2e-3 and rel_err(pose.t.grad, po["t"].grad) < 2e-3
+
+
+def test_properties_at_benchmark_size():
+    """BASELINE.json config 2 shapes (1024 rays x 64+64): size-independent invariants."""
+    torch.manual_seed(678)
+    r = C.training.build_networks(device=DEV)
+    n = 1024
+    o = torch.zeros(n, 3, device=DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV) - torch.tensor([0, 0, 2.0], device=DEV), dim=-1)
+    dn = torch.ones(n, 1, device=DEV)
+    near, far = C.training.near_far_from_sphere(o, d, (0.01, 5.0))
+    t = torch.zeros(1, device=DEV)
+    flat = r.sdf_network.flat_weights().detach()
+    z, n_coarse = r.sample_z(o, d, t, near, far, True, flat, it=1)
+    assert z.shape == (n, 128) and n_coarse == 64
+    assert (z[:, 1:] >= z[:, :-1]).all(), "merged depths must be sorted"
+    assert z.min() >= 0.01 - 1e-6 and z.max() <= 5.0 + 1e-6
+    out = r(o, d, dn, t, near, far, cos_anneal_ratio=0.5, it=1, eval=True)
+    w = out["weights"]
+    assert torch.isfinite(w).all() and (w >= 0).all() and (out["weight_sum"] <= 1 + 1e-4).all()
+    assert_close(out["weight_sum"], w.sum(-1, keepdim=True), 1e-5)
+    assert_close(out["weight_max"], w.max(-1, keepdim=True)[0], 0)
+    assert (out["color_fine"] >= 0).all() and (out["color_fine"] <= 1 + 1e-5).all()
+    # determinism of eval renders and linearity of the backward in the upstream gradient
+    out2 = r(o, d, dn, t, near, far, cos_anneal_ratio=0.5, it=1, eval=True)
+    assert torch.equal(out2["color_fine"], out["color_fine"])
+    r.zero_grad()
+    out["color_fine"].sum().backward()
+    g1 = r.sdf_network.lin4.weight_v.grad.clone()
+    r.zero_grad()
+    (3.0 * r(o, d, dn, t, near, far, cos_anneal_ratio=0.5, it=1, eval=True)["color_fine"].sum()).backward()
+    assert rel_err(r.sdf_network.lin4.weight_v.grad, 3.0 * g1) < 1e-4     # atomics reorder sums: not bit-exact
+
+
+def test_empty_and_ragged_batches():
+    r = C.training.build_networks(SMALL_CFG, device=DEV)
+    for n in (1, 3, 33):
+        o = torch.zeros(n, 3, device=DEV)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        near, far = C.training.near_far_from_sphere(o, d, (0.01, 5.0))
+        out = r(o, d, torch.ones(n, 1, device=DEV), torch.zeros(1, device=DEV), near, far, it=1, eval=True)
+        assert out["color_fine"].shape == (n, 3) and torch.isfinite(out["color_fine"]).all()
+    y = r.sdf_network(torch.zeros(0, 4, device=DEV))
+    assert y.shape == (0, 65)
