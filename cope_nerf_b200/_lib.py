@@ -87,13 +87,14 @@ def load():
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA fp32/int64 and dense enough for
-    the callee's stated layout; contiguity is the caller's contract."""
+    """Marshal a tensor argument (None -> NULL).  Returns the (contiguous) TENSOR, not its address: `call` takes
+    the address while holding a reference, so a temporary made by .contiguous()/.float() cannot be freed — and its
+    block re-used by the next temporary — before the kernel is enqueued."""
     if t is None:
         return None
     if not t.is_cuda:
         raise CopeError("cope_nerf_b200 kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
-    return t.data_ptr()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 def stream():
@@ -104,7 +105,17 @@ def stream():
 
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    keep = args                      # tensors stay referenced until the launch has been enqueued
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if not (a.is_cuda and a.is_contiguous()):
+                raise CopeError(f"{name}: tensor arguments must be contiguous CUDA tensors (use _lib.ptr)")
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    rc = getattr(lib, name)(*conv)
+    del keep
     if rc != 0:
         raise CopeError(f"{name} failed ({rc}): {lib.cope_last_error().decode()}")
 

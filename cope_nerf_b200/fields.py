@@ -235,8 +235,7 @@ class _ColorFn(torch.autograd.Function):
     def forward(ctx, net, flat, points, normals, view_dirs, feats, dirs_group, prec):
         P, dev = points.shape[0], points.device
         points, normals, view_dirs = points.contiguous().float(), normals.contiguous().float(), view_dirs.contiguous().float()
-        if feats.stride(-1) != 1:
-            feats = feats.contiguous()
+        feats = feats.contiguous().float()       # y[:, 1:] views arrive with row stride 257: densify
         rgb = torch.empty(P, net._dims_out[-1], dtype=torch.float32, device=dev)
         saved = torch.empty(L.query("cope_color_saved_floats", net.desc, P, prec), dtype=torch.float32, device=dev)
         ws = L.scratch(L.query("cope_color_ws_floats", net.desc, P, prec), dev)
