@@ -1,0 +1,62 @@
+// bf16 tcgen05 GEMM building blocks of the COPE_PREC_BF16 MLP path (declarations; kernels in tc_gemm.cu).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cope {
+
+typedef __nv_bfloat16 bf16;
+
+enum TcEpi : int {
+  TC_STORE = 0,        // v = alpha*(acc + bias?)                          n<nsplit -> out ; else out2[n-nsplit]
+  TC_BIAS_SOFTPLUS,    // out = alpha*softplus100(acc+bias)
+  TC_BIAS_RELU,        // out = max(acc+bias,0)
+  TC_BIAS_SIGMOID,     // out = sigmoid(acc+bias)
+  TC_MUL_SIGP,         // n<nsplit: out = alpha*acc*sp(H) ; else out2[n-nsplit] = alpha*acc
+  TC_TANGENT,          // sp = sp(H); out = alpha*acc*sp ; out2 = acc*D*100*(1-sp)
+  TC_BWD,              // a' = acc + r1[m]*r1w[n]; n<nsplit: out = alpha*a'*sp(H) + D? ; else out2[n-nsplit] = alpha*a'
+  TC_RELU_MASK,        // out = (H>0) ? acc + r1.. : 0
+};
+// sp(H) = softplus'(z) recovered from the stored activation h = softplus(z):  1 - exp(-100 * H * hscale)
+
+struct TcArgs {
+  int M, N, K;                 // rows; padded N (mult of 16, <= 256); padded K (mult of 64, <= 320)
+  const bf16* A; int lda;      // activations [M x lda] bf16, K-contiguous
+  const bf16* Bp;              // packed weights [K/8][N][8]
+  int epi; float alpha; float hscale;
+  int n_valid;                 // columns >= n_valid are not stored
+  int nsplit;                  // see TcEpi (>= N: no split)
+  const float* bias;           // [>= n_valid] or null
+  void* out; int ldo; int out_f32;
+  void* out2; int ldo2; int out2_f32; int n2_valid;
+  const bf16* H; int ldh;
+  const bf16* D; int ldd;
+  const float* r1; int r1_ld; const float* r1w;   // rank-1 update acc += r1[m*r1_ld] * r1w[n]
+};
+inline TcArgs tc_args(int M, int N, int K, const bf16* A, int lda, const bf16* Bp, void* out, int ldo, int out_f32) {
+  TcArgs t{};
+  t.M = M; t.N = N; t.K = K; t.A = A; t.lda = lda; t.Bp = Bp; t.out = out; t.ldo = ldo; t.out_f32 = out_f32;
+  t.epi = TC_STORE; t.alpha = 1.0f; t.hscale = 1.0f; t.n_valid = N; t.nsplit = 1 << 30; t.n2_valid = 1 << 30;
+  return t;
+}
+int launch_tc_gemm(const TcArgs& a, cudaStream_t s);
+
+// dW[m, n] += sum_p X[p, m] * Y[p, n]   for up to two (X, Y) operand pairs; m < m_valid, n < n_valid
+struct TcWgradArgs {
+  int64_t P;
+  int Mp, Np;                  // padded widths: Mp in {128, 256}, Np mult of 16 <= 256
+  int m_valid, n_valid;
+  const bf16* X[2]; int ldx[2];
+  const bf16* Y[2]; int ldy[2];
+  int n_pairs;
+  float* dW; int ldw;
+};
+int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
+
+// packed[(k/8) * Np + n][k%8] = W[...]: nmap[n], kmap[k] give source row/col (or -1 -> 0);
+// transposed: source element = W[kmap[k] * ldw + nmap[n]] instead of W[nmap[n] * ldw + kmap[k]]
+int launch_tc_pack(const float* W, int ldw, const int* nmap, const int* kmap, int Np, int Kp, int transposed, bf16* out,
+                   cudaStream_t s);
+
+}  // namespace cope
