@@ -60,7 +60,7 @@ _SIGS = {
     "cope_pose_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f]),
     "cope_raygen_fwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f]),
     "cope_raygen_bwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f, _f, _f]),
-    "cope_tc_pack": (_i, [_f, _i, _f, _f, _i, _i, _i, _f, _f]),
+    "cope_tc_pack": (_i, [_f, _i, _i, _i, _i, _i, _i, _f, _f]),
     "cope_tc_gemm": (_i, [_i, _i, _i, _f, _i, _f, _f, _i, _fl, _f, _i, _i, _f]),
     "cope_tc_wgrad": (_i, [_l, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "mlp_shape.cuh"
 
 namespace cope {
 
@@ -150,36 +151,6 @@ static int wgrad(const float* Zb, int ldz, const float* In, int ldi, int64_t P, 
   return launch_gemm(true, false, g, s);
 }
 
-// ------------------------------------------------------------------------------------------- layouts
-struct MlpShape {
-  int n_lin, d_in, L, pe_w, skip, ldh, d_out;
-  int64_t w_off[COPE_MAX_LIN], b_off[COPE_MAX_LIN], n_flat;
-  int in[COPE_MAX_LIN], out[COPE_MAX_LIN];
-};
-
-static int make_shape(const cope_mlp_desc* d, MlpShape* s) {
-  COPE_REQUIRE(d && d->n_lin >= 2 && d->n_lin <= COPE_MAX_LIN, "mlp desc: n_lin out of range");
-  s->n_lin = d->n_lin; s->d_in = d->d_in; s->L = d->multires; s->skip = d->skip_layer;
-  s->pe_w = d->d_in * (1 + 2 * d->multires);
-  int64_t off = 0;
-  int ldh = 0;
-  for (int l = 0; l < d->n_lin; ++l) { s->in[l] = d->dims_in[l]; s->out[l] = d->dims_out[l]; }
-  for (int l = 0; l < d->n_lin; ++l) {
-    COPE_REQUIRE(s->in[l] > 0 && s->out[l] > 0, "mlp desc: bad dims at layer %d", l);
-    s->w_off[l] = off; off += (int64_t)s->in[l] * s->out[l];
-    s->b_off[l] = off; off += s->out[l];
-    if (l > 0) ldh = std::max(ldh, s->in[l]);
-    if (l + 1 < d->n_lin) {
-      int expect = (l + 1 == s->skip) ? s->in[l + 1] - s->pe_w : s->in[l + 1];
-      COPE_REQUIRE(s->out[l] == expect, "mlp desc: layer %d emits %d but layer %d expects %d", l, s->out[l], l + 1, expect);
-    }
-  }
-  s->n_flat = off;
-  s->ldh = (ldh + 3) / 4 * 4;
-  s->d_out = s->out[d->n_lin - 1];
-  return 0;
-}
-
 struct SdfSaved {   // views into the caller's `saved` buffer
   float* pe; float* Z; float* H; float* D; int64_t P; int ldh, pe_w;
   float* z(int l) const { return Z + (int64_t)l * P * ldh; }        // l = 0..n_lin-2
@@ -217,14 +188,14 @@ int cope_embed_fwd(const float* x, int64_t P, int d, int L, float* out, cope_str
 int64_t cope_sdf_saved_floats(const cope_mlp_desc* d, int64_t P, int with_grad, int prec) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  (void)prec;
+  if (prec == COPE_PREC_BF16) return sdf_saved_floats_bf16(m, P, with_grad);
   return P * (m.pe_w + (int64_t)(m.n_lin - 1) * m.ldh * (2 + (with_grad ? 1 : 0)));
 }
 
 int64_t cope_sdf_ws_floats(const cope_mlp_desc* d, int64_t P, int prec) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  (void)prec;
+  if (prec == COPE_PREC_BF16) return sdf_ws_floats_bf16(m, P);
   int64_t ldw = (std::max(m.ldh, m.d_out) + 3) / 4 * 4;
   return P * ((int64_t)(m.n_lin + 6) * ldw + 4 * m.pe_w);
 }
@@ -233,7 +204,8 @@ int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, i
                    int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_query: precision %d not built into this entry point", prec);
+  if (prec == COPE_PREC_BF16) return sdf_query_bf16(m, Wflat, x, P, sdf_out, ws, as_stream(s_));
+  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_query: unknown precision %d", prec);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
   float* pe = ws;
@@ -262,7 +234,8 @@ int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
                  float* feat, int feat_ld, float* grad, float* saved, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_fwd: precision %d not built into this entry point", prec);
+  if (prec == COPE_PREC_BF16) return sdf_fwd_bf16(m, Wflat, x, P, sdf, sdf_ld, feat, feat_ld, grad, saved, ws, as_stream(s_));
+  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_fwd: unknown precision %d", prec);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
   SdfSaved sv = sdf_saved(m, P, saved);
@@ -313,7 +286,10 @@ int cope_sdf_bwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
                  float* dWflat, float* dx, int dx_accumulate, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_bwd: precision %d not built into this entry point", prec);
+  if (prec == COPE_PREC_BF16)
+    return sdf_bwd_bf16(m, Wflat, x, P, saved, d_sdf, d_sdf_ld, d_feat, d_feat_ld, dgrad, dWflat, dx, dx_accumulate, ws,
+                        as_stream(s_));
+  COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_bwd: unknown precision %d", prec);
   const bool have_dy = d_sdf || d_feat;
   if (P <= 0 || (!have_dy && !dgrad)) {
     if (dx && P > 0 && !dx_accumulate) cudaMemsetAsync(dx, 0, sizeof(float) * P * m.d_in, as_stream(s_));
@@ -489,13 +465,13 @@ extern "C" {
 int64_t cope_color_saved_floats(const cope_mlp_desc* d, int64_t P, int prec) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  (void)prec;
+  if (prec == COPE_PREC_BF16) return color_saved_floats_bf16(m, P);
   return P * (m.in[0] + (int64_t)(m.n_lin - 1) * m.ldh + m.d_out);
 }
 int64_t cope_color_ws_floats(const cope_mlp_desc* d, int64_t P, int prec) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  (void)prec;
+  if (prec == COPE_PREC_BF16) return color_ws_floats_bf16(m, P);
   return P * (2 * (int64_t)m.ldh + m.in[0] + 4 + m.d_out);
 }
 
@@ -504,7 +480,9 @@ int cope_color_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, c
                    int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  COPE_REQUIRE(prec == COPE_PREC_FP32, "color_fwd: precision %d not built into this entry point", prec);
+  if (prec == COPE_PREC_BF16)
+    return color_fwd_bf16(m, Wflat, x, dirs, dirs_group, Lv, normals, feat, feat_ld, P, rgb, saved, ws, as_stream(s_));
+  COPE_REQUIRE(prec == COPE_PREC_FP32, "color_fwd: unknown precision %d", prec);
   const int d_feat = m.in[0] - (4 + 3 * (1 + 2 * Lv) + 4);
   COPE_REQUIRE(d_feat > 0 && m.skip < 0, "color_fwd: layer-0 width %d does not match idr input", m.in[0]);
   if (P <= 0) return 0;
@@ -531,7 +509,10 @@ int cope_color_bwd(const cope_mlp_desc* d, const float* Wflat, const float* dirs
                    float* dfeat, int dfeat_ld, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  COPE_REQUIRE(prec == COPE_PREC_FP32, "color_bwd: precision %d not built into this entry point", prec);
+  if (prec == COPE_PREC_BF16)
+    return color_bwd_bf16(m, Wflat, dirs, dirs_group, Lv, P, saved, d_rgb, dWflat, dx, ddirs, dnormals, dfeat, dfeat_ld, ws,
+                          as_stream(s_));
+  COPE_REQUIRE(prec == COPE_PREC_FP32, "color_bwd: unknown precision %d", prec);
   const int d_feat = m.in[0] - (4 + 3 * (1 + 2 * Lv) + 4);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);

@@ -410,21 +410,24 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
 }
 
 // ================================================================================================ packing
-__global__ void tc_pack_kernel(const float* __restrict__ W, int ldw, const int* __restrict__ nmap,
-                               const int* __restrict__ kmap, int Np, int Kp, int transposed, bf16* __restrict__ out) {
+__device__ __forceinline__ int map_seg(const PackSeg* s, int n, int i) {
+  for (int q = 0; q < n; ++q)
+    if (i >= s[q].dst && i < s[q].dst + s[q].len) return s[q].src + (i - s[q].dst);
+  return -1;
+}
+__global__ void tc_pack_kernel(const float* __restrict__ W, int ldw, const PackSpec spec, int Np, int Kp, int transposed,
+                               bf16* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Np * Kp) return;
   const int kk = i & 7, n = (i >> 3) % Np, kg = i / (8 * Np);
-  const int k = kg * 8 + kk;
-  const int sn = nmap[n], sk = kmap[k];
+  const int sn = map_seg(spec.n, spec.nn, n), sk = map_seg(spec.k, spec.nk, kg * 8 + kk);
   float v = 0.0f;
   if (sn >= 0 && sk >= 0) v = transposed ? W[(int64_t)sk * ldw + sn] : W[(int64_t)sn * ldw + sk];
   out[i] = __float2bfloat16(v);
 }
 
-int launch_tc_pack(const float* W, int ldw, const int* nmap, const int* kmap, int Np, int Kp, int transposed, bf16* out,
-                   cudaStream_t s) {
-  tc_pack_kernel<<<(Np * Kp + 255) / 256, 256, 0, s>>>(W, ldw, nmap, kmap, Np, Kp, transposed, out);
+int launch_tc_pack(const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out, cudaStream_t s) {
+  tc_pack_kernel<<<(Np * Kp + 255) / 256, 256, 0, s>>>(W, ldw, spec, Np, Kp, transposed, out);
   COPE_CHECK_LAUNCH("tc_pack");
   return 0;
 }
@@ -435,9 +438,12 @@ int launch_tc_pack(const float* W, int ldw, const int* nmap, const int* kmap, in
 using namespace cope;
 extern "C" {
 
-int cope_tc_pack(const float* W, int ldw, const int32_t* nmap, const int32_t* kmap, int Np, int Kp, int transposed,
-                 void* out_bf16, cope_stream_t s) {
-  return launch_tc_pack(W, ldw, nmap, kmap, Np, Kp, transposed, reinterpret_cast<bf16*>(out_bf16), as_stream(s));
+int cope_tc_pack(const float* W, int ldw, int n_src, int k_src, int Np, int Kp, int transposed, void* out_bf16,
+                 cope_stream_t s) {
+  PackSpec sp = pack_spec();
+  seg_n(sp, 0, 0, n_src);
+  seg_k(sp, 0, 0, k_src);
+  return launch_tc_pack(W, ldw, sp, Np, Kp, transposed, reinterpret_cast<bf16*>(out_bf16), as_stream(s));
 }
 
 int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* Bp_bf16, const float* bias, int epi,

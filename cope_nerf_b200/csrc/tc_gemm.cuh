@@ -54,9 +54,16 @@ struct TcWgradArgs {
 };
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
 
-// packed[(k/8) * Np + n][k%8] = W[...]: nmap[n], kmap[k] give source row/col (or -1 -> 0);
-// transposed: source element = W[kmap[k] * ldw + nmap[n]] instead of W[nmap[n] * ldw + kmap[k]]
-int launch_tc_pack(const float* W, int ldw, const int* nmap, const int* kmap, int Np, int Kp, int transposed, bf16* out,
-                   cudaStream_t s);
+// packed[(k/8) * Np + n][k%8] = W[sn * ldw + sk] (transposed: W[sk * ldw + sn]) where sn / sk are the source indices
+// that the segment lists map packed row n / packed k to (unmapped -> 0).
+struct PackSeg { int dst, src, len; };
+struct PackSpec {
+  PackSeg n[4]; int nn;
+  PackSeg k[6]; int nk;
+};
+inline PackSpec pack_spec() { PackSpec p{}; return p; }
+inline PackSpec& seg_n(PackSpec& p, int dst, int src, int len) { p.n[p.nn++] = PackSeg{dst, src, len}; return p; }
+inline PackSpec& seg_k(PackSpec& p, int dst, int src, int len) { p.k[p.nk++] = PackSeg{dst, src, len}; return p; }
+int launch_tc_pack(const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out, cudaStream_t s);
 
 }  // namespace cope

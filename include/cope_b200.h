@@ -174,10 +174,10 @@ int cope_sgemm(int transA, int transB, int M, int N, int K, const float* A, int 
 
 /* ---- bf16 tcgen05 building blocks (exposed for kernel-level tests; the MLP entry points above use them when
  * prec == COPE_PREC_BF16).  Packed weight layout: [Kp/8][Np][8] bf16 = UMMA no-swizzle K-major core matrices.
- * nmap[Np] / kmap[Kp]: source row / column of W for each packed row / k (-1 = zero padding); transposed swaps the
- * roles (packs W^T).  epi: 0 store, 1 bias+softplus(beta=100), 2 bias+relu, 3 bias+sigmoid. */
-int cope_tc_pack(const float* W, int ldw, const int32_t* nmap, const int32_t* kmap, int Np, int Kp, int transposed,
-                 void* out_bf16, cope_stream_t s);
+ * Packed row n < n_src / packed k < k_src come from W (row stride ldw), the rest is zero padding; transposed packs W^T.
+ * epi: 0 store, 1 bias+softplus(beta=100), 2 bias+relu, 3 bias+sigmoid. */
+int cope_tc_pack(const float* W, int ldw, int n_src, int k_src, int Np, int Kp, int transposed, void* out_bf16,
+                 cope_stream_t s);
 /* out[M x N] = epi(A[M x K] (bf16, row stride lda) * Wpacked^T + bias); N mult of 16 <= 256, K mult of 64 <= 320 */
 int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* Bp_bf16, const float* bias, int epi,
                  float alpha, void* out, int ldo, int out_f32, cope_stream_t s);

@@ -13,11 +13,8 @@ DEV = "cuda"
 def pack(W, Np, Kp, transposed=False):
     out_dim, in_dim = W.shape
     n_src, k_src = (in_dim, out_dim) if transposed else (out_dim, in_dim)
-    nmap = torch.full((Np,), -1, dtype=torch.int32); nmap[:n_src] = torch.arange(n_src, dtype=torch.int32)
-    kmap = torch.full((Kp,), -1, dtype=torch.int32); kmap[:k_src] = torch.arange(k_src, dtype=torch.int32)
     out = torch.empty(Np * Kp, dtype=torch.bfloat16, device=DEV)
-    L.call("cope_tc_pack", L.ptr(W), in_dim, L.ptr(nmap.to(DEV)), L.ptr(kmap.to(DEV)), Np, Kp, int(transposed), L.ptr(out),
-           L.stream())
+    L.call("cope_tc_pack", L.ptr(W), in_dim, n_src, k_src, Np, Kp, int(transposed), L.ptr(out), L.stream())
     return out
 
 
