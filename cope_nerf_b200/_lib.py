@@ -62,7 +62,8 @@ _SIGS = {
     "cope_raygen_bwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f, _f, _f]),
     "cope_tc_pack": (_i, [_f, _i, _i, _i, _i, _i, _i, _f, _f]),
     "cope_tc_gemm": (_i, [_i, _i, _i, _f, _i, _f, _f, _i, _fl, _f, _i, _i, _f]),
-    "cope_tc_wgrad": (_i, [_l, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _f]),
+    "cope_tc_wgrad_ws_floats": (_l, []),
+    "cope_tc_wgrad": (_i, [_l, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _f, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }
 EXPORTS = tuple(_SIGS)

@@ -235,7 +235,7 @@ int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P) {
   if (make_sdfb(m, &b)) return -1;
   // packed weights + (T: top, ZB2: top, ZB: 2, dyb: 1, t0 + 3 spare) bf16 [P x LD] + 4 fp32 [P x 64]
   int64_t bf = (int64_t)b.w_total + P * ((int64_t)(2 * b.top + 4) * b.LD + 64);
-  return (bf + 1) / 2 + P * 4 * 64 + 1024;
+  return (bf + 1) / 2 + P * 4 * 64 + tc_wgrad_part_floats() + 1024;
 }
 
 // ------------------------------------------------------------------------------------------- SDF forward
@@ -339,6 +339,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   bf16* t0 = dyb + (int64_t)P * LD;                       // [P x 64]
   float* eb0 = reinterpret_cast<float*>(t0 + (int64_t)P * 64);
   float* eb1 = eb0 + P * 64;
+  float* part = eb1 + P * 64;                            // tc_wgrad partial tiles
   auto Tl = [&](int l) { return l == 0 ? t0 : T + (int64_t)(l - 1) * P * LD; };
   auto ldT = [&](int l) { return l == 0 ? 64 : LD; };
   auto zb2 = [&](int l) { return ZB2 + (int64_t)l * P * LD; };
@@ -381,7 +382,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         TcWgradArgs w{};
         w.P = P; w.Mp = r128(featW); w.Np = r16(m.in[top]); w.m_valid = featW; w.n_valid = m.in[top];
         w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
-        w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top];
+        w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part;
         if (d_feat) {
           if (int rc = launch_tc_wgrad(w, s)) return rc;
           if (int rc = wcolsum(dyb, LD, nullptr, 0, P, featW, dWflat + m.b_off[top] + 1, s)) return rc;
@@ -409,7 +410,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         w.n_valid = l == 0 ? m.pe_w : m.in[l];
         w.X[0] = zb; w.ldx[0] = LD; w.Y[0] = sv.in(l); w.ldy[0] = sv.ld_in(l); w.n_pairs = 1;
         if (with2) { w.X[1] = sv.dl(l); w.ldx[1] = LD; w.Y[1] = Tl(l); w.ldy[1] = ldT(l); w.n_pairs = 2; }
-        w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l];
+        w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part;
         if (int rc = launch_tc_wgrad(w, s)) return rc;
         if (int rc = wcolsum(zb, LD, nullptr, 0, P, m.out[l], dWflat + m.b_off[l], s)) return rc;
       }
@@ -593,7 +594,7 @@ int64_t color_saved_floats_bf16(const MlpShape& m, int64_t P) {
 int64_t color_ws_floats_bf16(const MlpShape& m, int64_t P) {
   ColB c;
   if (make_colb(m, -1, &c)) return -1;
-  return ((int64_t)c.w_total + P * (2 * (int64_t)c.LD + 128) + 1) / 2 + P * 64 + 1024;
+  return ((int64_t)c.w_total + P * (2 * (int64_t)c.LD + 128) + 1) / 2 + P * 64 + tc_wgrad_part_floats() + 1024;
 }
 
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
@@ -630,6 +631,7 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
   bf16* B[2] = {wp + c.w_total, wp + c.w_total + (int64_t)P * c.LD};
   bf16* dzt = B[1] + (int64_t)P * c.LD;                        // [P x 128]
   float* rest = reinterpret_cast<float*>(dzt + (int64_t)P * 128);
+  float* part = rest + P * 64;
   if (int rc = pack_color(m, c, Wflat, wp, false, true, s)) return rc;
   sigmoid_bwd_bf16_kernel<<<g1(P * 128), 256, 0, s>>>(d_rgb, sv.rgb, m.d_out, dzt, 128, P);
   COPE_CHECK_LAUNCH("sigmoid_bwd_bf16");
@@ -639,7 +641,7 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
   for (int l = c.top; l >= 0; --l) {
     // ---- weight + bias gradients
     TcWgradArgs w{};
-    w.P = P; w.Mp = r128(m.out[l]); w.m_valid = m.out[l]; w.X[0] = dz; w.ldx[0] = lddz; w.n_pairs = 1;
+    w.P = P; w.Mp = r128(m.out[l]); w.m_valid = m.out[l]; w.X[0] = dz; w.ldx[0] = lddz; w.n_pairs = 1; w.part = part;
     if (l > 0) {
       w.Np = r16(m.in[l]); w.n_valid = m.in[l]; w.Y[0] = sv.h(l); w.ldy[0] = c.LD; w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l];
       if (int rc = launch_tc_wgrad(w, s)) return rc;

@@ -1,13 +1,15 @@
 // bf16 tcgen05 GEMMs for the NeuS MLPs (sm_100a).
 //
-// tc_gemm_kernel   C[M x N] = epi(A[M x K] * W[N x K]^T): persistent CTAs, one 128-row tile at a time.
+// tc_gemm_kernel<EPI>  C[M x N] = epi(A[M x K] * W[N x K]^T): persistent CTAs, one 128-row tile at a time.
 //   * W (<= 160 KB, pre-packed in UMMA core-matrix order) is bulk-TMA'd into shared memory ONCE per CTA and
 //     stays resident; A streams through a 4-stage cp.async ring (128 x 64 bf16 per stage);
 //   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16) into one of two TMEM accumulators, so the
 //     epilogue of tile i overlaps the MMAs of tile i+1;
-//   * 8 epilogue warps pull the accumulator with tcgen05.ld and apply the fused NeuS epilogues.
-// tc_wgrad_kernel  dW[Mp x Np] += X^T Y with K = points (both operands MN-major), fp32 accumulation in TMEM over
-//   the CTA's slice of points, then one pass of fp32 atomics.
+//   * 8 epilogue warps pull 32-column slabs with tcgen05.ld, prefetch the next slab's auxiliary operands from
+//     global memory, and apply the NeuS epilogue selected at compile time (bias / rank-1 vectors live in smem).
+// tc_wgrad_kernel  dW[Mp x Np] += X^T Y with K = points (both operands MN-major): each CTA accumulates its slice of
+//   points in TMEM (fp32) and writes ONE partial tile; wgrad_reduce_kernel sums the partials (deterministic, no
+//   atomics).
 //
 // Shared-memory operand layout: no swizzle, 8 x 16 B core matrices (see tc_common.cuh::smem_desc).
 #include <algorithm>
@@ -23,120 +25,134 @@ constexpr int kStages = 4;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
 constexpr int kAStageBytes = kTileM * kChunkK * 2;   // 16 KB
+constexpr int kVecBytes = 2 * 256 * 4;               // bias + rank-1 row staged in smem
 
-struct Load16 { uint4 a, b; };
-__device__ __forceinline__ void load16_bf16(const bf16* p, float (&f)[16]) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
-  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_lo(w[i]); f[2 * i + 1] = bf16_hi(w[i]); }
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(beta=100): log2(1 + 2^(100 log2e z)) * ln2/100, torch's threshold (100 z > 20 -> z); 2 MUFU + 4 FP ops
+__device__ __forceinline__ float fast_softplus100(float z) {
+  const float t = z * (kSoftplusBeta * 1.4426950408889634f);
+  const float s = lg2f(1.0f + ex2f(t)) * (0.6931471805599453f / kSoftplusBeta);
+  return t > 28.853900817779268f ? z : s;
 }
-__device__ __forceinline__ void store16(void* base, int64_t elem_off, int is_f32, const float (&v)[16], int n_ok) {
+__device__ __forceinline__ float sp_from_h(float h, float hscale) {   // softplus'(z) = 1 - exp(-100 softplus(z))
+  return 1.0f - ex2f(h * (hscale * -kSoftplusBeta * 1.4426950408889634f));
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+struct Aux32 { uint4 q[4]; };   // 32 bf16
+__device__ __forceinline__ void load_aux32(const bf16* p, Aux32& a) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a.q[i] = __ldg(q + i);
+}
+
+// full 32-wide store (n0 multiple of 32, row pointer 16 B aligned)
+__device__ __forceinline__ void store32(void* base, int64_t off, int is_f32, const float (&v)[32]) {
   if (is_f32) {
-    float* o = reinterpret_cast<float*>(base) + elem_off;
-    if (n_ok >= 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < n_ok) o[i] = v[i];
-    }
+    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else {
-    bf16* o = reinterpret_cast<bf16*>(base) + elem_off;
-    if (n_ok >= 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-      uint4 a, b;
-      a.x = pack_bf16(v[0], v[1]); a.y = pack_bf16(v[2], v[3]); a.z = pack_bf16(v[4], v[5]); a.w = pack_bf16(v[6], v[7]);
-      b.x = pack_bf16(v[8], v[9]); b.y = pack_bf16(v[10], v[11]); b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
-      reinterpret_cast<uint4*>(o)[0] = a;
-      reinterpret_cast<uint4*>(o)[1] = b;
-    } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < n_ok) o[i] = __float2bfloat16(v[i]);
+    for (int i = 0; i < 4; ++i) {
+      uint4 q;
+      q.x = pack_bf16(v[8 * i], v[8 * i + 1]); q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      o[i] = q;
     }
   }
 }
-
-__device__ __forceinline__ float sp_from_h(float h, float hscale) {
-  // softplus'(z) = 1 - exp(-100 softplus(z))
-  return 1.0f - __expf(-kSoftplusBeta * h * hscale);
+__device__ __noinline__ void store_elem(void* base, int64_t off, int is_f32, float v) {
+  if (is_f32) reinterpret_cast<float*>(base)[off] = v;
+  else reinterpret_cast<bf16*>(base)[off] = __float2bfloat16(v);
 }
 
-// fused epilogue for 16 consecutive columns [n0, n0+16) of row m
-__device__ __forceinline__ void tc_epilogue16(const TcArgs& a, int64_t m, int n0, float (&acc)[16]) {
-  float o1[16], o2[16];
-  float hv[16], dv[16];
-  const bool needH = a.epi == TC_MUL_SIGP || a.epi == TC_TANGENT || a.epi == TC_BWD || a.epi == TC_RELU_MASK;
-  if (needH && n0 < a.nsplit) load16_bf16(a.H + m * a.ldh + n0, hv);
-  const bool needD = (a.epi == TC_TANGENT) || (a.epi == TC_BWD && a.D != nullptr);
-  if (needD && n0 < a.nsplit) load16_bf16(a.D + m * a.ldd + n0, dv);
-  const float r1 = a.r1 ? a.r1[m * a.r1_ld] : 0.0f;
+// One 32-column slab [n0, n0+32) of row m.  h/d: auxiliary operands already in registers.
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue32(const TcArgs& a, const float* s_bias, const float* s_r1w, int64_t m, int n0,
+                                              float (&acc)[32], const Aux32& h, const Aux32& d, float r1) {
+  constexpr bool kNeedH = EPI == TC_MUL_SIGP || EPI == TC_TANGENT || EPI == TC_BWD || EPI == TC_RELU_MASK;
+  constexpr bool kNeedD = EPI == TC_TANGENT || EPI == TC_BWD;
+  constexpr bool kSplit = EPI == TC_STORE || EPI == TC_MUL_SIGP || EPI == TC_BWD;
+  float o2[EPI == TC_TANGENT ? 32 : 1];
+  float hv[kNeedH ? 32 : 1], dv[kNeedD ? 32 : 1];
+  if (kNeedH) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 4; ++i) unpack8(h.q[i], hv + 8 * i);
+  }
+  const bool haveD = kNeedD && (EPI == TC_TANGENT || a.D != nullptr);
+  if (kNeedD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack8(d.q[i], dv + 8 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
     const int n = n0 + i;
     float v = acc[i];
-    if (a.bias && n < a.n_valid) v += a.bias[n];
-    if (a.r1) v += r1 * a.r1w[n];
-    o2[i] = 0.0f;
-    switch (a.epi) {
-      case TC_STORE: v *= a.alpha; break;
-      case TC_BIAS_SOFTPLUS: v = a.alpha * softplus100(v); break;
-      case TC_BIAS_RELU: v = fmaxf(v, 0.0f); break;
-      case TC_BIAS_SIGMOID: v = sigmoidf_(v); break;
-      case TC_MUL_SIGP:
-        v = (n < a.nsplit) ? a.alpha * v * sp_from_h(hv[i], a.hscale) : a.alpha * v;
-        break;
-      case TC_TANGENT: {
-        float sp = sp_from_h(hv[i], a.hscale);
-        o2[i] = v * dv[i] * (kSoftplusBeta * (1.0f - sp));
-        v = a.alpha * v * sp;
-      } break;
-      case TC_BWD:
-        if (n < a.nsplit) {
-          v = a.alpha * v * sp_from_h(hv[i], a.hscale);
-          if (a.D) v += dv[i];
-        } else {
-          v = a.alpha * v;
-        }
-        break;
-      case TC_RELU_MASK: v = hv[i] > 0.0f ? v : 0.0f; break;
-    }
-    o1[i] = v;
-  }
-  if (a.epi == TC_TANGENT) {
-    store16(a.out, m * a.ldo + n0, a.out_f32, o1, a.n_valid - n0);
-    store16(a.out2, m * a.ldo2 + n0, a.out2_f32, o2, a.n_valid - n0);
-    return;
-  }
-  // split outputs: columns < nsplit -> out, columns >= nsplit -> out2 (shifted)
-  if (n0 + 16 <= a.nsplit) {
-    store16(a.out, m * a.ldo + n0, a.out_f32, o1, a.n_valid - n0);
-  } else if (n0 >= a.nsplit) {
-    if (a.out2) store16(a.out2, m * a.ldo2 + (n0 - a.nsplit), a.out2_f32, o1, a.n2_valid - (n0 - a.nsplit));
-  } else {   // straddling chunk
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int n = n0 + i;
+    if (EPI <= TC_BIAS_SIGMOID) v += s_bias[n];
+    if (EPI == TC_BWD) v += r1 * s_r1w[n];
+    if (EPI == TC_STORE) v *= a.alpha;
+    else if (EPI == TC_BIAS_SOFTPLUS) v = a.alpha * fast_softplus100(v);
+    else if (EPI == TC_BIAS_RELU) v = fmaxf(v, 0.0f);
+    else if (EPI == TC_BIAS_SIGMOID) v = __fdividef(1.0f, 1.0f + ex2f(v * -1.4426950408889634f));
+    else if (EPI == TC_MUL_SIGP) v = (n < a.nsplit) ? a.alpha * v * sp_from_h(hv[kNeedH ? i : 0], a.hscale) : a.alpha * v;
+    else if (EPI == TC_TANGENT) {
+      const float sp = sp_from_h(hv[kNeedH ? i : 0], a.hscale);
+      o2[EPI == TC_TANGENT ? i : 0] = v * dv[kNeedD ? i : 0] * (kSoftplusBeta * (1.0f - sp));
+      v = a.alpha * v * sp;
+    } else if (EPI == TC_BWD) {
       if (n < a.nsplit) {
-        if (n < a.n_valid) {
-          if (a.out_f32) reinterpret_cast<float*>(a.out)[m * a.ldo + n] = o1[i];
-          else reinterpret_cast<bf16*>(a.out)[m * a.ldo + n] = __float2bfloat16(o1[i]);
-        }
-      } else if (a.out2 && (n - a.nsplit) < a.n2_valid) {
-        if (a.out2_f32) reinterpret_cast<float*>(a.out2)[m * a.ldo2 + (n - a.nsplit)] = o1[i];
-        else reinterpret_cast<bf16*>(a.out2)[m * a.ldo2 + (n - a.nsplit)] = __float2bfloat16(o1[i]);
+        v = a.alpha * v * sp_from_h(hv[kNeedH ? i : 0], a.hscale);
+        if (haveD) v += dv[kNeedD ? i : 0];
+      } else {
+        v = a.alpha * v;
       }
+    } else if (EPI == TC_RELU_MASK) v = hv[kNeedH ? i : 0] > 0.0f ? v : 0.0f;
+    acc[i] = v;
+  }
+  if constexpr (EPI == TC_TANGENT) {
+    if (n0 + 32 <= a.n_valid) {
+      store32(a.out, m * a.ldo + n0, a.out_f32, acc);
+      store32(a.out2, m * a.ldo2 + n0, a.out2_f32, o2);
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < a.n_valid) {
+          store_elem(a.out, m * a.ldo + n0 + i, a.out_f32, acc[i]);
+          store_elem(a.out2, m * a.ldo2 + n0 + i, a.out2_f32, o2[i]);
+        }
     }
+    return;
+  } else {
+  const int lim1 = kSplit ? min(a.n_valid, a.nsplit) : a.n_valid;     // columns < lim1 -> out
+  if (n0 + 32 <= lim1 && ((a.ldo * (a.out_f32 ? 4 : 2)) % 16 == 0)) {
+    store32(a.out, m * a.ldo + n0, a.out_f32, acc);
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      const int n = n0 + i;
+      if (n < lim1) store_elem(a.out, m * a.ldo + n, a.out_f32, acc[i]);
+      else if (kSplit && a.out2 && n >= a.nsplit && (n - a.nsplit) < a.n2_valid)
+        store_elem(a.out2, m * a.ldo2 + (n - a.nsplit), a.out2_f32, acc[i]);
+    }
+  }
   }
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool kNeedH = EPI == TC_MUL_SIGP || EPI == TC_TANGENT || EPI == TC_BWD || EPI == TC_RELU_MASK;
+  constexpr bool kNeedD = EPI == TC_TANGENT || EPI == TC_BWD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t wbytes = (uint32_t)a.K * a.N * 2;
   uint8_t* sW = smem;
   uint8_t* sA = smem + ((wbytes + 1023) & ~1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kAStageBytes);
+  float* s_bias = reinterpret_cast<float*>(sA + kStages * kAStageBytes);
+  float* s_r1w = s_bias + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_r1w + 256);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* a_empty = bars + 1 + kStages;
@@ -149,6 +165,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
     for (int s = 0; s < kStages; ++s) { mbar_init(a_full + s, 128); mbar_init(a_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 8); }
     fence_barrier_init();
+  }
+  if (threadIdx.x < 256) {
+    s_bias[threadIdx.x] = (a.bias && (int)threadIdx.x < a.n_valid) ? a.bias[threadIdx.x] : 0.0f;
+    s_r1w[threadIdx.x] = (a.r1w && (int)threadIdx.x < a.N) ? a.r1w[threadIdx.x] : 0.0f;
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -224,19 +244,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
   } else {
     // ------------------------------------------------------------------ epilogue warps 0..7
     const int q = warp & 3, half = warp >> 2;
-    const int nch = a.N / 16;
-    const int c_begin = half ? (nch + 1) / 2 : 0, c_end = half ? nch : (nch + 1) / 2;
+    const int nch = (a.N + 31) / 32;
     uint32_t accp = 0;
     int acc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m = (int64_t)tile * kTileM + q * 32 + lane;
+      const bool row_ok = m < a.M;
+      const int64_t mm = row_ok ? m : 0;
+      Aux32 h{}, d{};
+      int c = half;
+      // aux operands of the first slab: in flight while the MMAs of this tile finish
+      if (c < nch) {
+        if (kNeedH && c * 32 < a.nsplit) load_aux32(a.H + mm * a.ldh + c * 32, h);
+        if (kNeedD && a.D && c * 32 < a.nsplit) load_aux32(a.D + mm * a.ldd + c * 32, d);
+      }
+      const float r1 = (EPI == TC_BWD && a.r1) ? a.r1[mm * a.r1_ld] : 0.0f;
       mbar_wait(acc_full + acc, accp);
       tc_fence_after();
-      const int64_t m = (int64_t)tile * kTileM + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      for (int c = c_begin; c < c_end; ++c) {
-        float v[16];
-        tmem_ld16(taddr + c * 16, v);
-        if (m < a.M) tc_epilogue16(a, m, c * 16, v);
+      for (; c < nch; c += 2) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        Aux32 hn{}, dn{};
+        const int cn = c + 2;
+        if (cn < nch) {    // prefetch the next slab's aux operands
+          if (kNeedH && cn * 32 < a.nsplit) load_aux32(a.H + mm * a.ldh + cn * 32, hn);
+          if (kNeedD && a.D && cn * 32 < a.nsplit) load_aux32(a.D + mm * a.ldd + cn * 32, dn);
+        }
+        if (row_ok) tc_epilogue32<EPI>(a, s_bias, s_r1w, m, c * 32, v, h, d, r1);
+        h = hn; d = dn;
       }
       tc_fence_before();
       __syncwarp();
@@ -252,7 +288,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
 
 static size_t tc_gemm_smem(int N, int K) {
   size_t w = ((size_t)K * N * 2 + 1023) & ~(size_t)1023;
-  return w + kStages * kAStageBytes + 256;
+  return w + kStages * kAStageBytes + kVecBytes + 256;
+}
+
+template <int EPI>
+static int launch_tc_gemm_t(const TcArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    COPE_REQUIRE(e == cudaSuccess, "tc_gemm: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int ntiles = (a.M + kTileM - 1) / kTileM;
+  tc_gemm_kernel<EPI><<<std::min(ntiles, 148), kTcThreads, tc_gemm_smem(a.N, a.K), s>>>(a);
+  COPE_CHECK_LAUNCH("tc_gemm");
+  return 0;
 }
 
 int launch_tc_gemm(const TcArgs& a, cudaStream_t s) {
@@ -260,18 +310,23 @@ int launch_tc_gemm(const TcArgs& a, cudaStream_t s) {
   COPE_REQUIRE(a.N % 16 == 0 && a.N >= 16 && a.N <= 256, "tc_gemm: N=%d must be a multiple of 16 in [16,256]", a.N);
   COPE_REQUIRE(a.K % kChunkK == 0 && a.K >= kChunkK && a.K <= 320, "tc_gemm: K=%d must be a multiple of 64 in [64,320]", a.K);
   COPE_REQUIRE(a.lda % 8 == 0 && a.lda >= a.K, "tc_gemm: lda=%d must be >= K and a multiple of 8", a.lda);
-  static bool attr_set = false;
-  const size_t smem = tc_gemm_smem(a.N, a.K);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    COPE_REQUIRE(e == cudaSuccess, "tc_gemm: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr_set = true;
+  COPE_REQUIRE(tc_gemm_smem(a.N, a.K) <= 232448, "tc_gemm: N=%d K=%d does not fit shared memory", a.N, a.K);
+  const int n32 = ((a.N + 31) / 32) * 32;
+  const bool needH = a.epi == TC_MUL_SIGP || a.epi == TC_TANGENT || a.epi == TC_BWD || a.epi == TC_RELU_MASK;
+  const int aux_w = a.nsplit >= n32 ? n32 : std::min(n32, ((a.nsplit + 31) / 32) * 32);   // columns the epilogue reads
+  COPE_REQUIRE(!needH || (a.H && a.ldh % 8 == 0 && a.ldh >= aux_w), "tc_gemm: aux H missing / too narrow (ldh=%d)", a.ldh);
+  COPE_REQUIRE(!a.D || (a.ldd % 8 == 0 && a.ldd >= aux_w), "tc_gemm: aux D too narrow (ldd=%d)", a.ldd);
+  switch (a.epi) {
+    case TC_STORE: return launch_tc_gemm_t<TC_STORE>(a, s);
+    case TC_BIAS_SOFTPLUS: return launch_tc_gemm_t<TC_BIAS_SOFTPLUS>(a, s);
+    case TC_BIAS_RELU: return launch_tc_gemm_t<TC_BIAS_RELU>(a, s);
+    case TC_BIAS_SIGMOID: return launch_tc_gemm_t<TC_BIAS_SIGMOID>(a, s);
+    case TC_MUL_SIGP: return launch_tc_gemm_t<TC_MUL_SIGP>(a, s);
+    case TC_TANGENT: return launch_tc_gemm_t<TC_TANGENT>(a, s);
+    case TC_BWD: return launch_tc_gemm_t<TC_BWD>(a, s);
+    case TC_RELU_MASK: return launch_tc_gemm_t<TC_RELU_MASK>(a, s);
   }
-  int sms = 148;
-  const int ntiles = (a.M + kTileM - 1) / kTileM;
-  tc_gemm_kernel<<<std::min(ntiles, sms), kTcThreads, smem, s>>>(a);
-  COPE_CHECK_LAUNCH("tc_gemm");
-  return 0;
+  COPE_REQUIRE(false, "tc_gemm: unknown epilogue %d", a.epi);
 }
 
 // ================================================================================================ wgrad
@@ -299,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // this CTA's slice of points (multiples of the stage size)
+  // this CTA's slice of points (multiples of the stage size); the host sizes the grid so every CTA has work
   const int64_t nchunks_total = (a.P + kWgChunkP - 1) / kWgChunkP;
   const int64_t per = (nchunks_total + gridDim.x - 1) / gridDim.x;
   const int64_t ch0 = (int64_t)blockIdx.x * per, ch1 = min(nchunks_total, ch0 + per);
@@ -363,23 +418,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
       umma_commit(acc_full);
     }
   } else if (have_work) {
+    // partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
     const int q = warp & 3, half = warp >> 2;
     const int nch = a.Np / 16;
-    const int c_begin = half ? (nch + 1) / 2 : 0, c_end = half ? nch : (nch + 1) / 2;
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    float* part = a.part + (size_t)blockIdx.x * a.Mp * a.Np;
     for (int mb = 0; mb < nmb; ++mb) {
       const int m = mb * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + mb * 256 + ((uint32_t)(q * 32) << 16);
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int c = half; c < nch; c += 2) {
         float v[16];
         tmem_ld16(taddr + c * 16, v);
-        if (m < a.m_valid) {
-          float* o = a.dW + (int64_t)m * a.ldw + c * 16;
+        float4* o = reinterpret_cast<float4*>(part + (size_t)m * a.Np + c * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c * 16 + i < a.n_valid) atomicAdd(o + i, v[i]);
-        }
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
   }
@@ -388,10 +441,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
+// dW[m, n] += sum_c part[c][m][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Mp, int Np, int m_valid, int n_valid,
+                                    float* __restrict__ dW, int ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_valid * n_valid) return;
+  const int m = i / n_valid, n = i - m * n_valid;
+  const float* p = part + (size_t)m * Np + n;
+  const size_t stride = (size_t)Mp * Np;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int c = 0;
+  for (; c + 4 <= nparts; c += 4) {
+    s0 += p[(size_t)c * stride]; s1 += p[(size_t)(c + 1) * stride];
+    s2 += p[(size_t)(c + 2) * stride]; s3 += p[(size_t)(c + 3) * stride];
+  }
+  for (; c < nparts; ++c) s0 += p[(size_t)c * stride];
+  dW[(size_t)m * ldw + n] += (s0 + s1) + (s2 + s3);
+}
+
+int64_t tc_wgrad_part_floats() { return (int64_t)148 * 256 * 256; }
+
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   if (a.P <= 0 || a.n_pairs <= 0) return 0;
   COPE_REQUIRE((a.Mp == 128 || a.Mp == 256) && a.Np % 16 == 0 && a.Np >= 16 && a.Np <= 256,
                "tc_wgrad: Mp=%d Np=%d unsupported", a.Mp, a.Np);
+  COPE_REQUIRE(a.part != nullptr, "tc_wgrad: partial-sum workspace missing");
   for (int i = 0; i < a.n_pairs; ++i)
     COPE_REQUIRE(a.ldx[i] % 8 == 0 && a.ldy[i] % 8 == 0 && a.ldx[i] >= a.Mp && a.ldy[i] >= a.Np,
                  "tc_wgrad: operand %d leading dims (%d,%d) must cover the padded tile (%d,%d)", i, a.ldx[i], a.ldy[i], a.Mp, a.Np);
@@ -403,9 +477,14 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   }
   const size_t smem = (size_t)kWgStages * kWgChunkP * (a.Mp + a.Np) * 2 + 256;
   const int64_t nchunks = (a.P + kWgChunkP - 1) / kWgChunkP;
-  const int grid = (int)std::min<int64_t>(148, std::max<int64_t>(1, nchunks / 4));
+  int grid = (int)std::min<int64_t>(148, std::max<int64_t>(1, nchunks / 2));
+  const int64_t per = (nchunks + grid - 1) / grid;
+  grid = (int)((nchunks + per - 1) / per);                   // every CTA owns >= 1 chunk
   tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(a);
   COPE_CHECK_LAUNCH("tc_wgrad");
+  const int n = a.m_valid * a.n_valid;
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw);
+  COPE_CHECK_LAUNCH("wgrad_reduce");
   return 0;
 }
 
@@ -454,13 +533,15 @@ int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* B
   return launch_tc_gemm(t, as_stream(s));
 }
 
+int64_t cope_tc_wgrad_ws_floats(void) { return tc_wgrad_part_floats(); }
+
 int cope_tc_wgrad(int64_t P, int Mp, int Np, int m_valid, int n_valid, const void* X, int ldx, const void* Y, int ldy,
-                  float* dW, int ldw, cope_stream_t s) {
+                  float* dW, int ldw, float* ws, cope_stream_t s) {
   TcWgradArgs w{};
   w.P = P; w.Mp = Mp; w.Np = Np; w.m_valid = m_valid; w.n_valid = n_valid;
   w.X[0] = reinterpret_cast<const bf16*>(X); w.ldx[0] = ldx;
   w.Y[0] = reinterpret_cast<const bf16*>(Y); w.ldy[0] = ldy;
-  w.n_pairs = 1; w.dW = dW; w.ldw = ldw;
+  w.n_pairs = 1; w.dW = dW; w.ldw = ldw; w.part = ws;
   return launch_tc_wgrad(w, as_stream(s));
 }
 }

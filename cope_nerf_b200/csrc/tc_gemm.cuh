@@ -51,7 +51,9 @@ struct TcWgradArgs {
   const bf16* Y[2]; int ldy[2];
   int n_pairs;
   float* dW; int ldw;
+  float* part;                 // workspace: tc_wgrad_part_floats() floats (per-CTA partial tiles)
 };
+int64_t tc_wgrad_part_floats();
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
 
 // packed[(k/8) * Np + n][k%8] = W[sn * ldw + sk] (transposed: W[sk * ldw + sn]) where sn / sk are the source indices

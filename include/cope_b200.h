@@ -181,9 +181,11 @@ int cope_tc_pack(const float* W, int ldw, int n_src, int k_src, int Np, int Kp, 
 /* out[M x N] = epi(A[M x K] (bf16, row stride lda) * Wpacked^T + bias); N mult of 16 <= 256, K mult of 64 <= 320 */
 int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* Bp_bf16, const float* bias, int epi,
                  float alpha, void* out, int ldo, int out_f32, cope_stream_t s);
-/* dW[m_valid x n_valid] (fp32, row stride ldw) += X[P x Mp]^T Y[P x Np] (bf16); Mp in {128,256}, Np mult of 16 */
+/* dW[m_valid x n_valid] (fp32, row stride ldw) += X[P x Mp]^T Y[P x Np] (bf16); Mp in {128,256}, Np mult of 16.
+ * ws: cope_tc_wgrad_ws_floats() floats of scratch for the per-CTA partial tiles (summed without atomics). */
+int64_t cope_tc_wgrad_ws_floats(void);
 int cope_tc_wgrad(int64_t P, int Mp, int Np, int m_valid, int n_valid, const void* X, int ldx, const void* Y, int ldy,
-                  float* dW, int ldw, cope_stream_t s);
+                  float* dW, int ldw, float* ws, cope_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ def test_tc_wgrad(P, m, n, Mp, Np):
     Y = torch.zeros(P, Np, device=DEV); Y[:, :n] = torch.randn(P, n, device=DEV)
     Xb, Yb = X.to(torch.bfloat16), Y.to(torch.bfloat16)
     dW = torch.ones(m, n, device=DEV)
-    L.call("cope_tc_wgrad", P, Mp, Np, m, n, L.ptr(Xb), Mp, L.ptr(Yb), Np, L.ptr(dW), n, L.stream())
+    ws = torch.empty(L.query("cope_tc_wgrad_ws_floats"), device=DEV)
+    L.call("cope_tc_wgrad", P, Mp, Np, m, n, L.ptr(Xb), Mp, L.ptr(Yb), Np, L.ptr(dW), n, L.ptr(ws), L.stream())
     ref = Xb[:, :m].float().t() @ Yb[:, :n].float() + 1.0
     assert rel_err(dW, ref) < 2e-5
