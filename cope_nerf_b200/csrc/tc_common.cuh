@@ -45,6 +45,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// pull a contiguous global region into L2 ahead of the 16-byte cp.async gathers (one DRAM-friendly request)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load (tensor map in param/global space), completion in bytes on `bar`; c0 = inner (element) coord
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 // 16-byte cp.async with zero fill when src_bytes == 0
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -116,6 +130,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
+}
+// 128-byte-swizzled operand tile as written by a TMA box of 64 bf16 x rows (tile base 1024-B aligned):
+//   K-major : rows are 128 B apart, sbo = 1024 (8-row group), lbo unused; advance K by +32 B per MMA
+//   MN-major: lbo = byte stride between 64-element MN blocks, sbo = 1024 (8 k-rows); advance K by +2048 B per MMA
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return smem_desc(saddr, lbo, sbo) | (2ull << 61);
 }
 // instruction descriptor, kind::f16: A,B bf16, D fp32, M x N tile; a_mn / b_mn = 1 for MN-major operands
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {

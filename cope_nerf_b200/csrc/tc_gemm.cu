@@ -12,7 +12,11 @@
 //   atomics).
 //
 // Shared-memory operand layout: no swizzle, 8 x 16 B core matrices (see tc_common.cuh::smem_desc).
+#include <cuda.h>
+
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
@@ -21,10 +25,10 @@ namespace cope {
 using namespace tc;
 
 constexpr int kTcThreads = 416;          // warps 0-7 epilogue, 8-11 producers, 12 MMA + TMEM owner
-constexpr int kStages = 4;
+constexpr int kStages = 8;               // maximum ring depth; the launch picks as many as fit next to W
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
-constexpr int kAStageBytes = kTileM * kChunkK * 2;   // 16 KB
+constexpr int kAStageBytes = kTileM * kChunkK * 2;   // 16 KB: TMA box 64 x 128, 128B-swizzled
 constexpr int kVecBytes = 2 * 256 * 4;               // bias + rank-1 row staged in smem
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -142,7 +146,7 @@ __device__ __forceinline__ void tc_epilogue32(const TcArgs& a, const float* s_bi
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmA) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool kNeedH = EPI == TC_MUL_SIGP || EPI == TC_TANGENT || EPI == TC_BWD || EPI == TC_RELU_MASK;
   constexpr bool kNeedD = EPI == TC_TANGENT || EPI == TC_BWD;
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
   const uint32_t wbytes = (uint32_t)a.K * a.N * 2;
   uint8_t* sW = smem;
   uint8_t* sA = smem + ((wbytes + 1023) & ~1023u);
-  float* s_bias = reinterpret_cast<float*>(sA + kStages * kAStageBytes);
+  const int nstages = a.stages;
+  float* s_bias = reinterpret_cast<float*>(sA + nstages * kAStageBytes);
   float* s_r1w = s_bias + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_r1w + 256);
   uint64_t* w_full = bars;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(a_full + s, 128); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 8); }
     fence_barrier_init();
   }
@@ -179,33 +184,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
   const int nkc = a.K / kChunkK;
 
   if (warp >= 8 && warp < 12) {
-    // ------------------------------------------------------------------ producers: weights once, A ring
-    const int p = threadIdx.x - 256;
-    if (p == 0) {
+    // ------------------------------------------------------------------ producer: weights once (bulk TMA), A ring
+    // (2-D tiled TMA, 64 x 128 bf16 boxes, 128B swizzle; rows past M are zero-filled by the tensor map)
+    if (threadIdx.x == 256) {
+      tma_prefetch_desc(&tmA);
       mbar_arrive_expect_tx(w_full, wbytes);
       const uint32_t chunk = 32768;
       for (uint32_t off = 0; off < wbytes; off += chunk)
         bulk_g2s(sW + off, reinterpret_cast<const uint8_t*>(a.Bp) + off, min(chunk, wbytes - off), w_full);
-    }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t row0 = (int64_t)tile * kTileM;
-      for (int kc = 0; kc < nkc; ++kc) {
-        mbar_wait(a_empty + stage, phase ^ 1);
-        const uint32_t sbase = smem_u32(sA + stage * kAStageBytes);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = i * 128 + p;                 // 16-byte chunk id == linear smem position
-          const int rg = c >> 6, within = c & 63;
-          const int k8 = within >> 3, r8 = within & 7;
-          const int64_t row = row0 + rg * 8 + r8;
-          const bool ok = row < a.M;
-          const bf16* src = a.A + (ok ? row : 0) * a.lda + kc * kChunkK + k8 * 8;
-          cp_async16(sbase + c * 16, src, ok ? 16u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(a_empty + stage, phase ^ 1);
+          mbar_arrive_expect_tx(a_full + stage, kAStageBytes);
+          tma_load_2d(sA + stage * kAStageBytes, &tmA, kc * kChunkK, tile * kTileM, a_full + stage);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        cp_async_arrive_noinc(a_full + stage);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 12) {
@@ -224,17 +219,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(a_full + stage, phase);
-          fence_proxy_async();
           tc_fence_after();
           const uint32_t sAa = smem_u32(sA + stage * kAStageBytes);
 #pragma unroll
           for (int ks = 0; ks < kChunkK / 16; ++ks) {
-            const uint64_t ad = smem_desc(sAa + ks * 256, 128, 1024);
+            const uint64_t ad = smem_desc_sw128(sAa + ks * 32, 16, 1024);
             const uint64_t bd = smem_desc(sWa + (uint32_t)(kc * 8 + ks * 2) * b_lbo, b_lbo, 128);
             umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0);
           }
           umma_commit(a_empty + stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(acc_full + acc);
         acc ^= 1;
@@ -286,9 +280,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a) 
   if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
+static int tc_gemm_stages(int N, int K) {
+  size_t w = ((size_t)K * N * 2 + 1023) & ~(size_t)1023;
+  const int fit = (int)((232448 - (int64_t)w - kVecBytes - 256) / kAStageBytes);
+  return std::max(1, std::min(kStages, fit));
+}
 static size_t tc_gemm_smem(int N, int K) {
   size_t w = ((size_t)K * N * 2 + 1023) & ~(size_t)1023;
-  return w + kStages * kAStageBytes + kVecBytes + 256;
+  return w + tc_gemm_stages(N, K) * kAStageBytes + kVecBytes + 256;
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+struct MapKey {
+  const void* p; uint64_t cols, rows, ld; uint32_t box_rows;
+  bool operator==(const MapKey& o) const { return p == o.p && cols == o.cols && rows == o.rows && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.p);
+    h ^= k.cols * 0x9E3779B97F4A7C15ull + k.rows * 0xC2B2AE3D27D4EB4Full + k.ld * 0x165667B19E3779F9ull + k.box_rows;
+    return h;
+  }
+};
+// bf16 matrix [rows x cols] (row stride ld elements), boxes of 64 columns x box_rows rows, 128B swizzle, OOB -> 0
+static int make_tmap(const bf16* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, cols, rows, ld, box_rows};
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = encode_fn();
+  COPE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  COPE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned (ld=%llu)",
+               (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  COPE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] ld %llu", (int)r, (unsigned long long)rows,
+               (unsigned long long)cols, (unsigned long long)ld);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
 }
 
 template <int EPI>
@@ -300,7 +350,11 @@ static int launch_tc_gemm_t(const TcArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   const int ntiles = (a.M + kTileM - 1) / kTileM;
-  tc_gemm_kernel<EPI><<<std::min(ntiles, 148), kTcThreads, tc_gemm_smem(a.N, a.K), s>>>(a);
+  TcArgs b = a;
+  b.stages = tc_gemm_stages(a.N, a.K);
+  CUtensorMap tmA;
+  if (int rc = make_tmap(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, kTileM, &tmA)) return rc;
+  tc_gemm_kernel<EPI><<<std::min(ntiles, 148), kTcThreads, tc_gemm_smem(a.N, a.K), s>>>(b, tmA);
   COPE_CHECK_LAUNCH("tc_gemm");
   return 0;
 }
@@ -332,11 +386,16 @@ int launch_tc_gemm(const TcArgs& a, cudaStream_t s) {
 // ================================================================================================ wgrad
 constexpr int kWgStages = 3;
 constexpr int kWgChunkP = 64;            // points per pipeline stage
+constexpr int kWgBoxBytes = 64 * kWgChunkP * 2;   // one TMA box: 64 columns x 64 points, 128B-swizzled (8 KB)
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradArgs a) {
+struct WgMaps { CUtensorMap x[2], y[2]; };
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradArgs a, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t xbytes = kWgChunkP * a.Mp * 2, ybytes = kWgChunkP * a.Np * 2;
+  // stage = X tile (Mp/64 boxes) followed by Y tile (Np/64 boxes); box b of a tile holds columns [64b, 64b+64)
+  const int xb = a.Mp >> 6, yb = a.Np >> 6;
+  const uint32_t xbytes = xb * kWgBoxBytes, ybytes = yb * kWgBoxBytes;
   const uint32_t stage_bytes = xbytes + ybytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
   uint64_t* s_full = bars;
@@ -344,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   uint64_t* acc_full = bars + 2 * kWgStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(s_full + s, 128); mbar_init(s_empty + s, 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -361,52 +420,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   const int nmb = a.Mp / 128;
   const bool have_work = ch0 < ch1;
 
-  if (warp >= 8 && warp < 12) {
-    const int p = threadIdx.x - 256;
+  if (threadIdx.x == 256) {
+    // ------------------------------------------------------------------ TMA producer (points past P are zero-filled)
     int stage = 0;
     uint32_t phase = 0;
     for (int pr = 0; pr < a.n_pairs; ++pr) {
+      tma_prefetch_desc(&maps.x[pr]);
+      tma_prefetch_desc(&maps.y[pr]);
       for (int64_t ch = ch0; ch < ch1; ++ch) {
         mbar_wait(s_empty + stage, phase ^ 1);
-        const uint32_t sx = smem_u32(smem + stage * stage_bytes), sy = sx + xbytes;
-        const int64_t p0 = ch * kWgChunkP;
-        // X tile: 64 points x Mp columns -> chunk c: p8 = c&7, j = (c>>3) % (Mp/8), pg = c / Mp
-        const int xch = kWgChunkP * a.Mp / 8;
-        for (int c = p; c < xch; c += 128) {
-          const int p8 = c & 7, j = (c >> 3) % (a.Mp >> 3), pg = c / a.Mp;
-          const int64_t pt = p0 + pg * 8 + p8;
-          const bool ok = pt < a.P;
-          cp_async16(sx + c * 16, a.X[pr] + (ok ? pt : 0) * a.ldx[pr] + j * 8, ok ? 16u : 0u);
-        }
-        const int ych = kWgChunkP * a.Np / 8;
-        for (int c = p; c < ych; c += 128) {
-          const int p8 = c & 7, j = (c >> 3) % (a.Np >> 3), pg = c / a.Np;
-          const int64_t pt = p0 + pg * 8 + p8;
-          const bool ok = pt < a.P;
-          cp_async16(sy + c * 16, a.Y[pr] + (ok ? pt : 0) * a.ldy[pr] + j * 8, ok ? 16u : 0u);
-        }
-        cp_async_arrive_noinc(s_full + stage);
+        mbar_arrive_expect_tx(s_full + stage, stage_bytes);
+        uint8_t* sx = smem + stage * stage_bytes;
+        uint8_t* sy = sx + xbytes;
+        const int p0 = (int)(ch * kWgChunkP);
+        for (int b = 0; b < xb; ++b) tma_load_2d(sx + b * kWgBoxBytes, &maps.x[pr], b * 64, p0, s_full + stage);
+        for (int b = 0; b < yb; ++b) tma_load_2d(sy + b * kWgBoxBytes, &maps.y[pr], b * 64, p0, s_full + stage);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 12) {
     if (lane == 0 && have_work) {
       const uint32_t idesc = idesc_bf16(128, a.Np, 1, 1);
-      const uint32_t x_lbo = (uint32_t)a.Mp * 16, y_lbo = (uint32_t)a.Np * 16;   // one 8-point slab
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
       for (int pr = 0; pr < a.n_pairs; ++pr) {
         for (int64_t ch = ch0; ch < ch1; ++ch) {
           mbar_wait(s_full + stage, phase);
-          fence_proxy_async();
           tc_fence_after();
           const uint32_t sx = smem_u32(smem + stage * stage_bytes), sy = sx + xbytes;
 #pragma unroll
           for (int ks = 0; ks < kWgChunkP / 16; ++ks) {
-            const uint64_t bd = smem_desc(sy + ks * 2 * y_lbo, y_lbo, 128);
+            // MN-major, 128B swizzle: 64-column blocks kWgBoxBytes apart, 8-point groups 1024 B apart, 16 points per MMA
+            const uint64_t bd = smem_desc_sw128(sy + ks * 2048, kWgBoxBytes, 1024);
             for (int mb = 0; mb < nmb; ++mb) {
-              const uint64_t ad = smem_desc(sx + ks * 2 * x_lbo + mb * 2048, x_lbo, 128);
+              const uint64_t ad = smem_desc_sw128(sx + ks * 2048 + mb * 2 * kWgBoxBytes, kWgBoxBytes, 1024);
               umma_bf16(tmem_base + mb * 256, ad, bd, idesc, first ? 0u : 1u);
             }
             first = false;
@@ -417,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
       }
       umma_commit(acc_full);
     }
-  } else if (have_work) {
+  } else if (warp < 8 && have_work) {
     // partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
     const int q = warp & 3, half = warp >> 2;
     const int nch = a.Np / 16;
@@ -463,8 +511,8 @@ int64_t tc_wgrad_part_floats() { return (int64_t)148 * 256 * 256; }
 
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   if (a.P <= 0 || a.n_pairs <= 0) return 0;
-  COPE_REQUIRE((a.Mp == 128 || a.Mp == 256) && a.Np % 16 == 0 && a.Np >= 16 && a.Np <= 256,
-               "tc_wgrad: Mp=%d Np=%d unsupported", a.Mp, a.Np);
+  COPE_REQUIRE((a.Mp == 128 || a.Mp == 256) && a.Np % 64 == 0 && a.Np >= 64 && a.Np <= 256,
+               "tc_wgrad: Mp=%d Np=%d unsupported (Mp in {128,256}, Np multiple of 64)", a.Mp, a.Np);
   COPE_REQUIRE(a.part != nullptr, "tc_wgrad: partial-sum workspace missing");
   for (int i = 0; i < a.n_pairs; ++i)
     COPE_REQUIRE(a.ldx[i] % 8 == 0 && a.ldy[i] % 8 == 0 && a.ldx[i] >= a.Mp && a.ldy[i] >= a.Np,
@@ -475,12 +523,18 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
     COPE_REQUIRE(e == cudaSuccess, "tc_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t smem = (size_t)kWgStages * kWgChunkP * (a.Mp + a.Np) * 2 + 256;
+  const size_t smem = (size_t)kWgStages * ((a.Mp >> 6) + (a.Np >> 6)) * kWgBoxBytes + 256;
+  WgMaps maps;
+  for (int i = 0; i < 2; ++i) {
+    const int q = i < a.n_pairs ? i : 0;
+    if (int rc = make_tmap(a.X[q], (uint64_t)a.ldx[q], (uint64_t)a.P, (uint64_t)a.ldx[q], kWgChunkP, &maps.x[i])) return rc;
+    if (int rc = make_tmap(a.Y[q], (uint64_t)a.ldy[q], (uint64_t)a.P, (uint64_t)a.ldy[q], kWgChunkP, &maps.y[i])) return rc;
+  }
   const int64_t nchunks = (a.P + kWgChunkP - 1) / kWgChunkP;
   int grid = (int)std::min<int64_t>(148, std::max<int64_t>(1, nchunks / 2));
   const int64_t per = (nchunks + grid - 1) / grid;
   grid = (int)((nchunks + per - 1) / per);                   // every CTA owns >= 1 chunk
-  tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(a);
+  tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(a, maps);
   COPE_CHECK_LAUNCH("tc_wgrad");
   const int n = a.m_valid * a.n_valid;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw);

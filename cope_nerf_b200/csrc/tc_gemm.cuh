@@ -33,6 +33,7 @@ struct TcArgs {
   const bf16* H; int ldh;
   const bf16* D; int ldd;
   const float* r1; int r1_ld; const float* r1w;   // rank-1 update acc += r1[m*r1_ld] * r1w[n]
+  int stages;                  // A-ring depth (set by launch_tc_gemm)
 };
 inline TcArgs tc_args(int M, int N, int K, const bf16* A, int lda, const bf16* Bp, void* out, int ldo, int out_f32) {
   TcArgs t{};

@@ -22,6 +22,11 @@ for K in (64,256):
         out=torch.empty(M,N,dtype=torch.float32 if f32 else torch.bfloat16,device=dev)
         us=timeit(lambda: L.call("cope_tc_gemm",M,N,K,L.ptr(A),K,L.ptr(Bp),L.ptr(bias),epi,1.0,L.ptr(out),N,f32,L.stream()))
         print(f"K={K} N={N} {name:14s} {us:8.1f} us  {2*M*N*K/us/1e6:8.1f} TFLOP/s")
+for Mx in (18944, 18944*2, 18944*4, 18944*7):
+    A=torch.randn(Mx,256,device=dev).to(torch.bfloat16); W=torch.randn(16,256,device=dev)*0.1; Bp=pack(W,16,256); bias=torch.zeros(16,device=dev)
+    out=torch.empty(Mx,16,dtype=torch.bfloat16,device=dev)
+    us=timeit(lambda: L.call("cope_tc_gemm",Mx,16,256,L.ptr(A),256,L.ptr(Bp),L.ptr(bias),2,1.0,L.ptr(out),16,0,L.stream()))
+    print(f"Msweep N=16 M={Mx} tiles/CTA={Mx//18944}: {us:.1f} us")
 X=torch.randn(M,256,device=dev).to(torch.bfloat16); Y=torch.randn(M,256,device=dev).to(torch.bfloat16); dW=torch.zeros(256,256,device=dev); ws=torch.empty(L.query("cope_tc_wgrad_ws_floats"),device=dev)
 us=timeit(lambda: L.call("cope_tc_wgrad",M,256,256,256,256,L.ptr(X),256,L.ptr(Y),256,L.ptr(dW),256,L.ptr(ws),L.stream()))
 print(f"wgrad 256x256 P={M}: {us:.1f} us {2*M*256*256/us/1e6:.1f} TFLOP/s")
