@@ -15,6 +15,9 @@ from .common import (Exp, PoseRetriever, arange_pixels, convert3x4_4x4, get_worl
                      pixels_from_indices, vec2skew)
 from . import training
 
+# precision bench.py / smoke use when none is requested: the tensor-core path (strict fp32 parity mode: PREC_FP32)
+DEFAULT_PRECISION = PREC_BF16
+
 __all__ = ["CopeError", "PREC_BF16", "PREC_FP32", "load_library", "get_embedder", "RenderingNetwork", "SDFNetwork",
            "SingleVarianceNetwork", "NeuSRenderer", "sample_pdf", "Exp", "PoseRetriever", "arange_pixels",
            "convert3x4_4x4", "get_world_cameraOrigin_cameraRay", "make_c2w", "pixels_from_indices", "vec2skew",
