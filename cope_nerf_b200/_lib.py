@@ -38,6 +38,8 @@ _SIGS = {
     "cope_mlp_flat_floats": (_l, [_D]),
     "cope_weightnorm_fwd": (_i, [_f, _f, _f, _i, _i, _f]),
     "cope_weightnorm_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _f]),
+    "cope_flat_weights_fwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "cope_flat_weights_bwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
     "cope_embed_fwd": (_i, [_f, _l, _i, _i, _f, _f]),
     "cope_sdf_saved_floats": (_l, [_D, _l, _i, _i]),
     "cope_sdf_ws_floats": (_l, [_D, _l, _i]),
@@ -116,6 +118,8 @@ def call(name, *args):
             if not (a.is_cuda and a.is_contiguous()):
                 raise CopeError(f"{name}: tensor arguments must be contiguous CUDA tensors (use _lib.ptr)")
             conv.append(a.data_ptr())
+        elif isinstance(a, C.Array):
+            conv.append(C.cast(a, C.c_void_p))
         else:
             conv.append(a)
     rc = getattr(lib, name)(*conv)

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "mlp_shape.cuh"
+#include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
 namespace cope {
@@ -77,16 +78,25 @@ __global__ void pe_jvp_bf16_kernel(const float* __restrict__ x, int64_t P, int d
   }
 }
 
-// D[p, n] = w[n] * (1 - exp(-100 * H[p, n] * hscale))    (top of the reverse sweep), pad columns zeroed
+// D[p, n] = w[n] * (1 - exp(-100 * H[p, n] * hscale))    (top of the reverse sweep), pad columns zeroed; 8 cols / thread
 __global__ void bcast_sp_bf16_kernel(const float* __restrict__ w, const bf16* __restrict__ H, int ldh, float hscale,
                                      bf16* __restrict__ D, int ldd, int64_t P, int n, int npad) {
+  const int groups = npad >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * npad) return;
-  int64_t p = i / npad;
-  int c = (int)(i - p * npad);
-  float v = 0.0f;
-  if (c < n) v = w[c] * (1.0f - __expf(-kSoftplusBeta * __bfloat162float(H[p * ldh + c]) * hscale));
-  D[p * ldd + c] = __float2bfloat16(v);
+  if (i >= P * groups) return;
+  const int64_t p = i / groups;
+  const int c0 = (int)(i - p * groups) * 8;
+  float v[8];
+  const uint4 hq = *reinterpret_cast<const uint4*>(H + p * ldh + c0);
+  const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float h = (k & 1) ? tc::bf16_hi(hw[k >> 1]) : tc::bf16_lo(hw[k >> 1]);
+    v[k] = (c0 + k < n) ? w[c0 + k] * (1.0f - __expf(-kSoftplusBeta * h * hscale)) : 0.0f;
+  }
+  uint4 q;
+  q.x = tc::pack_bf16(v[0], v[1]); q.y = tc::pack_bf16(v[2], v[3]); q.z = tc::pack_bf16(v[4], v[5]); q.w = tc::pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(D + p * ldd + c0) = q;
 }
 
 // out[c] += sum_p w[p*ldw] * X[p, c]   (w == null -> 1)
@@ -181,6 +191,7 @@ static int make_sdfb(const MlpShape& m, SdfB* b) {
 
 // pack every layer (forward always; transposed when asked)
 static int pack_sdf(const MlpShape& m, const SdfB& b, const float* Wflat, bf16* wp, bool fwd, bool transposed, cudaStream_t s) {
+  PackBatch pb{};
   for (int l = 0; l < m.n_lin; ++l) {
     const float* W = Wflat + m.w_off[l];
     const bool top = l == b.top;
@@ -188,11 +199,11 @@ static int pack_sdf(const MlpShape& m, const SdfB& b, const float* Wflat, bf16* 
       PackSpec sp = pack_spec();
       if (top) seg_n(sp, 0, 1, m.d_out - 1); else seg_n(sp, 0, 0, m.out[l]);
       if (l == 0) { seg_k(sp, 0, 0, m.pe_w); seg_k(sp, m.pe_w, 0, m.d_in); } else seg_k(sp, 0, 0, m.in[l]);
-      if (int rc = launch_tc_pack(W, m.in[l], sp, top ? b.featN : b.Np[l], b.Kp[l], 0, wp + b.wf_off[l], s)) return rc;
+      pack_add(pb, W, m.in[l], sp, top ? b.featN : b.Np[l], b.Kp[l], 0, wp + b.wf_off[l]);
       if (top) {
         PackSpec s0 = pack_spec();
         seg_n(s0, 0, 0, 1); seg_k(s0, 0, 0, m.in[l]);
-        if (int rc = launch_tc_pack(W, m.in[l], s0, 16, b.Kp[l], 0, wp + b.wtop_sdf_off, s)) return rc;
+        pack_add(pb, W, m.in[l], s0, 16, b.Kp[l], 0, wp + b.wtop_sdf_off);
       }
     }
     if (transposed) {
@@ -201,10 +212,10 @@ static int pack_sdf(const MlpShape& m, const SdfB& b, const float* Wflat, bf16* 
       if (top) seg_k(sp, 0, 1, m.d_out - 1); else seg_k(sp, 0, 0, m.out[l]);
       const int nt = l == 0 ? 64 : r16(m.in[l]);
       const int kt = top ? r64(m.d_out - 1) : r64(m.out[l]);
-      if (int rc = launch_tc_pack(W, m.in[l], sp, nt, kt, 1, wp + b.wt_off[l], s)) return rc;
+      pack_add(pb, W, m.in[l], sp, nt, kt, 1, wp + b.wt_off[l]);
     }
   }
-  return 0;
+  return launch_tc_pack_batch(pb, s);
 }
 
 struct SdfSavedB {
@@ -291,7 +302,7 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   if (!grad) return 0;
   // ---- reverse sweep
   const int top = b.top;
-  bcast_sp_bf16_kernel<<<g1(P * b.LD), 256, 0, s>>>(Wflat + m.w_off[top], sv.h(top), b.LD, hscale_of(b, top), sv.dl(top - 1),
+  bcast_sp_bf16_kernel<<<g1(P * (b.LD / 8)), 256, 0, s>>>(Wflat + m.w_off[top], sv.h(top), b.LD, hscale_of(b, top), sv.dl(top - 1),
                                                     b.LD, P, m.out[top - 1], b.LD);
   COPE_CHECK_LAUNCH("bcast_sp_bf16");
   if (b.skip > 0 && b.skw < b.LD) {
@@ -486,6 +497,7 @@ static int make_colb(const MlpShape& m, int Lv_or_neg, ColB* c) {
 }
 
 static int pack_color(const MlpShape& m, const ColB& c, const float* Wflat, bf16* wp, bool fwd, bool transposed, cudaStream_t s) {
+  PackBatch pb{};
   const int F = c.d_feat, R = c.rest;
   for (int l = 0; l < m.n_lin; ++l) {
     const float* W = Wflat + m.w_off[l];
@@ -493,47 +505,64 @@ static int pack_color(const MlpShape& m, const ColB& c, const float* Wflat, bf16
       PackSpec sp = pack_spec();
       seg_n(sp, 0, 0, m.out[l]);
       if (l == 0) { seg_k(sp, 0, R, F); seg_k(sp, F, 0, R); seg_k(sp, F + R, 0, 4); } else seg_k(sp, 0, 0, m.in[l]);
-      if (int rc = launch_tc_pack(W, m.in[l], sp, r16(m.out[l]), l == 0 ? c.CK : r64(m.in[l]), 0, wp + c.wf_off[l], s)) return rc;
+      pack_add(pb, W, m.in[l], sp, r16(m.out[l]), l == 0 ? c.CK : r64(m.in[l]), 0, wp + c.wf_off[l]);
     }
     if (transposed) {
       PackSpec sp = pack_spec();
       if (l == 0) seg_n(sp, 0, R, F); else seg_n(sp, 0, 0, m.in[l]);
       seg_k(sp, 0, 0, m.out[l]);
-      if (int rc = launch_tc_pack(W, m.in[l], sp, l == 0 ? r16(F) : r16(m.in[l]), r64(m.out[l]), 1, wp + c.wt_off[l], s)) return rc;
+      pack_add(pb, W, m.in[l], sp, l == 0 ? r16(F) : r16(m.in[l]), r64(m.out[l]), 1, wp + c.wt_off[l]);
       if (l == 0) {
         PackSpec sr = pack_spec();
         seg_n(sr, 0, 0, R); seg_k(sr, 0, 0, m.out[0]);
-        if (int rc = launch_tc_pack(W, m.in[0], sr, 64, r64(m.out[0]), 1, wp + c.wt0_rest_off, s)) return rc;
+        pack_add(pb, W, m.in[0], sr, 64, r64(m.out[0]), 1, wp + c.wt0_rest_off);
       }
     }
   }
-  return 0;
+  return launch_tc_pack_batch(pb, s);
 }
 
+__device__ __forceinline__ float color_in_elem(const float* x, const float* dv, int Lv, const float* nrm, int e, int pe_w, int R) {
+  // e indexes the non-feature tail: [x_hi(4) | PE(dirs) | normals(4) | x_lo(4) | 0...]
+  if (e < 4) return __bfloat162float(__float2bfloat16(x[e]));
+  if (e < 4 + pe_w) {
+    const int q = e - 4;
+    if (q < 3) return dv[q];
+    const int blk = (q - 3) / 3, dd = (q - 3) % 3;
+    const float a = dv[dd] * (float)(1 << (blk >> 1));
+    return (blk & 1) ? cosf(a) : sinf(a);
+  }
+  if (e < R) return nrm[e - 4 - pe_w];
+  if (e < R + 4) { const float xv = x[e - R]; return xv - __bfloat162float(__float2bfloat16(xv)); }
+  return 0.0f;
+}
+// one thread = 8 consecutive columns of one row (16-byte stores; feature columns are 32-byte fp32 reads)
 __global__ void color_pack_bf16_kernel(const float* __restrict__ x, const float* __restrict__ dirs, int dirs_group, int Lv,
                                        const float* __restrict__ nrm, const float* __restrict__ feat, int feat_ld, int F,
                                        int64_t P, bf16* __restrict__ cin, int ld) {
   const int pe_w = 3 * (1 + 2 * Lv);
   const int R = 4 + pe_w + 4;
+  const int groups = ld >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * ld) return;
-  int64_t p = i / ld;
-  int c = (int)(i - p * ld);
-  float v = 0.0f;
-  if (c < F) v = feat[p * feat_ld + c];
-  else if (c < F + 4) v = __bfloat162float(__float2bfloat16(x[p * 4 + (c - F)]));
-  else if (c < F + 4 + pe_w) {
-    int e = c - F - 4;
+  if (i >= P * groups) return;
+  const int64_t p = i / groups;
+  const int c0 = (int)(i - p * groups) * 8;
+  float v[8];
+  if (c0 + 8 <= F) {
+    const float* f = feat + p * feat_ld + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = f[k];
+  } else {
     const float* dv = dirs + (p / dirs_group) * 3;
-    if (e < 3) v = dv[e];
-    else {
-      int blk = (e - 3) / 3, dd = (e - 3) % 3;
-      float a = dv[dd] * (float)(1 << (blk >> 1));
-      v = (blk & 1) ? cosf(a) : sinf(a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      v[k] = c < F ? feat[p * feat_ld + c] : color_in_elem(x + p * 4, dv, Lv, nrm + p * 4, c - F, pe_w, R);
     }
-  } else if (c < F + R) v = nrm[p * 4 + (c - F - 4 - pe_w)];
-  else if (c < F + R + 4) { float xv = x[p * 4 + (c - F - R)]; v = xv - __bfloat162float(__float2bfloat16(xv)); }
-  cin[i] = __float2bfloat16(v);
+  }
+  uint4 q;
+  q.x = tc::pack_bf16(v[0], v[1]); q.y = tc::pack_bf16(v[2], v[3]); q.z = tc::pack_bf16(v[4], v[5]); q.w = tc::pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(cin + p * ld + c0) = q;
 }
 
 // dz_top[p, c] = d_rgb * rgb (1 - rgb)  (bf16, zero padded to `ld`)
@@ -607,7 +636,7 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
   ColSavedB sv = col_saved_b(c, P, saved);
   bf16* wp = reinterpret_cast<bf16*>(ws);
   if (int rc = pack_color(m, c, Wflat, wp, true, false, s)) return rc;
-  color_pack_bf16_kernel<<<g1(P * c.CK), 256, 0, s>>>(x, dirs, dirs_group, Lv, normals, feat, feat_ld, c.d_feat, P, sv.cin, c.CK);
+  color_pack_bf16_kernel<<<g1(P * (c.CK / 8)), 256, 0, s>>>(x, dirs, dirs_group, Lv, normals, feat, feat_ld, c.d_feat, P, sv.cin, c.CK);
   COPE_CHECK_LAUNCH("color_pack_bf16");
   for (int l = 0; l < m.n_lin; ++l) {
     const bool last = l == c.top;

@@ -37,6 +37,50 @@ __global__ void weightnorm_bwd_kernel(const float* __restrict__ v, const float* 
   if (lane == 0) dg[row] = dot / nrm;
 }
 
+// all layers of one network in ONE launch: flat = [W_0 | b_0 | W_1 | b_1 ...]
+constexpr int kMaxWn = 16;
+struct WnBatch {
+  const float* v[kMaxWn]; const float* g[kMaxWn]; const float* b[kMaxWn];
+  float* dv[kMaxWn]; float* dg[kMaxWn]; float* db[kMaxWn];
+  int rows[kMaxWn], cols[kMaxWn], row0[kMaxWn];
+  long long w_off[kMaxWn], b_off[kMaxWn];
+  int n, total_rows;
+};
+__global__ void flat_weights_fwd_kernel(const __grid_constant__ WnBatch B, float* __restrict__ flat) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B.total_rows) return;
+  int l = 0;
+  while (l + 1 < B.n && row >= B.row0[l + 1]) ++l;
+  row -= B.row0[l];
+  const int lane = threadIdx.x & 31, cols = B.cols[l];
+  const float* vr = B.v[l] + (int64_t)row * cols;
+  float ss = 0.0f;
+  for (int c = lane; c < cols; c += 32) ss += vr[c] * vr[c];
+  ss = warp_sum(ss);
+  const float sc = B.g[l][row] / sqrtf(ss);
+  float* W = flat + B.w_off[l] + (int64_t)row * cols;
+  for (int c = lane; c < cols; c += 32) W[c] = vr[c] * sc;
+  if (lane == 0) flat[B.b_off[l] + row] = B.b[l][row];
+}
+__global__ void flat_weights_bwd_kernel(const __grid_constant__ WnBatch B, const float* __restrict__ dflat) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B.total_rows) return;
+  int l = 0;
+  while (l + 1 < B.n && row >= B.row0[l + 1]) ++l;
+  row -= B.row0[l];
+  const int lane = threadIdx.x & 31, cols = B.cols[l];
+  const float* vr = B.v[l] + (int64_t)row * cols;
+  const float* dr = dflat + B.w_off[l] + (int64_t)row * cols;
+  float ss = 0.0f, dot = 0.0f;
+  for (int c = lane; c < cols; c += 32) { ss += vr[c] * vr[c]; dot += vr[c] * dr[c]; }
+  ss = warp_sum(ss); dot = warp_sum(dot);
+  const float nrm = sqrtf(ss), gi = B.g[l][row];
+  const float a = gi / nrm, b = gi * dot / (nrm * ss);
+  float* dv = B.dv[l] + (int64_t)row * cols;
+  for (int c = lane; c < cols; c += 32) dv[c] = a * dr[c] - b * vr[c];
+  if (lane == 0) { B.dg[l][row] = dot / nrm; B.db[l][row] = dflat[B.b_off[l] + row]; }
+}
+
 // ------------------------------------------------------------------------------------ 4x4 helpers (fp64)
 __device__ void inv4(const double* m, double* o) {
   double a[16];
@@ -268,6 +312,36 @@ int cope_weightnorm_bwd(const float* v, const float* g, const float* dW, float* 
   if (rows <= 0) return 0;
   weightnorm_bwd_kernel<<<(rows + 3) / 4, 128, 0, as_stream(s)>>>(v, g, dW, dv, dg, rows, cols);
   COPE_CHECK_LAUNCH("weightnorm_bwd");
+  return 0;
+}
+
+static int fill_wn(WnBatch& B, int n, const void* const* v, const void* const* g, const void* const* b, const int* rows,
+                   const int* cols, const int64_t* w_off, const int64_t* b_off) {
+  COPE_REQUIRE(n >= 1 && n <= kMaxWn, "flat_weights: %d layers (max %d)", n, kMaxWn);
+  B.n = n; B.total_rows = 0;
+  for (int l = 0; l < n; ++l) {
+    B.v[l] = (const float*)v[l]; B.g[l] = (const float*)g[l]; B.b[l] = (const float*)b[l];
+    B.rows[l] = rows[l]; B.cols[l] = cols[l]; B.row0[l] = B.total_rows; B.total_rows += rows[l];
+    B.w_off[l] = w_off[l]; B.b_off[l] = b_off[l];
+  }
+  return 0;
+}
+int cope_flat_weights_fwd(int n, const void* const* v, const void* const* g, const void* const* b, const int* rows,
+                          const int* cols, const int64_t* w_off, const int64_t* b_off, float* flat, cope_stream_t s) {
+  WnBatch B{};
+  if (int rc = fill_wn(B, n, v, g, b, rows, cols, w_off, b_off)) return rc;
+  flat_weights_fwd_kernel<<<(B.total_rows + 3) / 4, 128, 0, as_stream(s)>>>(B, flat);
+  COPE_CHECK_LAUNCH("flat_weights_fwd");
+  return 0;
+}
+int cope_flat_weights_bwd(int n, const void* const* v, const void* const* g, const int* rows, const int* cols,
+                          const int64_t* w_off, const int64_t* b_off, const float* dflat, void* const* dv, void* const* dg,
+                          void* const* db, cope_stream_t s) {
+  WnBatch B{};
+  if (int rc = fill_wn(B, n, v, g, g, rows, cols, w_off, b_off)) return rc;
+  for (int l = 0; l < n; ++l) { B.dv[l] = (float*)dv[l]; B.dg[l] = (float*)dg[l]; B.db[l] = (float*)db[l]; }
+  flat_weights_bwd_kernel<<<(B.total_rows + 3) / 4, 128, 0, as_stream(s)>>>(B, dflat);
+  COPE_CHECK_LAUNCH("flat_weights_bwd");
   return 0;
 }
 

@@ -548,21 +548,30 @@ __device__ __forceinline__ int map_seg(const PackSeg* s, int n, int i) {
     if (i >= s[q].dst && i < s[q].dst + s[q].len) return s[q].src + (i - s[q].dst);
   return -1;
 }
-__global__ void tc_pack_kernel(const float* __restrict__ W, int ldw, const PackSpec spec, int Np, int Kp, int transposed,
-                               bf16* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Np * Kp) return;
-  const int kk = i & 7, n = (i >> 3) % Np, kg = i / (8 * Np);
-  const int sn = map_seg(spec.n, spec.nn, n), sk = map_seg(spec.k, spec.nk, kg * 8 + kk);
+__global__ void tc_pack_kernel(const __grid_constant__ PackBatch b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.total) return;
+  int q = 0;
+  while (q + 1 < b.n && i >= b.jobs[q + 1].first) ++q;
+  const PackJob& j = b.jobs[q];
+  const int e = i - j.first;
+  const int kk = e & 7, n = (e >> 3) % j.Np, kg = e / (8 * j.Np);
+  const int sn = map_seg(j.spec.n, j.spec.nn, n), sk = map_seg(j.spec.k, j.spec.nk, kg * 8 + kk);
   float v = 0.0f;
-  if (sn >= 0 && sk >= 0) v = transposed ? W[(int64_t)sk * ldw + sn] : W[(int64_t)sn * ldw + sk];
-  out[i] = __float2bfloat16(v);
+  if (sn >= 0 && sk >= 0) v = j.transposed ? j.W[(int64_t)sk * j.ldw + sn] : j.W[(int64_t)sn * j.ldw + sk];
+  j.out[e] = __float2bfloat16(v);
 }
 
-int launch_tc_pack(const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out, cudaStream_t s) {
-  tc_pack_kernel<<<(Np * Kp + 255) / 256, 256, 0, s>>>(W, ldw, spec, Np, Kp, transposed, out);
+int launch_tc_pack_batch(const PackBatch& b, cudaStream_t s) {
+  if (b.n == 0) return 0;
+  tc_pack_kernel<<<(b.total + 255) / 256, 256, 0, s>>>(b);
   COPE_CHECK_LAUNCH("tc_pack");
   return 0;
+}
+int launch_tc_pack(const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out, cudaStream_t s) {
+  PackBatch b{};
+  pack_add(b, W, ldw, spec, Np, Kp, transposed, out);
+  return launch_tc_pack_batch(b, s);
 }
 
 }  // namespace cope

@@ -58,15 +58,25 @@ int64_t tc_wgrad_part_floats();
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
 
 // packed[(k/8) * Np + n][k%8] = W[sn * ldw + sk] (transposed: W[sk * ldw + sn]) where sn / sk are the source indices
-// that the segment lists map packed row n / packed k to (unmapped -> 0).
+// that the segment lists map packed row n / packed k to (unmapped -> 0).  Jobs are queued into a PackBatch and
+// flushed as ONE kernel launch (all layers of a network).
 struct PackSeg { int dst, src, len; };
 struct PackSpec {
-  PackSeg n[4]; int nn;
-  PackSeg k[6]; int nk;
+  PackSeg n[2]; int nn;
+  PackSeg k[4]; int nk;
 };
 inline PackSpec pack_spec() { PackSpec p{}; return p; }
 inline PackSpec& seg_n(PackSpec& p, int dst, int src, int len) { p.n[p.nn++] = PackSeg{dst, src, len}; return p; }
 inline PackSpec& seg_k(PackSpec& p, int dst, int src, int len) { p.k[p.nk++] = PackSeg{dst, src, len}; return p; }
+constexpr int kMaxPackJobs = 24;
+struct PackJob { const float* W; bf16* out; PackSpec spec; int ldw, Np, Kp, transposed, first; };
+struct PackBatch { PackJob jobs[kMaxPackJobs]; int n, total; };
+inline void pack_add(PackBatch& b, const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out) {
+  PackJob& j = b.jobs[b.n++];
+  j.W = W; j.out = out; j.spec = spec; j.ldw = ldw; j.Np = Np; j.Kp = Kp; j.transposed = transposed; j.first = b.total;
+  b.total += Np * Kp;
+}
+int launch_tc_pack_batch(const PackBatch& b, cudaStream_t s);
 int launch_tc_pack(const float* W, int ldw, const PackSpec& spec, int Np, int Kp, int transposed, bf16* out, cudaStream_t s);
 
 }  // namespace cope

@@ -9,6 +9,7 @@ Differences that are deliberate:
     on `pts_time.detach()` (model/neus_renderer.py:356).
   * weight-norm is applied once per call into one flat fp32 buffer [W_l | b_l]* that every kernel reads.
 """
+import ctypes as C
 import math
 
 import numpy as np
@@ -43,40 +44,42 @@ class WNLinear(nn.Module):
         return (self.weight_v if self.weight_norm else self.weight).shape[1]
 
 
+def _ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
 class _FlatWeights(torch.autograd.Function):
-    """(v_0, g_0, b_0, v_1, ...) -> one flat fp32 buffer [W_0 | b_0 | W_1 | b_1 ...] via cope_weightnorm_fwd."""
+    """(v_0, g_0, b_0, v_1, ...) -> one flat fp32 buffer [W_0 | b_0 | W_1 | b_1 ...]: ONE launch for the whole network
+    (cope_flat_weights_fwd / _bwd)."""
 
     @staticmethod
     def forward(ctx, offsets, *params):
         n = len(params) // 3
-        total = offsets[-1]
-        flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
-        s = L.stream()
-        for l in range(n):
-            v, g, b = params[3 * l:3 * l + 3]
-            rows, cols = v.shape
-            w_off, b_off = offsets[2 * l], offsets[2 * l + 1]
-            L.call("cope_weightnorm_fwd", L.ptr(v), L.ptr(g), flat.data_ptr() + 4 * w_off, rows, cols, s)
-            flat[b_off:b_off + rows].copy_(b)
-        ctx.offsets = offsets
+        params = tuple(p.contiguous() for p in params)
+        vs, gs, bs = params[0::3], params[1::3], params[2::3]
+        flat = torch.empty(offsets[-1], dtype=torch.float32, device=params[0].device)
+        meta = dict(rows=(C.c_int * n)(*[v.shape[0] for v in vs]), cols=(C.c_int * n)(*[v.shape[1] for v in vs]),
+                    w_off=(C.c_int64 * n)(*offsets[0:2 * n:2]), b_off=(C.c_int64 * n)(*offsets[1:2 * n:2]))
+        L.call("cope_flat_weights_fwd", n, _ptr_array(vs), _ptr_array(gs), _ptr_array(bs), meta["rows"], meta["cols"],
+               meta["w_off"], meta["b_off"], flat, L.stream())
+        ctx.meta, ctx.n = meta, n
         ctx.save_for_backward(*params)
         return flat
 
     @staticmethod
     def backward(ctx, dflat):
         params = ctx.saved_tensors
-        offsets = ctx.offsets
+        n, meta = ctx.n, ctx.meta
+        vs, gs, bs = params[0::3], params[1::3], params[2::3]
         dflat = dflat.contiguous()
-        s = L.stream()
+        dvs = [torch.empty_like(v) for v in vs]
+        dgs = [torch.empty_like(g) for g in gs]
+        dbs = [torch.empty_like(b) for b in bs]
+        L.call("cope_flat_weights_bwd", n, _ptr_array(vs), _ptr_array(gs), meta["rows"], meta["cols"], meta["w_off"],
+               meta["b_off"], dflat, _ptr_array(dvs), _ptr_array(dgs), _ptr_array(dbs), L.stream())
         grads = []
-        for l in range(len(params) // 3):
-            v, g, b = params[3 * l:3 * l + 3]
-            rows, cols = v.shape
-            w_off, b_off = offsets[2 * l], offsets[2 * l + 1]
-            dv, dg = torch.empty_like(v), torch.empty_like(g)
-            L.call("cope_weightnorm_bwd", L.ptr(v), L.ptr(g), dflat.data_ptr() + 4 * w_off, L.ptr(dv), L.ptr(dg),
-                   rows, cols, s)
-            grads += [dv, dg, dflat[b_off:b_off + rows].clone()]
+        for dv, dg, db in zip(dvs, dgs, dbs):
+            grads += [dv, dg, db]
         return (None, *grads)
 
 
