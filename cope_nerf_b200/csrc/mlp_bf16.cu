@@ -121,14 +121,27 @@ __global__ void colsum_f32_strided_kernel(const float* __restrict__ X, int ld, i
   }
 }
 
-// dst[p, c] = bf16(src[p*lds + c] * scale) for c < n, 0 for n <= c < npad
+// dst[p, c] = bf16(src[p*lds + c] * scale) for c < n, 0 for n <= c < npad   (8 columns per thread, npad % 8 == 0)
 __global__ void cvt_f32_bf16_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, int64_t P, int n,
                                     int npad, float scale) {
+  const int groups = npad >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * npad) return;
-  int64_t p = i / npad;
-  int c = (int)(i - p * npad);
-  dst[p * ldd + c] = __float2bfloat16((c < n && src) ? src[p * lds + c] * scale : 0.0f);
+  if (i >= P * groups) return;
+  const int64_t p = i / groups;
+  const int c0 = (int)(i - p * groups) * 8;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (src && c0 + k < n) ? src[p * lds + c0 + k] * scale : 0.0f;
+  uint4 q;
+  q.x = tc::pack_bf16(v[0], v[1]); q.y = tc::pack_bf16(v[2], v[3]); q.z = tc::pack_bf16(v[4], v[5]); q.w = tc::pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst + p * ldd + c0) = q;
+}
+// out[0] += sum_p x[p * ld]
+__global__ void sum_strided_kernel(const float* __restrict__ x, int ld, int64_t P, float* __restrict__ out) {
+  float acc = 0.0f;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) acc += x[p * ld];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 __global__ void copy_bf16_scaled_kernel(const bf16* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, int64_t P,
                                         int n, float scale) {
@@ -375,7 +388,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
     if (int rc = wcolsum(Tl(top), LD, nullptr, 0, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
   }
   if (have_dy) {
-    cvt_f32_bf16_kernel<<<g1(P * r64(featW)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);
+    cvt_f32_bf16_kernel<<<g1(P * (r64(featW) / 8)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);
     COPE_CHECK_LAUNCH("cvt_dfeat");
   }
 
@@ -400,7 +413,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         }
         if (d_sdf) {
           if (int rc = wcolsum(sv.h(top), LD, d_sdf, d_sdf_ld, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
-          colsum_f32_strided_kernel<<<g1(P, 512), 32, 0, s>>>(d_sdf, d_sdf_ld, P, 1, 512, dWflat + m.b_off[top]);
+          sum_strided_kernel<<<(unsigned)std::min<int64_t>(296, ceil_div(P, 256)), 256, 0, s>>>(d_sdf, d_sdf_ld, P, dWflat + m.b_off[top]);
           COPE_CHECK_LAUNCH("colsum_dsdf");
         }
       }

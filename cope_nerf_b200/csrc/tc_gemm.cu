@@ -24,7 +24,8 @@
 namespace cope {
 using namespace tc;
 
-constexpr int kTcThreads = 416;          // warps 0-7 epilogue, 8-11 producers, 12 MMA + TMEM owner
+constexpr int kTcThreads = 320;          // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
+constexpr int kMmaWarp = 9;
 constexpr int kStages = 8;               // maximum ring depth; the launch picks as many as fit next to W
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void tc_epilogue32(const TcArgs& a, const float* s_bi
     const int n = n0 + i;
     float v = acc[i];
     if (EPI <= TC_BIAS_SIGMOID) v += s_bias[n];
-    if (EPI == TC_BWD) v += r1 * s_r1w[n];
+    if (EPI == TC_BWD) { if (a.r1) v += r1 * s_r1w[n]; }
     if (EPI == TC_STORE) v *= a.alpha;
     else if (EPI == TC_BIAS_SOFTPLUS) v = a.alpha * fast_softplus100(v);
     else if (EPI == TC_BIAS_RELU) v = fmaxf(v, 0.0f);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
     s_bias[threadIdx.x] = (a.bias && (int)threadIdx.x < a.n_valid) ? a.bias[threadIdx.x] : 0.0f;
     s_r1w[threadIdx.x] = (a.r1w && (int)threadIdx.x < a.N) ? a.r1w[threadIdx.x] : 0.0f;
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
   const int ntiles = (a.M + kTileM - 1) / kTileM;
   const int nkc = a.K / kChunkK;
 
-  if (warp >= 8 && warp < 12) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ producer: weights once (bulk TMA), A ring
     // (2-D tiled TMA, 64 x 128 bf16 boxes, 128B swizzle; rows past M are zero-filled by the tensor map)
     if (threadIdx.x == 256) {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       mbar_wait(w_full, 0);
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
         if (acc == 0) accp ^= 1;
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue warps 0..7
     const int q = warp & 3, half = warp >> 2;
     const int nch = (a.N + 31) / 32;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 static int tc_gemm_stages(int N, int K) {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0 && have_work) {
       const uint32_t idesc = idesc_bf16(128, a.Np, 1, 1);
       int stage = 0;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 // dW[m, n] += sum_c part[c][m][n]
