@@ -94,27 +94,33 @@ __device__ __forceinline__ void tc_epilogue32(const TcArgs& a, const float* s_bi
 #pragma unroll
     for (int i = 0; i < 4; ++i) unpack8(d.q[i], dv + 8 * i);
   }
+  // `lo` = this slab lies entirely below nsplit (the common case): no per-element split test
+  const bool lo = !kSplit || n0 + 32 <= a.nsplit;
+  const bool use_r1 = EPI == TC_BWD && a.r1 != nullptr;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int n = n0 + i;
     float v = acc[i];
     if (EPI <= TC_BIAS_SIGMOID) v += s_bias[n];
-    if (EPI == TC_BWD) { if (a.r1) v += r1 * s_r1w[n]; }
+    if (EPI == TC_BWD) { if (use_r1) v += r1 * s_r1w[n]; }
     if (EPI == TC_STORE) v *= a.alpha;
     else if (EPI == TC_BIAS_SOFTPLUS) v = a.alpha * fast_softplus100(v);
     else if (EPI == TC_BIAS_RELU) v = fmaxf(v, 0.0f);
     else if (EPI == TC_BIAS_SIGMOID) v = __fdividef(1.0f, 1.0f + ex2f(v * -1.4426950408889634f));
-    else if (EPI == TC_MUL_SIGP) v = (n < a.nsplit) ? a.alpha * v * sp_from_h(hv[kNeedH ? i : 0], a.hscale) : a.alpha * v;
-    else if (EPI == TC_TANGENT) {
+    else if (EPI == TC_MUL_SIGP) {
+      const float s = a.alpha * v;
+      v = (lo || n < a.nsplit) ? s * sp_from_h(hv[kNeedH ? i : 0], a.hscale) : s;
+    } else if (EPI == TC_TANGENT) {
       const float sp = sp_from_h(hv[kNeedH ? i : 0], a.hscale);
       o2[EPI == TC_TANGENT ? i : 0] = v * dv[kNeedD ? i : 0] * (kSoftplusBeta * (1.0f - sp));
       v = a.alpha * v * sp;
     } else if (EPI == TC_BWD) {
-      if (n < a.nsplit) {
-        v = a.alpha * v * sp_from_h(hv[kNeedH ? i : 0], a.hscale);
+      const float s = a.alpha * v;
+      if (lo || n < a.nsplit) {
+        v = s * sp_from_h(hv[kNeedH ? i : 0], a.hscale);
         if (haveD) v += dv[kNeedD ? i : 0];
       } else {
-        v = a.alpha * v;
+        v = s;
       }
     } else if (EPI == TC_RELU_MASK) v = hv[kNeedH ? i : 0] > 0.0f ? v : 0.0f;
     acc[i] = v;
@@ -135,6 +141,9 @@ __device__ __forceinline__ void tc_epilogue32(const TcArgs& a, const float* s_bi
   const int lim1 = kSplit ? min(a.n_valid, a.nsplit) : a.n_valid;     // columns < lim1 -> out
   if (n0 + 32 <= lim1 && ((a.ldo * (a.out_f32 ? 4 : 2)) % 16 == 0)) {
     store32(a.out, m * a.ldo + n0, a.out_f32, acc);
+  } else if (kSplit && a.out2 && n0 >= a.nsplit && (n0 - a.nsplit) + 32 <= a.n2_valid &&
+             (((n0 - a.nsplit) * (a.out2_f32 ? 4 : 2)) % 16 == 0) && ((a.ldo2 * (a.out2_f32 ? 4 : 2)) % 16 == 0)) {
+    store32(a.out2, m * a.ldo2 + (n0 - a.nsplit), a.out2_f32, acc);
   } else {
     for (int i = 0; i < 32; ++i) {
       const int n = n0 + i;
