@@ -7,6 +7,8 @@
 //     the derivative is sensitive (small h), so pre-activations are never stored
 //   * the raw coordinates enter layer 0 / the colour net as hi + lo bf16 pairs (duplicated weight columns), so the
 //     position is not quantised to 8 bits; everything that touches the PE Jacobian (ge0/ge1, dx, d_dirs) stays fp32
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "mlp_shape.cuh"
@@ -14,6 +16,11 @@
 #include "tc_gemm.cuh"
 
 namespace cope {
+
+// sdf_chain.cu: fully fused forward chain (reference architecture only)
+bool sdf_chain_supported(const MlpShape& m);
+int launch_sdf_chain_query(const MlpShape& m, const float* Wflat, const bf16* wp, const uint32_t* wf_off, uint32_t wtop_off,
+                           const float* x, int64_t P, float* sdf_out, cudaStream_t s);
 
 static inline int r16(int v) { return (v + 15) / 16 * 16; }
 static inline int r64(int v) { return (v + 63) / 64 * 64; }
@@ -99,15 +106,31 @@ __global__ void bcast_sp_bf16_kernel(const float* __restrict__ w, const bf16* __
   *reinterpret_cast<uint4*>(D + p * ldd + c0) = q;
 }
 
-// out[c] += sum_p w[p*ldw] * X[p, c]   (w == null -> 1)
+// out[c] += sum_p w[p*ldw] * X[p, c]   (w == null -> 1).  One thread per column PAIR, 4 independent row streams.
 __global__ void wcolsum_bf16_kernel(const bf16* __restrict__ X, int ld, const float* __restrict__ w, int ldw, int64_t P,
                                     int n, int rows_per_block, float* __restrict__ out) {
-  int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    float acc = 0.0f;
-    for (int64_t p = p0; p < p1; ++p) acc += (w ? w[p * ldw] : 1.0f) * __bfloat162float(X[p * ld + c]);
-    atomicAdd(out + c, acc);
+  const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
+  for (int c = threadIdx.x * 2; c < n; c += blockDim.x * 2) {
+    float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    int64_t p = p0;
+    for (; p + 4 <= p1; p += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = *reinterpret_cast<const uint32_t*>(X + (p + u) * ld + c);
+        const float wv = w ? w[(p + u) * ldw] : 1.0f;
+        a0[u] += wv * tc::bf16_lo(q);
+        a1[u] += wv * tc::bf16_hi(q);
+      }
+    }
+    for (; p < p1; ++p) {
+      const uint32_t q = *reinterpret_cast<const uint32_t*>(X + p * ld + c);
+      const float wv = w ? w[p * ldw] : 1.0f;
+      a0[0] += wv * tc::bf16_lo(q);
+      a1[0] += wv * tc::bf16_hi(q);
+    }
+    atomicAdd(out + c, (a0[0] + a0[1]) + (a0[2] + a0[3]));
+    if (c + 1 < n) atomicAdd(out + c + 1, (a1[0] + a1[1]) + (a1[2] + a1[3]));
   }
 }
 __global__ void colsum_f32_strided_kernel(const float* __restrict__ X, int ld, int64_t P, int n, int rows_per_block,
@@ -161,7 +184,7 @@ __global__ void zero_cols_bf16_kernel(bf16* __restrict__ dst, int ld, int64_t P,
 
 static int wcolsum(const bf16* X, int ld, const float* w, int ldw, int64_t P, int n, float* out, cudaStream_t s) {
   if (P <= 0 || n <= 0) return 0;
-  wcolsum_bf16_kernel<<<g1(P, 512), 256, 0, s>>>(X, ld, w, ldw, P, n, 512, out);
+  wcolsum_bf16_kernel<<<g1(P, 128), 128, 0, s>>>(X, ld, w, ldw, P, n, 128, out);
   COPE_CHECK_LAUNCH("wcolsum_bf16");
   return 0;
 }
@@ -290,6 +313,11 @@ int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_
   bf16* pe = wp + b.w_total;
   bf16* bufs[3] = {pe + P * 64, pe + P * 64 + P * b.LD, pe + P * 64 + 2 * P * b.LD};
   if (int rc = pack_sdf(m, b, Wflat, wp, true, false, s)) return rc;
+  if (sdf_chain_supported(m) && !getenv("COPE_NO_CHAIN")) {
+    uint32_t offs[COPE_MAX_LIN];
+    for (int l = 0; l < m.n_lin; ++l) offs[l] = (uint32_t)b.wf_off[l];
+    return launch_sdf_chain_query(m, Wflat, wp, offs, (uint32_t)b.wtop_sdf_off, x, P, sdf_out, s);
+  }
   bf16* hbuf[COPE_MAX_LIN + 1] = {nullptr};
   for (int l = 1; l <= b.top; ++l) hbuf[l] = (l == b.skip) ? bufs[2] : bufs[l & 1];
   pe_fwd_bf16_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, pe, 64, 64, b.skip > 0 ? hbuf[b.skip] + b.skw : nullptr, b.LD);

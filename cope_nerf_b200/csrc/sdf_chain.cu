@@ -1,0 +1,256 @@
+// Fully-fused SDF forward chain for the no-grad queries of hierarchical sampling (SDFNetwork.sdf under no_grad,
+// model/neus_renderer.py:499 and :292): PE -> 9 weight-normed linears with softplus(beta=100) -> sdf, ONE kernel,
+// activations never leave the SM.
+//
+//   * one 128-row tile per CTA at a time (persistent); the activation tile lives in shared memory as four
+//     [128 x 64] bf16 panels in the 128B-swizzled K-major UMMA layout, written by the epilogue warps themselves
+//   * weights stream layer by layer through a 4-deep ring of 32 KB K-chunks (bulk TMA from the packed L2-resident
+//     copy), issued by a dedicated producer warp that runs ahead of the MMAs
+//   * tcgen05.mma M128 x N256 x K16 into two alternating TMEM accumulators; the MMA of layer l+1 starts on K-panel j
+//     as soon as the epilogue of layer l has written panel j (per-panel mbarriers), so tensor pipe and epilogue overlap
+//   * the skip layer's [h | PE]/sqrt2 input takes its PE part from a shared-memory stash written with layer 0's input
+#include "mlp_shape.cuh"
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace cope {
+using namespace tc;
+
+constexpr int kChThreads = 320;      // warps 0-7: PE + epilogue, warp 8: weight producer, warp 9: MMA + TMEM
+constexpr int kChMma = 9;
+constexpr int kPanelBytes = 128 * 128;           // 128 rows x 64 bf16
+constexpr int kWChunkBytes = 256 * 64 * 2;       // N=256 x K=64
+constexpr int kWRing = 4;
+
+struct ChainArgs {
+  const float* x; int64_t P; float* sdf_out;
+  const bf16* wp; const float* Wflat;
+  int n_lin, skip, skw, pe_w, d_in, L;
+  uint32_t w_off[COPE_MAX_LIN];      // element offset of the packed forward weights of layer l (top: 16-row sdf block)
+  int Np[COPE_MAX_LIN], Kp[COPE_MAX_LIN], n_out[COPE_MAX_LIN];
+  int64_t b_off[COPE_MAX_LIN];
+};
+
+__device__ __forceinline__ float ch_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ch_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ch_softplus(float z) {
+  const float t = z * (kSoftplusBeta * 1.4426950408889634f);
+  const float s = ch_lg2(1.0f + ch_ex2(t)) * (0.6931471805599453f / kSoftplusBeta);
+  return t > 28.853900817779268f ? z : s;
+}
+// byte offset of 8 consecutive K elements starting at k (multiple of 8) of row r inside the 4-panel activation tile
+__device__ __forceinline__ uint32_t a_off(int r, int k) {
+  return (uint32_t)(k >> 6) * kPanelBytes + (uint32_t)r * 128 + (uint32_t)((((k & 63) >> 3) ^ (r & 7)) << 4);
+}
+
+__global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                   // 4 panels, 64 KB
+  uint8_t* sW = smem + 4 * kPanelBytes;                 // ring, 128 KB
+  bf16* sPE = reinterpret_cast<bf16*>(sW + kWRing * kWChunkBytes);   // [128][64] bf16 (PE / sqrt2), 16 KB
+  float* sBias = reinterpret_cast<float*>(sPE + 128 * 64);           // [n_lin][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + COPE_MAX_LIN * 256);
+  uint64_t* w_full = bars;                 // [kWRing]
+  uint64_t* w_empty = bars + kWRing;       // [kWRing]
+  uint64_t* a_ready = bars + 2 * kWRing;   // [4] one per K-panel, completes once per layer that owns the panel
+  uint64_t* acc_full = a_ready + 4;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWRing; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    for (int j = 0; j < 4; ++j) mbar_init(a_ready + j, 8);
+    mbar_init(acc_full + 0, 1); mbar_init(acc_full + 1, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < a.n_lin * 256; i += kChThreads) {
+    const int l = i >> 8, n = i & 255;
+    sBias[i] = n < a.n_out[l] ? a.Wflat[a.b_off[l] + n] : 0.0f;
+  }
+  if (warp == kChMma) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntiles = (int)((a.P + 127) / 128);
+  const int top = a.n_lin - 1;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l <= top; ++l) {
+          const int nkc = a.Kp[l] >> 6;
+          const uint32_t cbytes = (uint32_t)a.Np[l] * 128;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + a.w_off[l]);
+          for (int c = 0; c < nkc; ++c) {
+            mbar_wait(w_empty + stage, phase ^ 1);
+            mbar_arrive_expect_tx(w_full + stage, cbytes);
+            bulk_g2s(sW + stage * kWChunkBytes, src + (size_t)c * cbytes, cbytes, w_full + stage);
+            if (++stage == kWRing) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kChMma) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, aph = 0;     // aph: bit j = parity to wait for on a_ready[j]
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l <= top; ++l) {
+          const int nkc = a.Kp[l] >> 6;
+          const uint32_t idesc = idesc_bf16(128, a.Np[l], 0, 0);
+          const uint32_t b_lbo = (uint32_t)a.Np[l] * 16;
+          const uint32_t d_tmem = tmem_base + (l & 1) * 256;
+          for (int c = 0; c < nkc; ++c) {
+            mbar_wait(a_ready + c, (aph >> c) & 1);
+            aph ^= 1u << c;
+            mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            const uint32_t sAa = smem_u32(sA + c * kPanelBytes), sWa = smem_u32(sW + stage * kWChunkBytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(d_tmem, smem_desc_sw128(sAa + ks * 32, 16, 1024), smem_desc(sWa + ks * 2 * b_lbo, b_lbo, 128), idesc,
+                        (c | ks) != 0);
+            umma_commit(w_empty + stage);
+            if (++stage == kWRing) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(acc_full + (l & 1));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ PE + epilogue warps
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;                       // row of the tile == TMEM lane
+    uint32_t accp = 0;                                 // bit b = parity to wait for on acc_full[b]
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m = (int64_t)tile * 128 + r;
+      const bool ok = m < a.P;
+      // ---- layer-0 input: [x_hi | sin/cos | x_lo | 0] into panel 0 (this thread: 2 of the d_in coordinates)
+      {
+        // zero the 16-byte chunks that hold padding / are shared: done by the half-0 thread of the row
+        bf16* row0 = reinterpret_cast<bf16*>(sA);      // panel 0
+        auto put = [&](int k, float v) {               // element k of row r in panel 0 (swizzled)
+          row0[(a_off(r, k & ~7) >> 1) + (k & 7)] = __float2bfloat16(v);
+        };
+        if (half == 0)
+          for (int k = a.pe_w + a.d_in; k < 64; ++k) put(k, 0.0f);
+        for (int dd = half * 2; dd < min(a.d_in, half * 2 + 2); ++dd) {
+          const float v = ok ? a.x[m * a.d_in + dd] : 0.0f;
+          const bf16 hi = __float2bfloat16(v);
+          put(dd, v);
+          put(a.pe_w + dd, v - __bfloat162float(hi));
+          sPE[r * 64 + dd] = __float2bfloat16(v * kInvSqrt2);
+          float sn, cs;
+          sincosf(v, &sn, &cs);
+          for (int k = 0; k < a.L; ++k) {
+            const int ks = a.d_in * (1 + 2 * k) + dd, kc = a.d_in * (2 + 2 * k) + dd;
+            put(ks, sn); put(kc, cs);
+            sPE[r * 64 + ks] = __float2bfloat16(sn * kInvSqrt2);
+            sPE[r * 64 + kc] = __float2bfloat16(cs * kInvSqrt2);
+            const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;   // angle doubling: error grows 2x per octave
+            sn = s2; cs = c2;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready + 0);
+      }
+      // ---- layers
+      for (int l = 0; l <= top; ++l) {
+        const int b = l & 1;
+        mbar_wait(acc_full + b, (accp >> b) & 1);
+        accp ^= 1u << b;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
+        const float* bias = sBias + l * 256;
+        if (l == top) {
+          if (half == 0) {
+            float v[32];
+            tmem_ld32(taddr, v);
+            if (ok) a.sdf_out[m] = v[0] + bias[0];
+          }
+          tc_fence_before();
+          continue;
+        }
+        const bool to_skip = (l + 1 == a.skip);
+        const float alpha = to_skip ? kInvSqrt2 : 1.0f;
+        const int n_out = a.n_out[l];                  // real outputs of this layer (204 before the skip)
+        const int npan = a.Kp[l + 1] >> 6;             // panels of the next layer's input
+        for (int j = 0; j < npan; ++j) {
+          const int n0 = j * 64 + half * 32;           // this warp's 32-column slab of panel j
+          float v[32];
+          tmem_ld32(taddr + n0, v);
+          if (n0 + 32 <= n_out) {
+            // straight-line: 32 independent softplus chains, the compiler interleaves the MUFU latencies
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = alpha * ch_softplus(v[i] + bias[n0 + i]);
+          } else {
+            // slabs that straddle / follow the real outputs: zero padding, or the PE part of the skip concat
+            for (int i = 0; i < 32; ++i) {
+              const int n = n0 + i;
+              float val = 0.0f;
+              if (n < n_out) val = alpha * ch_softplus(v[i] + bias[n]);
+              else if (to_skip && n - n_out < a.pe_w) val = __bfloat162float(sPE[r * 64 + (n - n_out)]);
+              v[i] = val;
+            }
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)               // four 16-byte chunks of this row
+            *reinterpret_cast<uint4*>(sA + a_off(r, n0 + g8 * 8)) =
+                make_uint4(pack_bf16(v[g8 * 8], v[g8 * 8 + 1]), pack_bf16(v[g8 * 8 + 2], v[g8 * 8 + 3]),
+                           pack_bf16(v[g8 * 8 + 4], v[g8 * 8 + 5]), pack_bf16(v[g8 * 8 + 6], v[g8 * 8 + 7]));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready + j);
+        }
+        tc_fence_before();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kChMma) tmem_dealloc(tmem_base, 512);
+}
+
+// host side: eligible when every hidden width is 256 (the reference architecture); otherwise the caller falls back to
+// the layer-by-layer path
+bool sdf_chain_supported(const MlpShape& m) {
+  if (m.n_lin < 3 || m.pe_w + m.d_in > 64) return false;
+  for (int l = 1; l < m.n_lin; ++l)
+    if (m.in[l] != 256) return false;
+  return true;
+}
+
+int launch_sdf_chain_query(const MlpShape& m, const float* Wflat, const bf16* wp, const uint32_t* wf_off, uint32_t wtop_off,
+                           const float* x, int64_t P, float* sdf_out, cudaStream_t s) {
+  ChainArgs a{};
+  a.x = x; a.P = P; a.sdf_out = sdf_out; a.wp = wp; a.Wflat = Wflat;
+  a.n_lin = m.n_lin; a.skip = m.skip; a.pe_w = m.pe_w; a.d_in = m.d_in; a.L = m.L;
+  a.skw = m.skip > 0 ? m.in[m.skip] - m.pe_w : 0;
+  for (int l = 0; l < m.n_lin; ++l) {
+    const bool top = l == m.n_lin - 1;
+    a.w_off[l] = top ? wtop_off : wf_off[l];
+    a.Np[l] = top ? 16 : (m.out[l] + 15) / 16 * 16;
+    a.Kp[l] = l == 0 ? 64 : 256;
+    a.n_out[l] = top ? 1 : m.out[l];
+    a.b_off[l] = m.b_off[l];
+  }
+  static bool attr_set = false;
+  const size_t smem = 4 * kPanelBytes + kWRing * kWChunkBytes + 128 * 64 * 2 + COPE_MAX_LIN * 256 * 4 + 256;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sdf_chain_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    COPE_REQUIRE(e == cudaSuccess, "sdf_chain: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int ntiles = (int)((P + 127) / 128);
+  sdf_chain_query_kernel<<<std::min(ntiles, 148), kChThreads, smem, s>>>(a);
+  COPE_CHECK_LAUNCH("sdf_chain_query");
+  return 0;
+}
+
+}  // namespace cope
