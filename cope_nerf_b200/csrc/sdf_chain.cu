@@ -16,8 +16,9 @@
 namespace cope {
 using namespace tc;
 
-constexpr int kChThreads = 320;      // warps 0-7: PE + epilogue, warp 8: weight producer, warp 9: MMA + TMEM
-constexpr int kChMma = 9;
+constexpr int kChEpiWarps = 16;      // 4 warps per TMEM lane quarter: enough warps per scheduler to hide MUFU / TMEM latency
+constexpr int kChThreads = (kChEpiWarps + 2) * 32;   // + warp 16: weight producer, warp 17: MMA + TMEM
+constexpr int kChProd = kChEpiWarps, kChMma = kChEpiWarps + 1;
 constexpr int kPanelBytes = 128 * 128;           // 128 rows x 64 bf16
 constexpr int kWChunkBytes = 256 * 64 * 2;       // N=256 x K=64
 constexpr int kWRing = 4;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWRing; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
-    for (int j = 0; j < 4; ++j) mbar_init(a_ready + j, 8);
+    for (int j = 0; j < 4; ++j) mbar_init(a_ready + j, kChEpiWarps);
     mbar_init(acc_full + 0, 1); mbar_init(acc_full + 1, 1);
     fence_barrier_init();
   }
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
   const int ntiles = (int)((a.P + 127) / 128);
   const int top = a.n_lin - 1;
 
-  if (warp == 8) {
+  if (warp == kChProd) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
       int stage = 0;
@@ -122,9 +123,9 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kChEpiWarps) {
     // ------------------------------------------------------------------ PE + epilogue warps
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;     // part: which 16-column quarter of each 64-column panel
     const int r = q * 32 + lane;                       // row of the tile == TMEM lane
     uint32_t accp = 0;                                 // bit b = parity to wait for on acc_full[b]
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -137,9 +138,9 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
         auto put = [&](int k, float v) {               // element k of row r in panel 0 (swizzled)
           row0[(a_off(r, k & ~7) >> 1) + (k & 7)] = __float2bfloat16(v);
         };
-        if (half == 0)
+        if (part == 0)
           for (int k = a.pe_w + a.d_in; k < 64; ++k) put(k, 0.0f);
-        for (int dd = half * 2; dd < min(a.d_in, half * 2 + 2); ++dd) {
+        for (int dd = part; dd < a.d_in; dd += 4) {
           const float v = ok ? a.x[m * a.d_in + dd] : 0.0f;
           const bf16 hi = __float2bfloat16(v);
           put(dd, v);
@@ -169,9 +170,9 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
         const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
         const float* bias = sBias + l * 256;
         if (l == top) {
-          if (half == 0) {
-            float v[32];
-            tmem_ld32(taddr, v);
+          if (part == 0) {
+            float v[16];
+            tmem_ld16(taddr, v);
             if (ok) a.sdf_out[m] = v[0] + bias[0];
           }
           tc_fence_before();
@@ -182,16 +183,16 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
         const int n_out = a.n_out[l];                  // real outputs of this layer (204 before the skip)
         const int npan = a.Kp[l + 1] >> 6;             // panels of the next layer's input
         for (int j = 0; j < npan; ++j) {
-          const int n0 = j * 64 + half * 32;           // this warp's 32-column slab of panel j
-          float v[32];
-          tmem_ld32(taddr + n0, v);
-          if (n0 + 32 <= n_out) {
-            // straight-line: 32 independent softplus chains, the compiler interleaves the MUFU latencies
+          const int n0 = j * 64 + part * 16;           // this warp's 16-column slab of panel j
+          float v[16];
+          tmem_ld16(taddr + n0, v);
+          if (n0 + 16 <= n_out) {
+            // straight-line: 16 independent softplus chains, the compiler interleaves the MUFU latencies
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = alpha * ch_softplus(v[i] + bias[n0 + i]);
+            for (int i = 0; i < 16; ++i) v[i] = alpha * ch_softplus(v[i] + bias[n0 + i]);
           } else {
             // slabs that straddle / follow the real outputs: zero padding, or the PE part of the skip concat
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const int n = n0 + i;
               float val = 0.0f;
               if (n < n_out) val = alpha * ch_softplus(v[i] + bias[n]);
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
             }
           }
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8)               // four 16-byte chunks of this row
+          for (int g8 = 0; g8 < 2; ++g8)               // two 16-byte chunks of this row
             *reinterpret_cast<uint4*>(sA + a_off(r, n0 + g8 * 8)) =
                 make_uint4(pack_bf16(v[g8 * 8], v[g8 * 8 + 1]), pack_bf16(v[g8 * 8 + 2], v[g8 * 8 + 3]),
                            pack_bf16(v[g8 * 8 + 4], v[g8 * 8 + 5]), pack_bf16(v[g8 * 8 + 6], v[g8 * 8 + 7]));
