@@ -117,3 +117,43 @@ def test_bf16_full_size_step_vs_oracle_and_fp32():
     for tag, net in (("sdf", r.sdf_network), ("color", r.color_network), ("variance", r.deviation_network)):
         check_grads(net.named_parameters(), {k: v.grad for k, v in Pg[tag].items()}, tag)
     assert cos_sim(pose.r.grad, po["r"].grad) > 0.99 and cos_sim(pose.t.grad, po["t"].grad) > 0.99
+
+
+def test_fused_query_chain_matches_layered_path(monkeypatch):
+    """sdf_chain_query_kernel (one launch, activations on-chip) against the layer-by-layer tcgen05 path and the oracle."""
+    P = full_params(perturb=0.02)
+    r = bf16_renderer(P, C.training.DEFAULT_CFG)
+    torch.manual_seed(9)
+    for n in (1, 100, 128, 5000, 16384 + 77):
+        x = torch.cat([torch.randn(n, 3) * 0.7, torch.full((n, 1), 0.3)], -1)
+        flat = r.sdf_network.flat_weights().detach()
+        fused = r.sdf_network.query_flat(flat, cu(x))
+        monkeypatch.setenv("COPE_NO_CHAIN", "1")
+        layered = r.sdf_network.query_flat(flat, cu(x))
+        monkeypatch.delenv("COPE_NO_CHAIN")
+        ref = O.sdf_value(P["sdf"], x)
+        assert fused.shape == (n, 1) and torch.isfinite(fused).all()
+        assert_close(fused, layered, 5e-3, f"fused vs layered n={n}")
+        assert_close(fused, ref, 1e-2, f"fused vs oracle n={n}")
+
+
+def test_bf16_properties_at_benchmark_size():
+    torch.manual_seed(678)
+    r = C.training.build_networks(device=DEV, precision=C.PREC_BF16)
+    n = 1024
+    o = torch.zeros(n, 3, device=DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV) - torch.tensor([0, 0, 2.0], device=DEV), dim=-1)
+    near, far = C.training.near_far_from_sphere(o, d, (0.01, 5.0))
+    out = r(o, d, torch.ones(n, 1, device=DEV), torch.zeros(1, device=DEV), near, far, cos_anneal_ratio=0.5, it=1, eval=True)
+    w = out["weights"]
+    assert torch.isfinite(w).all() and (w >= 0).all() and (out["weight_sum"] <= 1 + 1e-4).all()
+    assert (out["color_fine"] >= 0).all() and (out["color_fine"] <= 1 + 1e-5).all()
+    out["color_fine"].sum().backward()
+    for p in r.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    # strict fp32 render of the same rays: the two precisions must agree on the image
+    r32 = C.training.build_networks(device=DEV, precision=C.PREC_FP32)
+    r32.load_state_dict(r.state_dict())
+    out32 = r32(o, d, torch.ones(n, 1, device=DEV), torch.zeros(1, device=DEV), near, far, cos_anneal_ratio=0.5, it=1, eval=True)
+    assert cos_sim(out["color_fine"], out32["color_fine"]) > COS
+    assert cos_sim(out["depth_pred"], out32["depth_pred"]) > COS
