@@ -175,12 +175,12 @@ def workload_name(rays):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("COPE_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
-    ap.add_argument("--cpu-rays", type=int, default=128, help="ray sample of the CPU baseline step")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="ray sample of the CPU baseline step (BASELINE.json configs[0]: 512 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -362,10 +362,10 @@ def main():
                          "algorithmic_flop_per_ray": FLOP_PER_TRAIN_RAY},
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, spt = cpu_train_rays_per_s(args.cpu_rays, 2, 1)
+            v, spt = cpu_train_rays_per_s(args.cpu_rays, 3, 1)
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_rays} rays x 64+64 samples per step (1 warm-up + 2 timed), same "
+                                    "sample": f"{args.cpu_rays} rays x 64+64 samples per step (1 warm-up + 3 timed), same "
                                               f"nets/losses/Adam, oracle port of the reference's PyTorch CPU path"}
         print(json.dumps(line))
     if world > 1:

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Per-kernel roofline sweep (BASELINE.json configs[4]): 4K-256K rays x 128 samples on one B200.
+
+For each HBM-bound kernel: achieved GB/s = algorithmic bytes (DESIGN.md §4 / SURVEY.md §8d) / CUDA-event time, against
+the measured copy bandwidth in MEASURED_PEAKS.json.  For the fused SDF query chain: TFLOP/s against the bf16 peak.
+Prints one JSON line per (kernel, rays).  Inputs are larger than L2 from 64K rays up; smaller sizes are L2-resident
+and flagged so."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import cope_nerf_b200 as C  # noqa: E402
+from cope_nerf_b200 import _lib as L  # noqa: E402
+from bench import peaks  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, nargs="*", default=[4096, 16384, 65536, 262144])
+    args = ap.parse_args()
+    dev = torch.device("cuda")
+    pk = peaks()
+    torch.manual_seed(678)
+    rnd = C.training.build_networks(device=dev, precision=C.PREC_BF16)
+    S = 128
+    for N in args.rays:
+        P = N * S
+        z = torch.sort(torch.rand(N, S, device=dev) * 4.9 + 0.01, dim=-1)[0].contiguous()
+        dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((N, 1), 0.078, device=dev)], -1).contiguous()
+        sdf = ((1.5 - z) * 0.7 + 0.02 * torch.randn(N, S, device=dev)).reshape(P, 1).contiguous()
+        grad = torch.randn(P, 4, device=dev)
+        rgb = torch.rand(P, 3, device=dev)
+        rays_d = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=-1)
+        dn = torch.ones(N, 1, device=dev)
+        var = rnd.deviation_network.variance.detach()
+        f = lambda *s: torch.empty(*s, device=dev)
+        weights, color, depth, wz, cdf, wsum, wmax, inv_s = f(N, S), f(N, 3), f(N, 1), f(N, 1), f(N, S), f(N, 1), f(N, 1), f(1)
+        st = L.stream()
+
+        def comp_fwd():
+            L.call("cope_composite_fwd", sdf, grad, rgb, z, dists, rays_d, dn, var, 0.5, 0, N, S, weights, color, depth, wz,
+                   None, wsum, wmax, inv_s, st)
+        d_color, d_depth, d_w = torch.rand(N, 3, device=dev), torch.rand(N, 1, device=dev), torch.rand(N, S, device=dev)
+        d_sdf, d_grad, d_rgb, d_var, d_rd = f(P, 1), torch.zeros(P, 4, device=dev), f(P, 3), torch.zeros(1, device=dev), f(N, 3)
+
+        def comp_bwd():
+            L.call("cope_composite_bwd", sdf, grad, rgb, z, dists, rays_d, dn, var, 0.5, 0, N, S, d_color, d_depth, d_w,
+                   d_sdf, d_grad, d_rgb, d_var, d_rd, st)
+        new_z = f(N, 16)
+
+        def ups():
+            L.call("cope_upsample", z, sdf, N, S - 16, 16, 512.0, new_z, None, None, st)
+        z112, s112 = z[:, :112].contiguous(), sdf.reshape(N, S)[:, :112].contiguous()
+        zo, so = f(N, S), f(N, S)
+
+        def mrg():
+            L.call("cope_merge_z", z112, new_z, s112, new_z, N, 112, 16, zo, so, st)
+        x = torch.cat([torch.randn(P, 3, device=dev) * 0.6, torch.zeros(P, 1, device=dev)], -1)
+        flat = rnd.sdf_network.flat_weights().detach()
+        rows = [
+            ("composite_fwd", comp_fwd, N * (S * 36 + 44), "hbm"),                # z,dists,sdf 12 + grad 16 + rgb 12 in; w 4 out
+            ("composite_bwd", comp_bwd, N * (S * 84 + 60), "hbm"),                # 40 in + d_w 4 + d_grad rw 32 + d_sdf 4 + d_rgb 12 - z
+            ("upsample", ups, N * ((S - 16) * 8 + 64), "hbm"),
+            ("merge_z", mrg, N * (2 * (112 + 16) * 4 + 2 * S * 4), "hbm"),
+            ("sdf_query_chain", lambda: rnd.sdf_network.query_flat(flat, x), P * 918016, "tensor"),
+        ]
+        for name, fn, work, bound in rows:
+            if name == "sdf_query_chain" and N > 65536:
+                continue
+            t = timeit(fn)
+            if bound == "hbm":
+                ach, peak, unit = work / t / 1e9, pk["hbm"], "GB/s"
+            else:
+                ach, peak, unit = work / t / 1e12, pk["bf16"], "TFLOP/s"
+            print(json.dumps({"kernel": name, "rays": N, "samples": S, "us": t * 1e6, "achieved": ach, "peak": peak, "unit": unit,
+                              "frac": ach / peak, "bound": bound, "bytes_or_flops": work,
+                              "l2_resident": bool(bound == "hbm" and work < 100e6), "peak_source": pk["src"]}))
+
+
+if __name__ == "__main__":
+    main()
