@@ -436,8 +436,8 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
         w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part;
         if (d_feat) {
+          w.db = dWflat + m.b_off[top] + 1;
           if (int rc = launch_tc_wgrad(w, s)) return rc;
-          if (int rc = wcolsum(dyb, LD, nullptr, 0, P, featW, dWflat + m.b_off[top] + 1, s)) return rc;
         }
         if (d_sdf) {
           if (int rc = wcolsum(sv.h(top), LD, d_sdf, d_sdf_ld, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
@@ -462,9 +462,8 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         w.n_valid = l == 0 ? m.pe_w : m.in[l];
         w.X[0] = zb; w.ldx[0] = LD; w.Y[0] = sv.in(l); w.ldy[0] = sv.ld_in(l); w.n_pairs = 1;
         if (with2) { w.X[1] = sv.dl(l); w.ldx[1] = LD; w.Y[1] = Tl(l); w.ldy[1] = ldT(l); w.n_pairs = 2; }
-        w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part;
+        w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part; w.db = dWflat + m.b_off[l];
         if (int rc = launch_tc_wgrad(w, s)) return rc;
-        if (int rc = wcolsum(zb, LD, nullptr, 0, P, m.out[l], dWflat + m.b_off[l], s)) return rc;
       }
       if (l == 0 && !want_e) break;
       const int kt = r64(m.out[l]);
@@ -712,16 +711,17 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
     // ---- weight + bias gradients
     TcWgradArgs w{};
     w.P = P; w.Mp = r128(m.out[l]); w.m_valid = m.out[l]; w.X[0] = dz; w.ldx[0] = lddz; w.n_pairs = 1; w.part = part;
+    w.db = dWflat + m.b_off[l];                  // bias gradient: fused column sum of dz inside the wgrad kernel
     if (l > 0) {
       w.Np = r16(m.in[l]); w.n_valid = m.in[l]; w.Y[0] = sv.h(l); w.ldy[0] = c.LD; w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l];
       if (int rc = launch_tc_wgrad(w, s)) return rc;
     } else {
       w.Np = r16(F); w.n_valid = F; w.Y[0] = sv.cin; w.ldy[0] = c.CK; w.dW = dWflat + m.w_off[0] + R; w.ldw = m.in[0];
       if (int rc = launch_tc_wgrad(w, s)) return rc;
+      w.db = nullptr;
       w.Np = 64; w.n_valid = R; w.Y[0] = sv.cin + r64(F); w.dW = dWflat + m.w_off[0];
       if (int rc = launch_tc_wgrad(w, s)) return rc;
     }
-    if (int rc = wcolsum(dz, lddz, nullptr, 0, P, m.out[l], dWflat + m.b_off[l], s)) return rc;
     // ---- data gradient
     const int kt = r64(m.out[l]);
     if (l > 0) {

@@ -399,6 +399,9 @@ constexpr int kWgChunkP = 64;            // points per pipeline stage
 constexpr int kWgBoxBytes = 64 * kWgChunkP * 2;   // one TMA box: 64 columns x 64 points, 128B-swizzled (8 KB)
 
 struct WgMaps { CUtensorMap x[2], y[2]; };
+// workspace = 148 partial tiles [256 x 256] + 148 partial column-sum rows [256]
+__host__ __device__ constexpr int64_t tc_wgrad_part_floats_c() { return (int64_t)148 * 256 * 256 + (int64_t)148 * 256; }
+int64_t tc_wgrad_part_floats() { return tc_wgrad_part_floats_c(); }
 
 __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradArgs a, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   uint64_t* acc_full = bars + 2 * kWgStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 1 + 8); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -476,7 +479,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
       umma_commit(acc_full);
     }
   } else if (warp < 8 && have_work) {
-    // partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
+    // ---- while the MMAs run: bias gradient = column sums of pair 0's X tile, read straight from the swizzled smem
+    // stage (thread t owns column t); every warp also releases the stage (s_empty counts MMA commit + 8 warps)
+    {
+      const int col = threadIdx.x;                       // 0..255
+      float csum = 0.0f;
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t cofs = (uint32_t)(col >> 6) * kWgBoxBytes + (uint32_t)(col & 7) * 2;
+      const int cchunk = (col & 63) >> 3;
+      for (int pr = 0; pr < a.n_pairs; ++pr) {
+        for (int64_t ch = ch0; ch < ch1; ++ch) {
+          mbar_wait(s_full + stage, phase);
+          if (pr == 0 && a.db != nullptr && col < a.Mp) {
+            const uint8_t* sx = smem + stage * stage_bytes + cofs;
+#pragma unroll 8
+            for (int p = 0; p < kWgChunkP; ++p)
+              csum += __bfloat162float(*reinterpret_cast<const bf16*>(sx + p * 128 + ((cchunk ^ (p & 7)) << 4)));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty + stage);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (a.db != nullptr && col < a.Mp) a.part[tc_wgrad_part_floats_c() - (int64_t)148 * 256 + (size_t)blockIdx.x * 256 + col] = csum;
+    }
+    // ---- partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
     const int q = warp & 3, half = warp >> 2;
     const int nch = a.Np / 16;
     mbar_wait(acc_full, 0);
@@ -499,11 +527,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
-// dW[m, n] += sum_c part[c][m][n]
+// dW[m, n] += sum_c part[c][m][n] ;  db[m] += sum_c colpart[c][m]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Mp, int Np, int m_valid, int n_valid,
-                                    float* __restrict__ dW, int ldw) {
+                                    float* __restrict__ dW, int ldw, float* __restrict__ db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m_valid * n_valid) return;
+  const int nw = m_valid * n_valid;
+  if (i >= nw) {
+    const int m = i - nw;
+    if (db == nullptr || m >= m_valid) return;
+    const float* p = part + (tc_wgrad_part_floats_c() - (int64_t)148 * 256) + m;
+    float s = 0.0f;
+    for (int c = 0; c < nparts; ++c) s += p[(size_t)c * 256];
+    db[m] += s;
+    return;
+  }
   const int m = i / n_valid, n = i - m * n_valid;
   const float* p = part + (size_t)m * Np + n;
   const size_t stride = (size_t)Mp * Np;
@@ -516,8 +553,6 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, 
   for (; c < nparts; ++c) s0 += p[(size_t)c * stride];
   dW[(size_t)m * ldw + n] += (s0 + s1) + (s2 + s3);
 }
-
-int64_t tc_wgrad_part_floats() { return (int64_t)148 * 256 * 256; }
 
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   if (a.P <= 0 || a.n_pairs <= 0) return 0;
@@ -546,8 +581,8 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   grid = (int)((nchunks + per - 1) / per);                   // every CTA owns >= 1 chunk
   tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(a, maps);
   COPE_CHECK_LAUNCH("tc_wgrad");
-  const int n = a.m_valid * a.n_valid;
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw);
+  const int n = a.m_valid * a.n_valid + (a.db ? a.m_valid : 0);
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw, a.db);
   COPE_CHECK_LAUNCH("wgrad_reduce");
   return 0;
 }

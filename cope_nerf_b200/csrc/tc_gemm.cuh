@@ -52,7 +52,8 @@ struct TcWgradArgs {
   const bf16* Y[2]; int ldy[2];
   int n_pairs;
   float* dW; int ldw;
-  float* part;                 // workspace: tc_wgrad_part_floats() floats (per-CTA partial tiles)
+  float* part;                 // workspace: tc_wgrad_part_floats() floats (per-CTA partial tiles + column sums)
+  float* db;                   // optional: db[m] += sum_p X[0][p, m]  (bias gradient, fused column sum of pair 0's X)
 };
 int64_t tc_wgrad_part_floats();
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
