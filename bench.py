@@ -33,7 +33,8 @@ FLOP_PER_TRAIN_RAY = 1_117_315_072          # 112*F_sdfq + 128*(
 H, W = 717, 1275
 DEPTH_RANGE = (0.01, 5.0)
 METRIC = "train rays/s fwd+bwd+eikonal (NeuS 64+64 samples)"
-MLP_CALLS = {"cope_sdf_query", "cope_sdf_fwd", "cope_sdf_bwd", "cope_color_fwd", "cope_color_bwd"}
+MLP_CALLS = {"cope_sdf_query", "cope_sdf_fwd", "cope_sdf_bwd", "cope_color_fwd", "cope_color_bwd", "cope_render_mlp_fwd",
+             "cope_render_mlp_bwd"}
 
 
 def peaks():
@@ -354,7 +355,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "SDF+colour MLP kernels (cope_sdf_query/fwd/bwd, cope_color_fwd/bwd)",
+            "roofline": {"bound": "tensor", "kernel": "SDF+colour MLP kernels (cope_sdf_query, cope_render_mlp_fwd/bwd = tc_gemm / tc_wgrad / sdf_chain)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                          "measured": "CUDA events around the MLP entry points, same K batches launched eagerly after the timed region",

@@ -288,15 +288,16 @@ int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P) {
 // ------------------------------------------------------------------------------------------- SDF forward
 static int sdf_layers_fwd(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P,
                           const bf16* pe, bf16* const* hbuf /* hbuf[l] = input buffer of layer l (l>=1) */, float* sdf,
-                          int sdf_ld, float* feat, int feat_ld, cudaStream_t s) {
+                          int sdf_ld, float* feat, int feat_ld, cudaStream_t s, bf16* feat_b16 = nullptr, int feat_b16_ld = 0) {
   for (int l = 0; l < b.top; ++l) {
     TcArgs t = tc_args((int)P, b.Np[l], b.Kp[l], l == 0 ? pe : hbuf[l], l == 0 ? 64 : b.LD, wp + b.wf_off[l], hbuf[l + 1], b.LD, 0);
     t.bias = Wflat + m.b_off[l]; t.epi = TC_BIAS_SOFTPLUS; t.alpha = alpha_of(b, l + 1); t.n_valid = m.out[l];
     if (int rc = launch_tc_gemm(t, s)) return rc;
   }
   const int l = b.top;
-  if (feat) {
-    TcArgs t = tc_args((int)P, b.featN, b.Kp[l], hbuf[l], b.LD, wp + b.wf_off[l], feat, feat_ld, 1);
+  if (feat || feat_b16) {
+    TcArgs t = feat_b16 ? tc_args((int)P, b.featN, b.Kp[l], hbuf[l], b.LD, wp + b.wf_off[l], feat_b16, feat_b16_ld, 0)
+                        : tc_args((int)P, b.featN, b.Kp[l], hbuf[l], b.LD, wp + b.wf_off[l], feat, feat_ld, 1);
     t.bias = Wflat + m.b_off[l] + 1; t.n_valid = m.d_out - 1;
     if (int rc = launch_tc_gemm(t, s)) return rc;
   }
@@ -326,7 +327,7 @@ int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_
 }
 
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
-                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s) {
+                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, bf16* feat_b16, int feat_b16_ld) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   if (P <= 0) return 0;
@@ -339,7 +340,7 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   for (int l = 1; l <= b.top; ++l) hbuf[l] = sv.h(l);
   pe_fwd_bf16_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, sv.pe, 64, 64, b.skip > 0 ? sv.h(b.skip) + b.skw : nullptr, b.LD);
   COPE_CHECK_LAUNCH("pe_fwd_bf16");
-  if (int rc = sdf_layers_fwd(m, b, Wflat, wp, x, P, sv.pe, hbuf, sdf, sdf_ld, feat, feat_ld, s)) return rc;
+  if (int rc = sdf_layers_fwd(m, b, Wflat, wp, x, P, sv.pe, hbuf, sdf, sdf_ld, feat, feat_ld, s, feat_b16, feat_b16_ld)) return rc;
   if (!grad) return 0;
   // ---- reverse sweep
   const int top = b.top;
@@ -370,13 +371,25 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   return 0;
 }
 
+// bf16 [P x LD] slot inside sdf_bwd_bf16's workspace that holds d_feat (written directly by the colour backward in the
+// fused renderer path)
+bf16* sdf_bwd_dfeat_slot(const MlpShape& m, int64_t P, float* ws, int* ld) {
+  SdfB b;
+  if (make_sdfb(m, &b)) return nullptr;
+  bf16* wp = reinterpret_cast<bf16*>(ws);
+  bf16* T = wp + b.w_total;
+  bf16* ZB2 = T + (int64_t)b.top * P * b.LD;
+  *ld = b.LD;
+  return ZB2 + (int64_t)(b.top + 2) * P * b.LD;
+}
+
 // ------------------------------------------------------------------------------------------- SDF backward
 int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, const float* saved, const float* d_sdf,
                  int d_sdf_ld, const float* d_feat, int d_feat_ld, const float* dgrad, float* dWflat, float* dx,
-                 int dx_accumulate, float* ws, cudaStream_t s) {
+                 int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
-  const bool have_dy = d_sdf || d_feat;
+  const bool have_dy = d_sdf || d_feat || d_feat_in_ws;
   if (P <= 0 || (!have_dy && !dgrad)) {
     if (dx && P > 0 && !dx_accumulate) cudaMemsetAsync(dx, 0, sizeof(float) * P * m.d_in, s);
     return 0;
@@ -415,7 +428,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
     // last layer: delta_top = e_0  =>  dW_top[0, :] += sum_p T_top[p, :]
     if (int rc = wcolsum(Tl(top), LD, nullptr, 0, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
   }
-  if (have_dy) {
+  if (have_dy && !d_feat_in_ws) {
     cvt_f32_bf16_kernel<<<g1(P * (r64(featW) / 8)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);
     COPE_CHECK_LAUNCH("cvt_dfeat");
   }
@@ -435,7 +448,7 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         w.P = P; w.Mp = r128(featW); w.Np = r16(m.in[top]); w.m_valid = featW; w.n_valid = m.in[top];
         w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
         w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part;
-        if (d_feat) {
+        if (d_feat || d_feat_in_ws) {
           w.db = dWflat + m.b_off[top] + 1;
           if (int rc = launch_tc_wgrad(w, s)) return rc;
         }
@@ -579,14 +592,15 @@ __device__ __forceinline__ float color_in_elem(const float* x, const float* dv, 
 // one thread = 8 consecutive columns of one row (16-byte stores; feature columns are 32-byte fp32 reads)
 __global__ void color_pack_bf16_kernel(const float* __restrict__ x, const float* __restrict__ dirs, int dirs_group, int Lv,
                                        const float* __restrict__ nrm, const float* __restrict__ feat, int feat_ld, int F,
-                                       int64_t P, bf16* __restrict__ cin, int ld) {
+                                       int64_t P, bf16* __restrict__ cin, int ld, int col0) {
+  // col0 > 0: the first col0 (= F) columns already hold the bf16 features; only the tail is written
   const int pe_w = 3 * (1 + 2 * Lv);
   const int R = 4 + pe_w + 4;
-  const int groups = ld >> 3;
+  const int groups = (ld - col0) >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * groups) return;
   const int64_t p = i / groups;
-  const int c0 = (int)(i - p * groups) * 8;
+  const int c0 = col0 + (int)(i - p * groups) * 8;
   float v[8];
   if (c0 + 8 <= F) {
     const float* f = feat + p * feat_ld + c0;
@@ -655,6 +669,12 @@ static ColSavedB col_saved_b(const ColB& c, int64_t P, float* base) {
   v.H = v.cin + P * c.CK;
   return v;
 }
+bf16* color_cin_slot(const MlpShape& m, int Lv, int64_t P, float* saved, int* ld) {
+  ColB c;
+  if (make_colb(m, Lv, &c)) return nullptr;
+  *ld = c.CK;
+  return col_saved_b(c, P, saved).cin;
+}
 int64_t color_saved_floats_bf16(const MlpShape& m, int64_t P) {
   ColB c;
   if (make_colb(m, -1, &c)) return -1;
@@ -668,7 +688,7 @@ int64_t color_ws_floats_bf16(const MlpShape& m, int64_t P) {
 
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
                    const float* normals, const float* feat, int feat_ld, int64_t P, float* rgb, float* saved, float* ws,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool feat_in_cin) {
   ColB c;
   if (make_colb(m, Lv, &c)) return -1;
   COPE_REQUIRE(m.skip < 0, "bf16 colour path: skip connections are not supported");
@@ -676,7 +696,8 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
   ColSavedB sv = col_saved_b(c, P, saved);
   bf16* wp = reinterpret_cast<bf16*>(ws);
   if (int rc = pack_color(m, c, Wflat, wp, true, false, s)) return rc;
-  color_pack_bf16_kernel<<<g1(P * (c.CK / 8)), 256, 0, s>>>(x, dirs, dirs_group, Lv, normals, feat, feat_ld, c.d_feat, P, sv.cin, c.CK);
+  color_pack_bf16_kernel<<<g1(P * ((feat_in_cin ? c.CK - c.d_feat : c.CK) / 8)), 256, 0, s>>>(
+      x, dirs, dirs_group, Lv, normals, feat, feat_ld, c.d_feat, P, sv.cin, c.CK, feat_in_cin ? c.d_feat : 0);
   COPE_CHECK_LAUNCH("color_pack_bf16");
   for (int l = 0; l < m.n_lin; ++l) {
     const bool last = l == c.top;
@@ -691,7 +712,7 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
 
 int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int dirs_group, int Lv, int64_t P,
                    const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs, float* dnormals,
-                   float* dfeat, int dfeat_ld, float* ws, cudaStream_t s) {
+                   float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, bf16* dfeat_b16, int dfeat_b16_ld) {
   ColB c;
   if (make_colb(m, Lv, &c)) return -1;
   if (P <= 0) return 0;
@@ -731,8 +752,9 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
       if (int rc = launch_tc_gemm(t, s)) return rc;
       dz = nxt; lddz = c.LD;
     } else {
-      if (dfeat) {
-        TcArgs t = tc_args((int)P, r16(F), kt, dz, lddz, wp + c.wt_off[0], dfeat, dfeat_ld, 1);
+      if (dfeat || dfeat_b16) {
+        TcArgs t = dfeat_b16 ? tc_args((int)P, r16(F), kt, dz, lddz, wp + c.wt_off[0], dfeat_b16, dfeat_b16_ld, 0)
+                             : tc_args((int)P, r16(F), kt, dz, lddz, wp + c.wt_off[0], dfeat, dfeat_ld, 1);
         t.n_valid = F;
         if (int rc = launch_tc_gemm(t, s)) return rc;
       }

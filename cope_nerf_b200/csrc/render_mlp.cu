@@ -1,0 +1,66 @@
+// render_core's MLP stage as one call: SDF value + analytic gradient, then the colour network, with the 256-wide
+// feature vector (and its gradient on the way back) handed over in bf16 inside the colour net's input buffer on the
+// tensor-core path — no fp32 round trip, no re-pack.  model/neus_renderer.py:352-358.
+#include "mlp_shape.cuh"
+
+using namespace cope;
+
+extern "C" {
+
+int64_t cope_render_mlp_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
+  const int64_t a = cope_sdf_ws_floats(sd, P, prec), b = cope_color_ws_floats(cd, P, prec);
+  if (a < 0 || b < 0) return -1;
+  MlpShape ms;
+  if (make_shape(sd, &ms)) return -1;
+  return a + b + 2 * P * (int64_t)(ms.d_out - 1) + 1024;     // + fp32 feature / feature-gradient temporaries (strict path)
+}
+
+int cope_render_mlp_fwd(const cope_mlp_desc* sd, const float* sdfW, const cope_mlp_desc* cd, const float* colW, const float* x,
+                        const float* dirs, int dirs_group, int Lv, int64_t P, float* sdf, float* grad, float* rgb,
+                        float* sdf_saved, float* col_saved, float* ws, int prec, cope_stream_t s_) {
+  MlpShape ms, mc;
+  if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
+  if (P <= 0) return 0;
+  cudaStream_t s = as_stream(s_);
+  if (prec == COPE_PREC_BF16) {
+    int ld = 0;
+    __nv_bfloat16* cin = color_cin_slot(mc, Lv, P, col_saved, &ld);
+    COPE_REQUIRE(cin != nullptr, "render_mlp_fwd: colour network shape not supported on the bf16 path");
+    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld)) return rc;
+    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true);
+  }
+  const int F = ms.d_out - 1;
+  float* feat = ws;
+  float* rest = ws + P * (int64_t)F;
+  if (int rc = cope_sdf_fwd(sd, sdfW, x, P, sdf, 1, feat, F, grad, sdf_saved, rest, prec, s_)) return rc;
+  return cope_color_fwd(cd, colW, x, dirs, dirs_group, Lv, grad, feat, F, P, rgb, col_saved, rest, prec, s_);
+}
+
+int cope_render_mlp_bwd(const cope_mlp_desc* sd, const float* sdfW, const cope_mlp_desc* cd, const float* colW, const float* x,
+                        const float* dirs, int dirs_group, int Lv, int64_t P, const float* sdf_saved, const float* col_saved,
+                        const float* d_sdf, float* d_grad, const float* d_rgb, float* dW_sdf, float* dW_col, float* dx,
+                        float* ddirs_pp, float* ws, int prec, cope_stream_t s_) {
+  MlpShape ms, mc;
+  if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
+  if (P <= 0) return 0;
+  cudaStream_t s = as_stream(s_);
+  const int64_t col_ws = cope_color_ws_floats(cd, P, prec);
+  if (prec == COPE_PREC_BF16) {
+    float* ws_sdf = ws + col_ws;
+    int ld = 0;
+    __nv_bfloat16* slot = sdf_bwd_dfeat_slot(ms, P, ws_sdf, &ld);
+    COPE_REQUIRE(slot != nullptr, "render_mlp_bwd: SDF network shape not supported on the bf16 path");
+    if (int rc = color_bwd_bf16(mc, colW, dirs, dirs_group, Lv, P, col_saved, d_rgb, dW_col, dx, ddirs_pp, d_grad, nullptr, 0, ws, s,
+                                slot, ld))
+      return rc;
+    return sdf_bwd_bf16(ms, sdfW, x, P, sdf_saved, d_sdf, 1, nullptr, 0, d_grad, dW_sdf, dx, 1, ws_sdf, s, true);
+  }
+  const int F = ms.d_out - 1;
+  float* dfeat = ws;
+  float* rest = ws + P * (int64_t)F;
+  if (int rc = cope_color_bwd(cd, colW, dirs, dirs_group, Lv, P, col_saved, d_rgb, dW_col, dx, ddirs_pp, d_grad, dfeat, F, rest, prec, s_))
+    return rc;
+  return cope_sdf_bwd(sd, sdfW, x, P, sdf_saved, d_sdf, 1, dfeat, F, d_grad, dW_sdf, dx, 1, rest, prec, s_);
+}
+
+}  // extern "C"

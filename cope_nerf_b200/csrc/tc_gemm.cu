@@ -168,15 +168,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
   float* s_bias = reinterpret_cast<float*>(sA + nstages * kAStageBytes);
   float* s_r1w = s_bias + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_r1w + 256);
-  uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* a_empty = bars + 1 + kStages;
-  uint64_t* acc_full = bars + 1 + 2 * kStages;
+  uint64_t* w_full = bars;                 // [5] one per 64-wide K slab of W
+  uint64_t* a_full = bars + 5;
+  uint64_t* a_empty = bars + 5 + kStages;
+  uint64_t* acc_full = bars + 5 + 2 * kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (threadIdx.x == 0) {
-    mbar_init(w_full, 1);
+    for (int k = 0; k < 5; ++k) mbar_init(w_full + k, 1);
     for (int s = 0; s < nstages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 8); }
     fence_barrier_init();
@@ -198,10 +198,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
     // (2-D tiled TMA, 64 x 128 bf16 boxes, 128B swizzle; rows past M are zero-filled by the tensor map)
     if (threadIdx.x == 256) {
       tma_prefetch_desc(&tmA);
-      mbar_arrive_expect_tx(w_full, wbytes);
-      const uint32_t chunk = 32768;
-      for (uint32_t off = 0; off < wbytes; off += chunk)
-        bulk_g2s(sW + off, reinterpret_cast<const uint8_t*>(a.Bp) + off, min(chunk, wbytes - off), w_full);
+      const uint32_t slab = (uint32_t)a.N * 128;          // one K chunk of W: [8 k-cores][N][8] bf16
+      for (int k = 0; k < nkc; ++k) {
+        mbar_arrive_expect_tx(w_full + k, slab);
+        bulk_g2s(sW + k * slab, reinterpret_cast<const uint8_t*>(a.Bp) + (size_t)k * slab, slab, w_full + k);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      mbar_wait(w_full, 0);
       const uint32_t idesc = idesc_bf16(kTileM, a.N, 0, 0);
+      bool w_ready = false;
       const uint32_t sWa = smem_u32(sW);
       const uint32_t b_lbo = (uint32_t)a.N * 16;     // K-adjacent cores of W: one full [N][8] slab apart
       int stage = 0;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kc = 0; kc < nkc; ++kc) {
+          if (!w_ready) mbar_wait(w_full + kc, 0);          // first tile only: this K slab of W has landed
           mbar_wait(a_full + stage, phase);
           tc_fence_after();
           const uint32_t sAa = smem_u32(sA + stage * kAStageBytes);
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const TcArgs a, 
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(acc_full + acc);
+        w_ready = true;
         acc ^= 1;
         if (acc == 0) accp ^= 1;
       }

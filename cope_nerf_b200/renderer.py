@@ -56,24 +56,21 @@ class _RenderCoreFn(torch.autograd.Function):
         near, far = near.contiguous().float(), far.contiguous().float()
         tstep = time_step.reshape(-1)[:1].contiguous().float()
         prec_s, prec_c = sdf_net.precision, col_net.precision
-        d_feat = sdf_net._dims_out[-1] - 1
+        if prec_s != prec_c:
+            raise L.CopeError("SDF and colour networks must use the same precision inside NeuSRenderer")
 
         pts = _f32(P, 4, device=dev)
         dists, mid_z = _f32(N, S, device=dev), _f32(N, S, device=dev)
         L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
                n_coarse, N, S, 1, L.ptr(pts), L.ptr(dists), L.ptr(mid_z), s)
 
-        sdf, feat, grad = _f32(P, 1, device=dev), _f32(P, d_feat, device=dev), _f32(P, 4, device=dev)
+        sdf, grad, rgb = _f32(P, 1, device=dev), _f32(P, 4, device=dev), _f32(P, 3, device=dev)
         sdf_saved = _f32(L.query("cope_sdf_saved_floats", sdf_net.desc, P, 1, prec_s), device=dev)
-        ws = L.scratch(max(L.query("cope_sdf_ws_floats", sdf_net.desc, P, prec_s),
-                           L.query("cope_color_ws_floats", col_net.desc, P, prec_c)), dev)
-        L.call("cope_sdf_fwd", sdf_net.desc, L.ptr(sdf_flat), L.ptr(pts), P, L.ptr(sdf), 1, L.ptr(feat), d_feat,
-               L.ptr(grad), L.ptr(sdf_saved), L.ptr(ws), prec_s, s)
-
-        rgb = _f32(P, 3, device=dev)
         col_saved = _f32(L.query("cope_color_saved_floats", col_net.desc, P, prec_c), device=dev)
-        L.call("cope_color_fwd", col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S, col_net.multires_view,
-               L.ptr(grad), L.ptr(feat), d_feat, P, L.ptr(rgb), L.ptr(col_saved), L.ptr(ws), prec_c, s)
+        ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
+        L.call("cope_render_mlp_fwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
+               col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(ws),
+               prec_s, s)
 
         weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
         color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
@@ -100,7 +97,6 @@ class _RenderCoreFn(torch.autograd.Function):
         N, S, n_coarse, cos_anneal, eval_mode = ctx.cfg
         P, dev, s = N * S, z.device, L.stream()
         prec_s, prec_c = sdf_net.precision, col_net.precision
-        d_feat_w = sdf_net._dims_out[-1] - 1
         need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
 
         # upstream of the analytic gradient (normals | sdf_flow), accumulated into by compositing + colour net
@@ -119,22 +115,18 @@ class _RenderCoreFn(torch.autograd.Function):
         if d_sdf_up is not None:
             d_sdf = d_sdf + d_sdf_up.reshape(P, 1)
 
-        ws = L.scratch(max(L.query("cope_sdf_ws_floats", sdf_net.desc, P, prec_s),
-                           L.query("cope_color_ws_floats", col_net.desc, P, prec_c)), dev)
+        ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
         d_col_flat = torch.zeros_like(col_flat)
         d_sdf_flat = torch.zeros_like(sdf_flat)
-        d_feat = _f32(P, d_feat_w, device=dev)
         d_pts = d_dirs_pp = None
         if need_rays:
             d_pts = torch.zeros(P, 4, dtype=torch.float32, device=dev)
             if d_points is not None:
                 d_pts[:, :3] = d_points.reshape(P, 3)
             d_dirs_pp = _f32(P, 3, device=dev)
-        L.call("cope_color_bwd", col_net.desc, L.ptr(col_flat), L.ptr(rays_d), S, col_net.multires_view, P,
-               L.ptr(col_saved), L.ptr(d_rgb), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(d_grad),
-               L.ptr(d_feat), d_feat_w, L.ptr(ws), prec_c, s)
-        L.call("cope_sdf_bwd", sdf_net.desc, L.ptr(sdf_flat), L.ptr(pts), P, L.ptr(sdf_saved), L.ptr(d_sdf), 1,
-               L.ptr(d_feat), d_feat_w, L.ptr(d_grad), L.ptr(d_sdf_flat), L.ptr(d_pts), 1, L.ptr(ws), prec_s, s)
+        L.call("cope_render_mlp_bwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
+               col_net.multires_view, P, L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb),
+               L.ptr(d_sdf_flat), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(ws), prec_s, s)
         d_rays_o = None
         if need_rays:
             d_rays_o = _f32(N, 3, device=dev)

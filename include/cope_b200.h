@@ -108,6 +108,20 @@ int cope_color_bwd(const cope_mlp_desc* d, const float* Wflat, const float* dirs
                    int64_t P, const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs,
                    float* dnormals, float* dfeat, int dfeat_ld, float* ws, int prec, cope_stream_t s);
 
+/* ---- render_core's MLP stage in one call (model/neus_renderer.py:352-358): sdf [P], grad [P x 4] (= .gradient()),
+ * rgb [P x 3].  On the bf16 path the feature vector / its gradient are handed between the two networks in bf16.
+ * Backward: d_sdf [P] (or NULL), d_grad [P x 4] holds the upstream gradient of `grad` on entry and is ACCUMULATED with
+ * the colour net's contribution, d_rgb [P x 3]; dW_sdf / dW_col ACCUMULATED; dx [P x 4] ACCUMULATED (value path only) or
+ * NULL; ddirs_pp [P x 3] per-point view-direction gradient (OVERWRITTEN) or NULL. */
+int64_t cope_render_mlp_ws_floats(const cope_mlp_desc* sdf_desc, const cope_mlp_desc* col_desc, int64_t P, int prec);
+int cope_render_mlp_fwd(const cope_mlp_desc* sdf_desc, const float* sdfW, const cope_mlp_desc* col_desc, const float* colW,
+                        const float* x, const float* dirs, int dirs_group, int Lv, int64_t P, float* sdf, float* grad,
+                        float* rgb, float* sdf_saved, float* col_saved, float* ws, int prec, cope_stream_t s);
+int cope_render_mlp_bwd(const cope_mlp_desc* sdf_desc, const float* sdfW, const cope_mlp_desc* col_desc, const float* colW,
+                        const float* x, const float* dirs, int dirs_group, int Lv, int64_t P, const float* sdf_saved,
+                        const float* col_saved, const float* d_sdf, float* d_grad, const float* d_rgb, float* dW_sdf,
+                        float* dW_col, float* dx, float* ddirs_pp, float* ws, int prec, cope_stream_t s);
+
 /* ---- ray points (neus_renderer.py:337-350 / :495-498 / :285) --------------------------------------
  * pts_time [N*S x 4] = (o + d * zz, t) with zz = z + dists/2 if use_mid else z.
  * dists / mid_z [N x S] may be NULL.  The last interval is sample_dist = (far[0]-near[0])/n_coarse,
