@@ -8,12 +8,14 @@
 //   * the raw coordinates enter layer 0 / the colour net as hi + lo bf16 pairs (duplicated weight columns), so the
 //     position is not quantised to 8 bits; everything that touches the PE Jacobian (ge0/ge1, dx, d_dirs) stays fp32
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
 #include "mlp_shape.cuh"
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
+#include "sdf_fused.cuh"
 
 namespace cope {
 
@@ -280,8 +282,8 @@ int64_t sdf_saved_floats_bf16(const MlpShape& m, int64_t P, int with_grad) {
 int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
-  // packed weights + (T: top, ZB2: top, ZB: 2, dyb: 1, t0 + 3 spare) bf16 [P x LD] + 4 fp32 [P x 64]
-  int64_t bf = (int64_t)b.w_total + P * ((int64_t)(2 * b.top + 4) * b.LD + 64);
+  // packed weights + (T: top, ZB2: top, ZB: top, dyb: 1, spare: 1) bf16 [P x LD] + t0 bf16 [P x 64] + 4 fp32 [P x 64]
+  int64_t bf = (int64_t)b.w_total + P * ((int64_t)(3 * b.top + 2) * b.LD + 64);
   return (bf + 1) / 2 + P * 4 * 64 + tc_wgrad_part_floats() + 1024;
 }
 
@@ -304,6 +306,56 @@ static int sdf_layers_fwd(const MlpShape& m, const SdfB& b, const float* Wflat, 
   TcArgs t = tc_args((int)P, 16, b.Kp[l], hbuf[l], b.LD, wp + b.wtop_sdf_off, sdf, sdf_ld, 1);
   t.bias = Wflat + m.b_off[l]; t.n_valid = 1;
   return launch_tc_gemm(t, s);
+}
+
+
+// ------------------------------------------------------------------------------------------- fused chains (sdf_fused.cu)
+// COPE_NO_FUSED=1 (or "all") disables every fused chain; a list such as "fwd,adj" disables single passes (A/B tests)
+static bool fused_enabled(const MlpShape& m, const SdfB& b, const char* pass) {
+  const char* e = getenv("COPE_NO_FUSED");
+  if (e && (strstr(e, pass) || strstr(e, "all") || !strcmp(e, "1"))) return false;
+  return b.LD == 256 && sdf_fused_supported(m);
+}
+static void fz_common(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P, FzArgs* a) {
+  a->P = P; a->x = x; a->Wflat = Wflat; a->wp = wp;
+  a->n_lin = m.n_lin; a->skip = m.skip; a->skw = b.skw; a->pe_w = m.pe_w; a->d_in = m.d_in; a->L = m.L;
+  for (int l = 0; l < m.n_lin; ++l) a->b_off[l] = m.b_off[l];
+  a->w_top_off = m.w_off[b.top];
+}
+static void fz_job(FzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a, int commit) {
+  FzJob& j = a->jobs[a->n_jobs++];
+  j.w_off = (uint32_t)w_off; j.Np = (uint16_t)Np; j.Kp = (uint16_t)Kp; j.acc = (uint8_t)acc; j.wait_a = (uint8_t)wait_a;
+  j.commit = (uint8_t)commit; j.pad = 0;
+}
+
+// value pass + reverse sweep in ONE kernel: writes sv.pe, sv.h(1..top), sv.dl(0..top-1), sdf, the bf16 feature block and
+// ge0 / ge1 (gradient w.r.t. the PE)
+static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P,
+                         const SdfSavedB& sv, float* sdf, int sdf_ld, bf16* feat_b16, int feat_b16_ld, float* ge0, float* ge1,
+                         cudaStream_t s) {
+  FzArgs a{};
+  fz_common(m, b, Wflat, wp, x, P, &a);
+  const int top = b.top;
+  for (int l = 0; l < top; ++l) fz_job(&a, b.wf_off[l], b.Np[l], b.Kp[l], l & 1, 1, (l & 1) + 1);
+  fz_job(&a, b.wf_off[top], b.featN, b.Kp[top], top & 1, 1, 0);
+  fz_job(&a, b.wtop_sdf_off, 16, b.Kp[top], (top & 1) ^ 1, 0, (top & 1) + 1);
+  for (int l = top - 1; l >= 0; --l) {
+    const int st = top + 1 + (top - 1 - l);
+    fz_job(&a, b.wt_off[l], l == 0 ? 64 : r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
+  }
+  a.sdf = sdf; a.sdf_ld = sdf_ld; a.has_feat = feat_b16 != nullptr; a.ge0 = ge0; a.ge1 = ge1;
+  FzMaps maps{};
+  const uint64_t LD = (uint64_t)b.LD, Pu = (uint64_t)P;
+  if (int rc = make_tmap3(sv.pe, 64, Pu, 1, 64, Pu * 64, &maps.in0)) return rc;
+  if (int rc = make_tmap3(sv.H, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.H)) return rc;
+  if (int rc = make_tmap3(sv.D, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.D)) return rc;
+  if (feat_b16) {
+    if (int rc = make_tmap3(feat_b16, (uint64_t)b.featN, Pu, 1, (uint64_t)feat_b16_ld, Pu * (uint64_t)feat_b16_ld, &maps.out)) return rc;
+  } else {
+    maps.out = maps.H;
+  }
+  maps.Z2 = maps.H;
+  return launch_sdf_fused(FZ_FWD, a, maps, s);
 }
 
 int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s) {
@@ -336,6 +388,12 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   float* ge0 = reinterpret_cast<float*>(wp + b.w_total);
   float* ge1 = ge0 + P * 64;
   if (int rc = pack_sdf(m, b, Wflat, wp, true, grad != nullptr, s)) return rc;
+  if (grad && !feat && fused_enabled(m, b, "fwd")) {
+    if (int rc = sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, feat_b16, feat_b16_ld, ge0, ge1, s)) return rc;
+    pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, ge0, 64, b.skip > 0 ? ge1 : nullptr, 64, grad, m.d_in, 0);
+    COPE_CHECK_LAUNCH("pe_vjp");
+    return 0;
+  }
   bf16* hbuf[COPE_MAX_LIN + 1] = {nullptr};
   for (int l = 1; l <= b.top; ++l) hbuf[l] = sv.h(l);
   pe_fwd_bf16_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, sv.pe, 64, 64, b.skip > 0 ? sv.h(b.skip) + b.skw : nullptr, b.LD);
@@ -371,6 +429,35 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   return 0;
 }
 
+// layer-by-layer tangent pass: T_{l+1} = alpha * (W_l T_l) * sp ; zb2_l = (W_l T_l) * delta_l * 100 (1 - sp)
+static int sdf_tangent_layered(const MlpShape& m, const SdfB& b, const SdfSavedB& sv, const bf16* wp, const float* x, int64_t P,
+                               const float* dgrad, bf16* T, bf16* t0, bf16* ZB2, float* dWflat, cudaStream_t s) {
+  const int top = b.top, LD = b.LD;
+  auto Tl = [&](int l) { return l == 0 ? t0 : T + (int64_t)(l - 1) * P * LD; };
+  auto ldT = [&](int l) { return l == 0 ? 64 : LD; };
+  auto zb2 = [&](int l) { return ZB2 + (int64_t)l * P * LD; };
+  pe_jvp_bf16_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, dgrad, t0, 64, 64, b.skip > 0 ? Tl(b.skip) + b.skw : nullptr, LD);
+  COPE_CHECK_LAUNCH("pe_jvp_bf16");
+  for (int l = 0; l < top; ++l) {
+    TcArgs t = tc_args((int)P, b.Np[l], b.Kp[l], Tl(l), ldT(l), wp + b.wf_off[l], Tl(l + 1), LD, 0);
+    t.epi = TC_TANGENT; t.alpha = alpha_of(b, l + 1); t.H = sv.h(l + 1); t.ldh = LD; t.hscale = hscale_of(b, l + 1);
+    t.D = sv.dl(l); t.ldd = LD; t.out2 = zb2(l); t.ldo2 = LD; t.out2_f32 = 0; t.n_valid = m.out[l];
+    if (int rc = launch_tc_gemm(t, s)) return rc;
+  }
+  if (b.skip > 0 && b.skw < LD) {
+    zero_cols_bf16_kernel<<<g1(P * (LD - b.skw)), 256, 0, s>>>(zb2(b.skip - 1), LD, P, b.skw, LD);
+    COPE_CHECK_LAUNCH("zero_cols");
+  }
+  // last layer: delta_top = e_0  =>  dW_top[0, :] += sum_p T_top[p, :]
+  return wcolsum(Tl(top), LD, nullptr, 0, P, m.in[top], dWflat + m.w_off[top], s);
+}
+
+// float offset of eb0 ([P x 64] fp32, followed by eb1) inside sdf_bwd_bf16's workspace (kernel-level tests)
+int64_t sdf_bwd_eb_offset(const MlpShape& m, int64_t P) {
+  SdfB b;
+  if (make_sdfb(m, &b)) return -1;
+  return ((int64_t)b.w_total + P * ((int64_t)(3 * b.top + 1) * b.LD + 64)) / 2;
+}
 // bf16 [P x LD] slot inside sdf_bwd_bf16's workspace that holds d_feat (written directly by the colour backward in the
 // fused renderer path)
 bf16* sdf_bwd_dfeat_slot(const MlpShape& m, int64_t P, float* ws, int* ld) {
@@ -380,7 +467,7 @@ bf16* sdf_bwd_dfeat_slot(const MlpShape& m, int64_t P, float* ws, int* ld) {
   bf16* T = wp + b.w_total;
   bf16* ZB2 = T + (int64_t)b.top * P * b.LD;
   *ld = b.LD;
-  return ZB2 + (int64_t)(b.top + 2) * P * b.LD;
+  return ZB2 + (int64_t)(2 * b.top) * P * b.LD;
 }
 
 // ------------------------------------------------------------------------------------------- SDF backward
@@ -399,8 +486,9 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   bf16* wp = reinterpret_cast<bf16*>(ws);
   bf16* T = wp + b.w_total;                               // T_l, l = 1..top   -> T + (l-1) P LD
   bf16* ZB2 = T + (int64_t)top * P * LD;                  // zb2_l, l = 0..top-1
-  bf16* ZB[2] = {ZB2 + (int64_t)top * P * LD, ZB2 + (int64_t)(top + 1) * P * LD};
-  bf16* dyb = ZB[1] + (int64_t)P * LD;                    // bf16 copy of d_feat
+  bf16* ZBall = ZB2 + (int64_t)top * P * LD;              // zb_l, l = 0..top-1 (fused chain); the layer-by-layer path
+  bf16* ZB[2] = {ZBall, ZBall + (int64_t)P * LD};         // ping-pongs between the first two
+  bf16* dyb = ZBall + (int64_t)top * P * LD;              // bf16 copy of d_feat
   bf16* t0 = dyb + (int64_t)P * LD;                       // [P x 64]
   float* eb0 = reinterpret_cast<float*>(t0 + (int64_t)P * 64);
   float* eb1 = eb0 + P * 64;
@@ -411,22 +499,84 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   if (int rc = pack_sdf(m, b, Wflat, wp, dgrad != nullptr, true, s)) return rc;
   const int featW = m.d_out - 1;
 
-  if (dgrad) {
-    // ---- tangent pass: T_{l+1} = alpha * (W_l T_l) * sp ; zb2_l = (W_l T_l) * delta_l * 100 (1 - sp)
-    pe_jvp_bf16_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, dgrad, t0, 64, 64, b.skip > 0 ? Tl(b.skip) + b.skw : nullptr, LD);
-    COPE_CHECK_LAUNCH("pe_jvp_bf16");
-    for (int l = 0; l < top; ++l) {
-      TcArgs t = tc_args((int)P, b.Np[l], b.Kp[l], Tl(l), ldT(l), wp + b.wf_off[l], Tl(l + 1), LD, 0);
-      t.epi = TC_TANGENT; t.alpha = alpha_of(b, l + 1); t.H = sv.h(l + 1); t.ldh = LD; t.hscale = hscale_of(b, l + 1);
-      t.D = sv.dl(l); t.ldd = LD; t.out2 = zb2(l); t.ldo2 = LD; t.out2_f32 = 0; t.n_valid = m.out[l];
-      if (int rc = launch_tc_gemm(t, s)) return rc;
-    }
-    if (b.skip > 0 && b.skw < LD) {
-      zero_cols_bf16_kernel<<<g1(P * (LD - b.skw)), 256, 0, s>>>(zb2(b.skip - 1), LD, P, b.skw, LD);
-      COPE_CHECK_LAUNCH("zero_cols");
-    }
-    // last layer: delta_top = e_0  =>  dW_top[0, :] += sum_p T_top[p, :]
+  const uint64_t LDu = (uint64_t)LD, Pu = (uint64_t)P;
+  const bool fused_tan = dgrad && fused_enabled(m, b, "tan");
+  if (fused_tan) {
+    // ---- fused tangent sweep: T_1..T_top, zb2_0..zb2_{top-1} in one kernel
+    FzMaps maps{};
+    if (int rc = make_tmap3(sv.H, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.H)) return rc;
+    if (int rc = make_tmap3(sv.D, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.D)) return rc;
+    if (int rc = make_tmap3(ZB2, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.Z2)) return rc;
+    FzArgs a{};
+    fz_common(m, b, Wflat, wp, x, P, &a);
+    a.g = dgrad;
+    for (int l = 0; l < top; ++l) fz_job(&a, b.wf_off[l], b.Np[l], b.Kp[l], l & 1, 1, (l & 1) + 1);
+    if (int rc = make_tmap3(t0, 64, Pu, 1, 64, Pu * 64, &maps.in0)) return rc;
+    if (int rc = make_tmap3(T, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.out)) return rc;
+    if (int rc = launch_sdf_fused(FZ_TAN, a, maps, s)) return rc;
     if (int rc = wcolsum(Tl(top), LD, nullptr, 0, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
+  }
+  if (dgrad && (d_feat || d_feat_in_ws) && fused_enabled(m, b, "adj")) {
+    // ---- fused adjoint sweep (stores every zb_l), then all weight gradients, then the value-path adjoint for dx
+    FzMaps maps{};
+    if (int rc = make_tmap3(sv.H, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.H)) return rc;
+    if (int rc = make_tmap3(sv.D, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.D)) return rc;
+    if (int rc = make_tmap3(ZB2, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.Z2)) return rc;
+    if (!fused_tan) {
+      if (int rc = sdf_tangent_layered(m, b, sv, wp, x, P, dgrad, T, t0, ZB2, dWflat, s)) return rc;
+    }
+    if (!d_feat_in_ws) {
+      cvt_f32_bf16_kernel<<<g1(P * (r64(featW) / 8)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);
+      COPE_CHECK_LAUNCH("cvt_dfeat");
+    }
+    if (int rc = make_tmap3(dyb, LDu, Pu, 1, LDu, Pu * LDu, &maps.in0)) return rc;
+    if (int rc = make_tmap3(ZBall, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.out)) return rc;
+    for (int pass = 0; pass < (dx ? 2 : 1); ++pass) {
+      FzArgs a{};
+      fz_common(m, b, Wflat, wp, x, P, &a);
+      a.d_sdf = d_sdf; a.d_sdf_ld = d_sdf_ld; a.eb0 = eb0; a.eb1 = eb1;
+      a.has_d = pass == 0; a.store_out = pass == 0; a.want_e = pass == 1;
+      if (const char* dbg = getenv("COPE_DBG_ADJ")) { const int f = atoi(dbg); if (pass == 1) { if (f & 1) a.has_d = 1; if (f & 2) a.store_out = 1; } if (pass == 0 && (f & 4)) a.want_e = 1; }
+      fz_job(&a, b.wt_off[top], r16(m.in[top]), r64(featW), 0, 2, 1);
+      for (int l = top - 1; l >= 1; --l) {
+        const int st = top - l;
+        fz_job(&a, b.wt_off[l], r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
+      }
+      if (a.want_e) fz_job(&a, b.wt_off[0], 64, r64(m.out[0]), top & 1, 1, (top & 1) + 1);
+      if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, s)) return rc;
+      if (pass == 0) {
+        // ---- weight / bias gradients from the stored adjoints
+        {
+          TcWgradArgs w{};
+          w.P = P; w.Mp = r128(featW); w.Np = r16(m.in[top]); w.m_valid = featW; w.n_valid = m.in[top];
+          w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
+          w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part; w.db = dWflat + m.b_off[top] + 1;
+          if (int rc = launch_tc_wgrad(w, s)) return rc;
+          if (d_sdf) {
+            if (int rc = wcolsum(sv.h(top), LD, d_sdf, d_sdf_ld, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
+            sum_strided_kernel<<<(unsigned)std::min<int64_t>(296, ceil_div(P, 256)), 256, 0, s>>>(d_sdf, d_sdf_ld, P, dWflat + m.b_off[top]);
+            COPE_CHECK_LAUNCH("colsum_dsdf");
+          }
+        }
+        for (int l = top - 1; l >= 0; --l) {
+          TcWgradArgs w{};
+          w.P = P; w.Mp = r128(m.out[l]); w.Np = l == 0 ? 64 : r16(m.in[l]); w.m_valid = m.out[l];
+          w.n_valid = l == 0 ? m.pe_w : m.in[l];
+          w.X[0] = ZBall + (int64_t)l * P * LD; w.ldx[0] = LD; w.Y[0] = sv.in(l); w.ldy[0] = sv.ld_in(l);
+          w.X[1] = sv.dl(l); w.ldx[1] = LD; w.Y[1] = Tl(l); w.ldy[1] = ldT(l); w.n_pairs = 2;
+          w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part; w.db = dWflat + m.b_off[l];
+          if (int rc = launch_tc_wgrad(w, s)) return rc;
+        }
+      } else {
+        pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, eb0, 64, b.skip > 0 ? eb1 : nullptr, 64, dx, m.d_in, dx_accumulate);
+        COPE_CHECK_LAUNCH("pe_vjp");
+      }
+    }
+    return 0;
+  }
+
+  if (dgrad && !fused_tan) {
+    if (int rc = sdf_tangent_layered(m, b, sv, wp, x, P, dgrad, T, t0, ZB2, dWflat, s)) return rc;
   }
   if (have_dy && !d_feat_in_ws) {
     cvt_f32_bf16_kernel<<<g1(P * (r64(featW) / 8)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);

@@ -5,7 +5,16 @@
 
 using namespace cope;
 
+namespace cope { int64_t sdf_bwd_eb_offset(const MlpShape& m, int64_t P); }
+
 extern "C" {
+
+/* test hook: float offset (inside the ws of cope_render_mlp_bwd) of the [P x 64] fp32 PE-gradient buffers eb0, eb1 */
+int64_t cope_dbg_render_bwd_eb_offset(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P) {
+  MlpShape ms;
+  if (make_shape(sd, &ms)) return -1;
+  return cope_color_ws_floats(cd, P, COPE_PREC_BF16) + sdf_bwd_eb_offset(ms, P);
+}
 
 int64_t cope_render_mlp_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
   const int64_t a = cope_sdf_ws_floats(sd, P, prec), b = cope_color_ws_floats(cd, P, prec);

@@ -1,0 +1,649 @@
+// Fused SDF training chains for the bf16 tcgen05 path (reference architecture: 8 x 256 hidden, skip at 4, 4-D input).
+//
+// One persistent CTA per SM walks 128-point tiles.  The [128 x 256] bf16 activation / adjoint tile stays in shared
+// memory (four 128B-swizzled K-major panels) through a whole pass over the layers; only what a LATER pass needs is
+// moved to HBM, by TMA, straight from / into the swizzled panels:
+//
+//   FZ_FWD  PE -> 8 softplus layers (TMA-store H_1..H_8) -> sdf + feature -> reverse sweep of d sdf / dx
+//           (TMA-load H_l back, TMA-store delta_l) -> ge0 / ge1 (fp32 gradient w.r.t. the PE)
+//   FZ_TAN  tangent sweep of the double backward: T_{l+1} = a (W_l T_l) sp_{l+1},  zb2_l = (W_l T_l) delta_l 100 (1 - sp_{l+1})
+//   FZ_ADJ  adjoint sweep: zb_{l-1} = a (W_l^T zb_l) sp_l + zb2_{l-1}; eb0 / eb1 = gradient w.r.t. the PE
+//
+// Warp roles: 0-15 epilogue (4 per TMEM lane quarter; each owns a 16-column slab of every 64-column panel),
+// 16 weight producer (bulk TMA of 16 KB K=32 chunks into a 3-deep ring), 17 tcgen05.mma issuer + TMEM owner,
+// 18 TMA-store issuer, 19 auxiliary-tile producer (H / delta / zb2 panels into a 4-deep ring).
+// The MMAs of layer l+1 start on K-panel j as soon as the epilogue of layer l has written panel j.
+#include "sdf_fused.cuh"
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace cope {
+using namespace tc;
+
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kWProd = 16, kMma = 17, kStore = 18, kAuxW = 19;
+constexpr int kThreads = 20 * 32;
+constexpr int kPanel = 128 * 128;        // 128 rows x 64 bf16
+constexpr int kWStage = 256 * 32 * 2;    // N = 256 x K = 32
+constexpr int kWRing = 3, kAuxRing = 4, kStgRing = 2;
+constexpr int oA = 0;
+constexpr int oW = oA + 4 * kPanel;
+constexpr int oAux = oW + kWRing * kWStage;
+constexpr int oStg = oAux + kAuxRing * kPanel;
+constexpr int oBias = oStg + kStgRing * kPanel;
+constexpr int oBars = oBias + COPE_MAX_LIN * 256 * 4;
+constexpr int kSmem = oBars + 256;
+static_assert(kSmem <= 232448, "fused chain: shared memory budget");
+
+constexpr float kC2 = -kSoftplusBeta * 1.4426950408889634f;   // exp(-100 h) = 2^(kC2 h)
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(beta=100)(a) = max(a, 0) + log1p(u) / 100, u = exp(-100 |a|): ONE MUFU; log1p(u)/u on (0, 1] is a degree-4
+// minimax polynomial (max rel. error 6e-5, far below the bf16 rounding of the stored activation).  Above torch's
+// threshold (100 a > 20) u < 2.1e-9 and the result equals a in fp32.
+__device__ __forceinline__ float softplus_poly(float a) {
+  const float u = ex2(fabsf(a) * kC2);
+  float q = fmaf(u, 0.0415511144734499e-2f, -0.15783837660869504e-2f);
+  q = fmaf(u, q, 0.3065610999388736e-2f);
+  q = fmaf(u, q, -0.49703084266368813e-2f);
+  q = fmaf(u, q, 0.9999449934273398e-2f);
+  return fmaf(u, q, fmaxf(a, 0.0f));
+}
+
+// byte offset of 16-byte chunk c8 (8 bf16) of row r inside one 128B-swizzled panel
+__device__ __forceinline__ uint32_t pan_off(int r, int c8) { return (uint32_t)r * 128 + (uint32_t)((c8 ^ (r & 7)) << 4); }
+// scalar element k (0..255) of row r inside the 4-panel tile
+__device__ __forceinline__ void put_elem(uint8_t* tile, int r, int k, float v) {
+  *reinterpret_cast<bf16*>(tile + (k >> 6) * kPanel + pan_off(r, (k & 63) >> 3) + (k & 7) * 2) = __float2bfloat16(v);
+}
+__device__ __forceinline__ void write16(uint8_t* panel, int r, int part, const float (&v)[16]) {
+  *reinterpret_cast<uint4*>(panel + pan_off(r, part * 2)) =
+      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  *reinterpret_cast<uint4*>(panel + pan_off(r, part * 2 + 1)) =
+      make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+struct Pk16 { uint32_t w[8]; };   // 16 bf16
+__device__ __forceinline__ Pk16 read16(const uint8_t* panel, int r, int part) {
+  const uint4 a = *reinterpret_cast<const uint4*>(panel + pan_off(r, part * 2));
+  const uint4 b = *reinterpret_cast<const uint4*>(panel + pan_off(r, part * 2 + 1));
+  Pk16 p;
+  p.w[0] = a.x; p.w[1] = a.y; p.w[2] = a.z; p.w[3] = a.w; p.w[4] = b.x; p.w[5] = b.y; p.w[6] = b.z; p.w[7] = b.w;
+  return p;
+}
+__device__ __forceinline__ float pk_get(const Pk16& p, int i) {
+  const uint32_t w = p.w[i >> 1];
+  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
+}
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct Bars {
+  uint64_t *w_full, *w_empty, *aux_full, *aux_empty, *a_ready, *acc_full, *stg_full, *stg_empty, *a_free, *a_init, *tile_done,
+      *h_stored, *epi_done;
+};
+
+// epilogue-side view of the rings
+struct EpiCtx {
+  uint8_t *sA, *sAux, *sStg;
+  Bars B;
+  int r, q, part, lane;
+  uint32_t ev, auxc, stgc, accp;
+  uint32_t tmem_base;
+
+  __device__ __forceinline__ void begin_event() {          // about to overwrite A panels: the previous event's TMA stores
+    if (ev > 0) mbar_wait(B.a_free, (ev - 1) & 1);         // must have finished reading them
+    ++ev;
+  }
+  __device__ __forceinline__ void panel_done(int j) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(B.a_ready + j);
+  }
+  __device__ __forceinline__ uint32_t wait_acc(int b) {
+    mbar_wait(B.acc_full + b, (accp >> b) & 1);
+    accp ^= 1u << b;
+    tc_fence_after();
+    return tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
+  }
+  // wait for the next auxiliary panel and pull this thread's 16 values; the slot is handed back (aux_release) only after
+  // the values have been CONSUMED: releasing right after the loads were issued let the refill overtake them
+  __device__ __forceinline__ Pk16 aux_take() {
+    const uint32_t slot = auxc % kAuxRing, par = (auxc / kAuxRing) & 1;
+    mbar_wait(B.aux_full + slot, par);
+    ++auxc;
+    return read16(sAux + slot * kPanel, r, part);
+  }
+  __device__ __forceinline__ void aux_release(int n) {     // the n most recently taken slots
+    __syncwarp();
+    if (lane == 0)
+      for (int k = n; k >= 1; --k) mbar_arrive(B.aux_empty + ((auxc - k) % kAuxRing));
+  }
+  __device__ __forceinline__ void stg_put(const float (&v)[16]) {
+    const uint32_t slot = stgc % kStgRing, par = (stgc / kStgRing) & 1;
+    mbar_wait(B.stg_empty + slot, par ^ 1);
+    write16(sStg + slot * kPanel, r, part, v);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(B.stg_full + slot);
+    ++stgc;
+  }
+};
+
+// positional-encoding columns of input dimension dd (this thread's), value or Jacobian-vector product:
+//   TAN == false: col dd = x, sin block k = sin(2^k x), cos block k = cos(2^k x)
+//   TAN == true : col dd = g, sin block k = 2^k cos(2^k x) g, cos block k = -2^k sin(2^k x) g
+template <bool TAN, class F>
+__device__ __forceinline__ void pe_cols(float xv, float gv, int dd, int d_in, int L, F&& emit) {
+  emit(dd, TAN ? gv : xv);
+  float sn, cs;
+  sincosf(xv, &sn, &cs);
+  float f = 1.0f;
+  for (int k = 0; k < L; ++k) {
+    const int ks = d_in * (1 + 2 * k) + dd, kc = d_in * (2 + 2 * k) + dd;
+    if (TAN) { emit(ks, f * cs * gv); emit(kc, -f * sn * gv); }
+    else { emit(ks, sn); emit(kc, cs); }
+    const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;   // angle doubling
+    sn = s2; cs = c2; f *= 2.0f;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_constant__ FzArgs a, const __grid_constant__ FzMaps tm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + oA;
+  uint8_t* sW = smem + oW;
+  uint8_t* sAux = smem + oAux;
+  uint8_t* sStg = smem + oStg;
+  float* sBias = reinterpret_cast<float*>(smem + oBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBars);
+  Bars B;
+  B.w_full = bars; B.w_empty = bars + 3; B.aux_full = bars + 6; B.aux_empty = bars + 10; B.a_ready = bars + 14;
+  B.acc_full = bars + 18; B.stg_full = bars + 20; B.stg_empty = bars + 22; B.a_free = bars + 24; B.a_init = bars + 25;
+  B.tile_done = bars + 26; B.h_stored = bars + 27; B.epi_done = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWRing; ++s) { mbar_init(B.w_full + s, 1); mbar_init(B.w_empty + s, 1); }
+    for (int s = 0; s < kAuxRing; ++s) { mbar_init(B.aux_full + s, 1); mbar_init(B.aux_empty + s, kEpiWarps); }
+    for (int j = 0; j < 4; ++j) mbar_init(B.a_ready + j, kEpiWarps);
+    for (int s = 0; s < 2; ++s) { mbar_init(B.acc_full + s, 1); mbar_init(B.stg_full + s, kEpiWarps); mbar_init(B.stg_empty + s, 1); }
+    mbar_init(B.a_free, 1); mbar_init(B.a_init, 1); mbar_init(B.tile_done, 1); mbar_init(B.h_stored, 1);
+    mbar_init(B.epi_done, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (MODE == FZ_FWD) {
+    for (int i = threadIdx.x; i < a.n_lin * 256; i += kThreads) {
+      const int l = i >> 8, n = i & 255;
+      if (l == a.n_lin - 1) sBias[i] = a.Wflat[a.b_off[l] + 1 + n];          // last layer: feature biases (rows 1..256)
+      else sBias[i] = n < (l + 1 == a.skip ? a.skw : 256) ? a.Wflat[a.b_off[l] + n] : 0.0f;
+    }
+    if (threadIdx.x == 0) sBias[a.n_lin * 256] = a.Wflat[a.b_off[a.n_lin - 1]];   // sdf bias (row 0)
+  }
+  if (warp == kMma) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntiles = (int)((a.P + 127) / 128);
+  const int top = a.n_lin - 1;            // 8
+
+  if (warp == kWProd) {
+    // ================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int jb = 0; jb < a.n_jobs; ++jb) {
+          const FzJob J = a.jobs[jb];
+          const int nch = J.Kp >> 5;
+          const uint32_t cbytes = (uint32_t)J.Np * 64;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + J.w_off);
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(B.w_empty + stage, phase ^ 1);
+            mbar_arrive_expect_tx(B.w_full + stage, cbytes);
+            bulk_g2s(sW + stage * kWStage, src + (size_t)c * cbytes, cbytes, B.w_full + stage);
+            if (++stage == kWRing) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kMma) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, aph = 0, initph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int jb = 0; jb < a.n_jobs; ++jb) {
+          const FzJob J = a.jobs[jb];
+          const int nch = J.Kp >> 5;
+          const uint32_t idesc = idesc_bf16(128, J.Np, 0, 0);
+          const uint32_t b_lbo = (uint32_t)J.Np * 16;
+          const uint32_t d_tmem = tmem_base + J.acc * 256;
+          if (J.wait_a == 2) { mbar_wait(B.a_init, initph); initph ^= 1; }
+          for (int c = 0; c < nch; ++c) {
+            if (J.wait_a == 1 && !(c & 1)) {
+              const int j = c >> 1;
+              mbar_wait(B.a_ready + j, (aph >> j) & 1);
+              aph ^= 1u << j;
+            }
+            mbar_wait(B.w_full + stage, phase);
+            tc_fence_after();
+            const uint32_t sAa = smem_u32(sA + (c >> 1) * kPanel) + (c & 1) * 64, sWa = smem_u32(sW + stage * kWStage);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(d_tmem, smem_desc_sw128(sAa + ks * 32, 16, 1024), smem_desc(sWa + ks * 2 * b_lbo, b_lbo, 128), idesc,
+                        (c | ks) != 0);
+            umma_commit(B.w_empty + stage);
+            if (++stage == kWRing) { stage = 0; phase ^= 1; }
+          }
+          if (J.commit) umma_commit(B.acc_full + (J.commit - 1));
+        }
+        // the last A-write of the tile has no MMA consumer: keep the panel parities in step
+        if (MODE == FZ_TAN || (MODE == FZ_ADJ && !a.want_e)) {
+          for (int j = 0; j < 4; ++j) { mbar_wait(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; }
+        }
+        if (MODE == FZ_ADJ) umma_commit(B.tile_done);
+      }
+    }
+  } else if (warp == kStore) {
+    // ================================================================== TMA-store issuer
+    if (lane == 0) {
+      uint32_t aph = 0, stgc = 0;
+      auto wait_panel = [&](int j) { mbar_wait(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; };
+      auto store_tile = [&](const CUtensorMap* map, int row0, int layer, int npan, bool do_store) {
+        for (int j = 0; j < npan; ++j) {
+          wait_panel(j);
+          if (do_store) tma_store_3d(map, sA + j * kPanel, j * 64, row0, layer);
+        }
+        if (do_store) { bulk_commit(); bulk_wait_read0(); }
+        mbar_arrive(B.a_free);
+      };
+      auto store_stg = [&](const CUtensorMap* map, int c0, int row0, int layer) {
+        const uint32_t slot = stgc % kStgRing, par = (stgc / kStgRing) & 1;
+        mbar_wait(B.stg_full + slot, par);
+        tma_store_3d(map, sStg + slot * kPanel, c0, row0, layer);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(B.stg_empty + slot);
+        ++stgc;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
+        if (MODE == FZ_FWD) {
+          store_tile(&tm.in0, row0, 0, 1, true);                                  // PE
+          for (int l = 0; l < top; ++l) store_tile(&tm.H, row0, l, 4, true);      // H_{l+1}
+          bulk_wait0();                                                           // H tiles globally visible:
+          mbar_arrive(B.h_stored);                                                // the sweep may load them back
+          if (a.has_feat)
+            for (int j = 0; j < 4; ++j) store_stg(&tm.out, j * 64, row0, 0);      // feature -> colour input slot
+          for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, true); // delta_l
+        } else if (MODE == FZ_TAN) {
+          store_tile(&tm.in0, row0, 0, 1, true);                                  // T_0
+          for (int l = 0; l < top; ++l) {
+            for (int j = 0; j < 4; ++j) {
+              store_stg(&tm.Z2, j * 64, row0, l);                                 // zb2_l
+              wait_panel(j);
+              tma_store_3d(&tm.out, sA + j * kPanel, j * 64, row0, l);            // T_{l+1}
+            }
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(B.a_free);
+          }
+        } else {
+          for (int l = top - 1; l >= 0; --l) store_tile(&tm.out, row0, l, 4, a.store_out != 0);   // zb_l
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp == kAuxW) {
+    // ================================================================== auxiliary-tile producer
+    if (lane == 0) {
+      uint32_t auxc = 0, t_local = 0;
+      auto load_aux = [&](const CUtensorMap* map, int j, int row0, int layer) {
+        const uint32_t slot = auxc % kAuxRing, par = (auxc / kAuxRing) & 1;
+        mbar_wait(B.aux_empty + slot, par ^ 1);
+        mbar_arrive_expect_tx(B.aux_full + slot, kPanel);
+        tma_load_3d(sAux + slot * kPanel, map, j * 64, row0, layer, B.aux_full + slot);
+        ++auxc;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+        const int row0 = tile * 128;
+        if (MODE == FZ_FWD) {
+          mbar_wait(B.h_stored, t_local & 1);
+          for (int l = top - 1; l >= 1; --l)
+            for (int j = 0; j < 4; ++j) load_aux(&tm.H, j, row0, l - 1);          // H_l
+        } else if (MODE == FZ_TAN) {
+          for (int l = 0; l < top; ++l)
+            for (int j = 0; j < 4; ++j) { load_aux(&tm.H, j, row0, l); load_aux(&tm.D, j, row0, l); }   // H_{l+1}, delta_l
+        } else {
+          // next tile's upstream feature gradient into the A panels: the previous tile's MMAs and stores are done with them
+          if (t_local > 0) {
+            mbar_wait(B.tile_done, (t_local - 1) & 1);
+            mbar_wait(B.epi_done, (t_local - 1) & 1);      // ... and its epilogue with the TMEM accumulators
+            const uint32_t evs = t_local * (uint32_t)top;                         // A-write events so far
+            mbar_wait(B.a_free, (evs - 1) & 1);
+          }
+          mbar_arrive_expect_tx(B.a_init, 4 * kPanel);
+          for (int j = 0; j < 4; ++j) tma_load_3d(sA + j * kPanel, &tm.in0, j * 64, row0, 0, B.a_init);
+          for (int l = top; l >= 1; --l)
+            for (int j = 0; j < 4; ++j) {
+              load_aux(&tm.H, j, row0, l - 1);                                    // H_l
+              if (a.has_d) load_aux(&tm.Z2, j, row0, l - 1);                      // zb2_{l-1}
+            }
+        }
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps 0..15
+    EpiCtx E;
+    E.sA = sA; E.sAux = sAux; E.sStg = sStg; E.B = B;
+    E.q = warp & 3; E.part = warp >> 2; E.lane = lane; E.r = E.q * 32 + lane;
+    E.ev = 0; E.auxc = 0; E.stgc = 0; E.accp = 0; E.tmem_base = tmem_base;
+    const int r = E.r, part = E.part;
+    const float* w0 = a.Wflat + a.w_top_off;       // row 0 of the last layer (d sdf / d H_top)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m = (int64_t)tile * 128 + r;
+      const bool ok = m < a.P;
+      const int64_t mm = ok ? m : 0;
+      float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (MODE != FZ_ADJ && ok) {
+        const float4 t = *reinterpret_cast<const float4*>(a.x + mm * 4);
+        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        if (MODE == FZ_TAN) {
+          const float4 u = *reinterpret_cast<const float4*>(a.g + mm * 4);
+          gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+        }
+      }
+      const float xd = xv[part], gd = gv[part];    // this thread's input dimension (d_in == 4 == slabs per panel)
+
+      if (MODE == FZ_FWD || MODE == FZ_TAN) {
+        // ---------------- layer-0 input into panel 0: [x_hi | sin / cos | x_lo | 0]  (TAN: [J_PE g | 0])
+        E.begin_event();
+        if (part == 0)
+          for (int k = a.pe_w + (MODE == FZ_FWD ? a.d_in : 0); k < 64; ++k) put_elem(sA, r, k, 0.0f);
+        pe_cols<MODE == FZ_TAN>(xd, gd, part, a.d_in, a.L, [&](int k, float v) { put_elem(sA, r, k, v); });
+        if (MODE == FZ_FWD) put_elem(sA, r, a.pe_w + part, xd - __bfloat162float(__float2bfloat16(xd)));
+        E.panel_done(0);
+
+        // ---------------- forward-direction layers 0 .. top-1
+        for (int l = 0; l < top; ++l) {
+          const uint32_t taddr = E.wait_acc(l & 1);
+          E.begin_event();
+          const bool to_skip = (l + 1 == a.skip);
+          const float alpha = to_skip ? kInvSqrt2 : 1.0f;
+          const int n_out = to_skip ? a.skw : 256;
+          const float* bias = sBias + l * 256;
+          if (to_skip)    // PE part of the skip concat (columns n_out + d_in ..): this thread's dimension, scaled
+            pe_cols<MODE == FZ_TAN>(xd, gd, part, a.d_in, a.L, [&](int k, float v) {
+              if (k >= a.d_in) put_elem(sA, r, n_out + k, v * kInvSqrt2);
+            });
+          const float hc = kC2 * (to_skip ? 1.41421356237309505f : 1.0f);     // H_{l+1} = alpha * softplus
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int n0 = j * 64 + part * 16;
+            Pk16 hp, dp;
+            if constexpr (MODE == FZ_TAN) { hp = E.aux_take(); dp = E.aux_take(); }
+            float v[16];
+            tmem_ld16(taddr + n0, v);
+            float z2[MODE == FZ_TAN ? 16 : 1];
+            if (n0 + 16 <= n_out) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (MODE == FZ_FWD) {
+                  v[i] = alpha * softplus_poly(v[i] + bias[n0 + i]);
+                } else {
+                  const float e100 = ex2(fmaf(pk_get(hp, i), hc, 6.643856189774724f));   // 100 exp(-100 h)
+                  const float sp = fmaf(e100, -0.01f, 1.0f);
+                  z2[MODE == FZ_TAN ? i : 0] = v[i] * pk_get(dp, i) * e100;
+                  v[i] = alpha * v[i] * sp;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                float val = 0.0f, zz = 0.0f;
+                if (n < n_out) {
+                  if (MODE == FZ_FWD) {
+                    val = alpha * softplus_poly(v[i] + bias[n]);
+                  } else {
+                    const float e100 = ex2(fmaf(pk_get(hp, i), hc, 6.643856189774724f));
+                    zz = v[i] * pk_get(dp, i) * e100;
+                    val = alpha * v[i] * fmaf(e100, -0.01f, 1.0f);
+                  }
+                } else if (n - n_out < a.d_in) {
+                  val = (MODE == FZ_TAN ? gv[n - n_out] : xv[n - n_out]) * kInvSqrt2;
+                }
+                v[i] = val;
+                if (MODE == FZ_TAN) z2[MODE == FZ_TAN ? i : 0] = zz;
+              }
+            }
+            if constexpr (MODE == FZ_TAN) { E.aux_release(2); E.stg_put(z2); }
+            if (n0 < n_out + a.d_in) write16(sA + j * kPanel, r, part, v);     // beyond: the scalar PE writes own the columns
+            E.panel_done(j);
+          }
+          tc_fence_before();
+        }
+      }
+
+      if (MODE == FZ_FWD) {
+        // ---------------- last layer: feature (acc 0, bf16 via staging -> colour input) and sdf (acc 1, column 0)
+        {
+          const uint32_t taddr = E.wait_acc(top & 1);
+          const float* bias = sBias + top * 256;
+          if (a.has_feat) {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              const int n0 = j * 64 + part * 16;
+              float v[16];
+              tmem_ld16(taddr + n0, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += bias[n0 + i];
+              E.stg_put(v);
+            }
+          }
+          if (part == 0) {
+            float v[16];
+            tmem_ld16(tmem_base + ((top & 1) ^ 1) * 256 + ((uint32_t)(E.q * 32) << 16), v);
+            if (ok) a.sdf[m * a.sdf_ld] = v[0] + sBias[a.n_lin * 256];
+          }
+          tc_fence_before();
+        }
+        // ---------------- top of the reverse sweep, in place: delta_{top-1} = w0 * sp(H_top)
+        E.begin_event();
+        {
+          const float hc = kC2 * (top == a.skip ? 1.41421356237309505f : 1.0f);
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int n0 = j * 64 + part * 16;
+            const Pk16 hp = read16(sA + j * kPanel, r, part);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __ldg(w0 + n0 + i) * (1.0f - ex2(pk_get(hp, i) * hc));
+            write16(sA + j * kPanel, r, part, v);
+            E.panel_done(j);
+          }
+        }
+        // ---------------- reverse sweep: delta_{l-1} = alpha_l (W_l^T delta_l) sp(H_l), l = top-1 .. 1
+        for (int l = top - 1; l >= 1; --l) {
+          const int s = top + 1 + (top - 1 - l);
+          const uint32_t taddr = E.wait_acc(s & 1);
+          E.begin_event();
+          const bool split = (l == a.skip);
+          const float alpha = split ? kInvSqrt2 : 1.0f;
+          const float hc = kC2 * (split ? 1.41421356237309505f : 1.0f);
+          const int nsplit = split ? a.skw : 256;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int n0 = j * 64 + part * 16;
+            const Pk16 hp = E.aux_take();
+            float v[16];
+            tmem_ld16(taddr + n0, v);
+            if (n0 + 16 <= nsplit) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sv = alpha * v[i];
+                v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                const float sv = alpha * v[i];
+                if (n < nsplit) {
+                  v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv);
+                } else {
+                  if (ok) a.ge1[m * 64 + (n - nsplit)] = sv;
+                  v[i] = 0.0f;
+                }
+              }
+            }
+            E.aux_release(1);
+            write16(sA + j * kPanel, r, part, v);
+            E.panel_done(j);
+          }
+          tc_fence_before();
+        }
+        // ---------------- layer 0: ge0 = W_0^T delta_0 (fp32, 64 columns)
+        {
+          const int s = 2 * top;
+          const uint32_t taddr = E.wait_acc(s & 1);
+          float v[16];
+          tmem_ld16(taddr + part * 16, v);
+          if (ok) {
+            float4* o = reinterpret_cast<float4*>(a.ge0 + m * 64 + part * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          tc_fence_before();
+        }
+      }
+
+      if (MODE == FZ_ADJ) {
+        const float dsdf = (ok && a.d_sdf) ? a.d_sdf[m * a.d_sdf_ld] : 0.0f;
+        for (int l = top; l >= 1; --l) {
+          const int s = top - l;
+          const uint32_t taddr = E.wait_acc(s & 1);
+          E.begin_event();
+          const bool split = (l == a.skip);
+          const float alpha = split ? kInvSqrt2 : 1.0f;
+          const float hc = kC2 * (split ? 1.41421356237309505f : 1.0f);
+          const int nsplit = split ? a.skw : 256;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int n0 = j * 64 + part * 16;
+            const Pk16 hp = E.aux_take();
+            Pk16 dp;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dp.w[i] = 0u;
+            if (a.has_d) dp = E.aux_take();
+            float v[16];
+            tmem_ld16(taddr + n0, v);
+            if (l == top && a.d_sdf) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(dsdf, __ldg(w0 + n0 + i), v[i]);
+            }
+            if (n0 + 16 <= nsplit) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sv = alpha * v[i];
+                v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv + pk_get(dp, i));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                const float sv = alpha * v[i];
+                if (n < nsplit) {
+                  v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv + pk_get(dp, i));
+                } else {
+                  if (ok && a.want_e) a.eb1[m * 64 + (n - nsplit)] = sv;
+                  v[i] = 0.0f;
+                }
+              }
+            }
+            E.aux_release(a.has_d ? 2 : 1);
+            write16(sA + j * kPanel, r, part, v);
+            E.panel_done(j);
+          }
+          tc_fence_before();
+        }
+        if (a.want_e) {
+          const uint32_t taddr = E.wait_acc(top & 1);
+          float v[16];
+          tmem_ld16(taddr + part * 16, v);
+          if (ok) {
+            float4* o = reinterpret_cast<float4*>(a.eb0 + m * 64 + part * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          tc_fence_before();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.epi_done);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMma) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool sdf_fused_supported(const MlpShape& m) {
+  if (m.n_lin != 9 || m.d_in != 4 || m.pe_w + m.d_in > 64 || m.d_out != 257) return false;
+  if (m.skip <= 1 || m.skip >= m.n_lin - 1) return false;
+  for (int l = 1; l < m.n_lin; ++l)
+    if (m.in[l] != 256) return false;
+  const int skw = m.in[m.skip] - m.pe_w;
+  if ((skw + m.d_in) % 16 != 0) return false;
+  for (int l = 0; l < m.n_lin; ++l)
+    if (m.b_off[l] % 4 != 0 || m.w_off[l] % 4 != 0) return false;
+  return true;
+}
+
+template <int MODE>
+static int launch_t(const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sdf_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    COPE_REQUIRE(e == cudaSuccess, "sdf_fused: cannot raise dynamic shared memory to %d: %s", kSmem, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int ntiles = (int)((a.P + 127) / 128);
+  sdf_fused_kernel<MODE><<<std::min(ntiles, 148), kThreads, kSmem, s>>>(a, maps);
+  COPE_CHECK_LAUNCH("sdf_fused");
+  return 0;
+}
+
+int launch_sdf_fused(int mode, const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
+  if (a.P <= 0) return 0;
+  COPE_REQUIRE(a.n_jobs > 0 && a.n_jobs <= kFzMaxJobs, "sdf_fused: bad job list (%d)", a.n_jobs);
+  switch (mode) {
+    case FZ_FWD: return launch_t<FZ_FWD>(a, maps, s);
+    case FZ_TAN: return launch_t<FZ_TAN>(a, maps, s);
+    case FZ_ADJ: return launch_t<FZ_ADJ>(a, maps, s);
+  }
+  COPE_REQUIRE(false, "sdf_fused: unknown mode %d", mode);
+}
+
+}  // namespace cope

@@ -17,9 +17,12 @@
 #include <algorithm>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
+#include "sdf_fused.cuh"
 
 namespace cope {
 using namespace tc;
@@ -351,6 +354,36 @@ static int make_tmap(const bf16* ptr, uint64_t cols, uint64_t rows, uint64_t ld,
                (unsigned long long)cols, (unsigned long long)ld);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, *out);
+  return 0;
+}
+
+// bf16 [layers][rows][ld] buffer (cols addressed), boxes of 64 columns x 128 rows x 1 layer, 128B swizzle; rows past
+// `rows` are zero-filled on load and clipped on store, so a partial last tile never touches the next layer
+int make_tmap3(const bf16* ptr, uint64_t cols, uint64_t rows, uint64_t layers, uint64_t ld, uint64_t layer_stride, CUtensorMap* out) {
+  struct Key3 { const void* p; uint64_t c, r, l, ld, ls; };
+  static std::vector<std::pair<Key3, CUtensorMap>> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  for (auto& e : cache)
+    if (e.first.p == ptr && e.first.c == cols && e.first.r == rows && e.first.l == layers && e.first.ld == ld && e.first.ls == layer_stride) {
+      *out = e.second;
+      return 0;
+    }
+  EncodeTiledFn fn = encode_fn();
+  COPE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  COPE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0 && (layer_stride * 2) % 16 == 0,
+               "TMA operand must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
+  cuuint64_t dims[3] = {cols, rows, layers};
+  cuuint64_t strides[2] = {ld * 2, layer_stride * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  COPE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed (%d) for [%llu x %llu x %llu] ld %llu", (int)r,
+               (unsigned long long)layers, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  if (cache.size() > 256) cache.clear();
+  cache.emplace_back(Key3{ptr, cols, rows, layers, ld, layer_stride}, *out);
   return 0;
 }
 

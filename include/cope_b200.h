@@ -122,6 +122,10 @@ int cope_render_mlp_bwd(const cope_mlp_desc* sdf_desc, const float* sdfW, const 
                         const float* col_saved, const float* d_sdf, float* d_grad, const float* d_rgb, float* dW_sdf,
                         float* dW_col, float* dx, float* ddirs_pp, float* ws, int prec, cope_stream_t s);
 
+/* test hook (bf16 path): float offset, inside the `ws` of cope_render_mlp_bwd, of the two [P x 64] fp32 buffers that hold
+ * the value-path gradient w.r.t. the positional encoding (layer 0 / skip layer) before the PE backward folds them into dx */
+int64_t cope_dbg_render_bwd_eb_offset(const cope_mlp_desc* sdf_desc, const cope_mlp_desc* col_desc, int64_t P);
+
 /* ---- ray points (neus_renderer.py:337-350 / :495-498 / :285) --------------------------------------
  * pts_time [N*S x 4] = (o + d * zz, t) with zz = z + dists/2 if use_mid else z.
  * dists / mid_z [N x S] may be NULL.  The last interval is sample_dist = (far[0]-near[0])/n_coarse,
