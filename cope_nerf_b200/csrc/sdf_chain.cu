@@ -33,11 +33,32 @@ struct ChainArgs {
 };
 
 __device__ __forceinline__ float ch_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float ch_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(beta=100)(z) = max(z, 0) + log1p(u) / 100 with u = exp(-100 |z|): one MUFU; log1p(u)/u on (0, 1] as a degree-4
+// minimax polynomial (max rel. error 6e-5).  Above torch's threshold (100 z > 20) u < 2.1e-9: the result is z in fp32.
 __device__ __forceinline__ float ch_softplus(float z) {
-  const float t = z * (kSoftplusBeta * 1.4426950408889634f);
-  const float s = ch_lg2(1.0f + ch_ex2(t)) * (0.6931471805599453f / kSoftplusBeta);
-  return t > 28.853900817779268f ? z : s;
+  const float u = ch_ex2(fabsf(z) * (-kSoftplusBeta * 1.4426950408889634f));
+  float q = fmaf(u, 0.0415511144734499e-2f, -0.15783837660869504e-2f);
+  q = fmaf(u, q, 0.3065610999388736e-2f);
+  q = fmaf(u, q, -0.49703084266368813e-2f);
+  q = fmaf(u, q, 0.9999449934273398e-2f);
+  return fmaf(u, q, fmaxf(z, 0.0f));
+}
+// single-thread roles park on a failed probe instead of re-issuing it (they share schedulers with the epilogue warps)
+__device__ __forceinline__ void ch_wait_park(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
 }
 // byte offset of 8 consecutive K elements starting at k (multiple of 8) of row r inside the 4-panel activation tile
 __device__ __forceinline__ uint32_t a_off(int r, int k) {
@@ -87,7 +108,7 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
           const uint32_t cbytes = (uint32_t)a.Np[l] * 128;
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + a.w_off[l]);
           for (int c = 0; c < nkc; ++c) {
-            mbar_wait(w_empty + stage, phase ^ 1);
+            ch_wait_park(w_empty + stage, phase ^ 1);
             mbar_arrive_expect_tx(w_full + stage, cbytes);
             bulk_g2s(sW + stage * kWChunkBytes, src + (size_t)c * cbytes, cbytes, w_full + stage);
             if (++stage == kWRing) { stage = 0; phase ^= 1; }
@@ -107,9 +128,9 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
           const uint32_t b_lbo = (uint32_t)a.Np[l] * 16;
           const uint32_t d_tmem = tmem_base + (l & 1) * 256;
           for (int c = 0; c < nkc; ++c) {
-            mbar_wait(a_ready + c, (aph >> c) & 1);
+            ch_wait_park(a_ready + c, (aph >> c) & 1);
             aph ^= 1u << c;
-            mbar_wait(w_full + stage, phase);
+            ch_wait_park(w_full + stage, phase);
             tc_fence_after();
             const uint32_t sAa = smem_u32(sA + c * kPanelBytes), sWa = smem_u32(sW + stage * kWChunkBytes);
 #pragma unroll
@@ -188,8 +209,16 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
           tmem_ld16(taddr + n0, v);
           if (n0 + 16 <= n_out) {
             // straight-line: 16 independent softplus chains, the compiler interleaves the MUFU latencies
+            float bz[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = alpha * ch_softplus(v[i] + bias[n0 + i]);
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(bz + 4 * i) = *reinterpret_cast<const float4*>(bias + n0 + 4 * i);
+            if (to_skip) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = kInvSqrt2 * ch_softplus(v[i] + bz[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = ch_softplus(v[i] + bz[i]);
+            }
           } else {
             // slabs that straddle / follow the real outputs: zero padding, or the PE part of the skip concat
             for (int i = 0; i < 16; ++i) {

@@ -15,6 +15,8 @@
 // The MMAs of layer l+1 start on K-panel j as soon as the epilogue of layer l has written panel j.
 #include "sdf_fused.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -28,29 +30,39 @@ constexpr int kEpiWarps = 16;
 constexpr int kWProd = 16, kMma = 17, kStore = 18, kAuxW = 19;
 constexpr int kThreads = 20 * 32;
 constexpr int kPanel = 128 * 128;        // 128 rows x 64 bf16
-constexpr int kWStage = 256 * 32 * 2;    // N = 256 x K = 32
-constexpr int kWRing = 3, kAuxRing = 4, kStgRing = 2;
-constexpr int oA = 0;
-constexpr int oW = oA + 4 * kPanel;
-constexpr int oAux = oW + kWRing * kWStage;
-constexpr int oStg = oAux + kAuxRing * kPanel;
-constexpr int oBias = oStg + kStgRing * kPanel;
-constexpr int oBars = oBias + COPE_MAX_LIN * 256 * 4;
-constexpr int kSmem = oBars + 256;
-static_assert(kSmem <= 232448, "fused chain: shared memory budget");
+constexpr int kWStage = 256 * 64 * 2;    // N = 256 x K = 64: one weight chunk per activation panel
+// Shared-memory rings, sized per pass (everything next to the 64 KB activation tile).  Weight chunks are 32 KB
+// (N = 256 x K = 64): chunk c multiplies activation panel c, so the issuer pays one barrier round trip per FOUR
+// tcgen05.mma; an L2 -> SM bulk copy takes ~1100 cycles, which two slots cover while the epilogue paces the step.
+template <int MODE> struct Cfg;
+template <> struct Cfg<FZ_FWD> { static constexpr int kW = 3, kAux = 2, kStg = 1, kBias = (COPE_MAX_LIN * 256 + 64) * 4; };
+template <> struct Cfg<FZ_TAN> { static constexpr int kW = 2, kAux = 5, kStg = 1, kBias = 0; };
+template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 2, kAux = 6, kStg = 0, kBias = 0; };
+constexpr int kMaxRing = 8;
+constexpr int kBarBytes = 512;
+template <int MODE> struct Lay {
+  static constexpr int oA = 0;
+  static constexpr int oW = oA + 4 * kPanel;
+  static constexpr int oAux = oW + Cfg<MODE>::kW * kWStage;
+  static constexpr int oStg = oAux + Cfg<MODE>::kAux * kPanel;
+  static constexpr int oBias = oStg + Cfg<MODE>::kStg * kPanel;
+  static constexpr int oBars = oBias + Cfg<MODE>::kBias;
+  static constexpr int kSmem = oBars + kBarBytes;
+  static_assert(kSmem <= 232448, "fused chain: shared memory budget");
+  static_assert(Cfg<MODE>::kW <= kMaxRing && Cfg<MODE>::kAux <= kMaxRing, "ring too deep for the barrier block");
+};
 
 constexpr float kC2 = -kSoftplusBeta * 1.4426950408889634f;   // exp(-100 h) = 2^(kC2 h)
 
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// softplus(beta=100)(a) = max(a, 0) + log1p(u) / 100, u = exp(-100 |a|): ONE MUFU; log1p(u)/u on (0, 1] is a degree-4
-// minimax polynomial (max rel. error 6e-5, far below the bf16 rounding of the stored activation).  Above torch's
-// threshold (100 a > 20) u < 2.1e-9 and the result equals a in fp32.
+// softplus(beta=100)(a) = max(a, 0) + log1p(u) / 100, u = exp(-100 |a|): ONE MUFU; log1p(u)/u on (0, 1] is a degree-3
+// minimax polynomial (max rel. error 4.1e-4 of a term that is itself <= 0.7 % of the bf16-rounded activation scale).
+// Above torch's threshold (100 a > 20) u < 2.1e-9 and the result equals a in fp32.
 __device__ __forceinline__ float softplus_poly(float a) {
   const float u = ex2(fabsf(a) * kC2);
-  float q = fmaf(u, 0.0415511144734499e-2f, -0.15783837660869504e-2f);
-  q = fmaf(u, q, 0.3065610999388736e-2f);
-  q = fmaf(u, q, -0.49703084266368813e-2f);
-  q = fmaf(u, q, 0.9999449934273398e-2f);
+  float q = fmaf(u, -0.07473614766179527e-2f, 0.2546222068470616e-2f);
+  q = fmaf(u, q, -0.4866430640453249e-2f);
+  q = fmaf(u, q, 0.9996203753455154e-2f);
   return fmaf(u, q, fmaxf(a, 0.0f));
 }
 
@@ -94,12 +106,41 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// timeline stamps (CTA 0 only, when a.dbg != nullptr): region `role` holds (tag << 48 | clock) entries
+struct Stamp {
+  long long* p; int n;
+  __device__ __forceinline__ void init(long long* base, int role) { p = (base && blockIdx.x == 0) ? base + role * 4096 : nullptr; n = 1; }
+  __device__ __forceinline__ void operator()(int tag) {
+    if (p && n < 4096) { p[n++] = ((long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFll); p[0] = n; }
+  }
+};
+
+// mbarrier wait for the single-thread roles (producers, MMA issuer, store issuer): they sit on the same schedulers as
+// the epilogue warps, so a failed probe parks the thread (suspend-time hint) instead of re-issuing the probe at once
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 struct Bars {
   uint64_t *w_full, *w_empty, *aux_full, *aux_empty, *a_ready, *acc_full, *stg_full, *stg_empty, *a_free, *a_init, *tile_done,
       *h_stored, *epi_done;
 };
 
 // epilogue-side view of the rings
+template <int kAuxRing, int kStgRing>
 struct EpiCtx {
   uint8_t *sA, *sAux, *sStg;
   Bars B;
@@ -110,16 +151,20 @@ struct EpiCtx {
   __device__ __forceinline__ void begin_event() {          // about to overwrite A panels: the previous event's TMA stores
     if (ev > 0) mbar_wait(B.a_free, (ev - 1) & 1);         // must have finished reading them
     ++ev;
+    st(510);
   }
+  Stamp st;
   __device__ __forceinline__ void panel_done(int j) {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(B.a_ready + j);
+    st(600 + j);
   }
   __device__ __forceinline__ uint32_t wait_acc(int b) {
     mbar_wait(B.acc_full + b, (accp >> b) & 1);
     accp ^= 1u << b;
     tc_fence_after();
+    st(500 + b);
     return tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
   }
   // wait for the next auxiliary panel and pull this thread's 16 values; the slot is handed back (aux_release) only after
@@ -128,6 +173,7 @@ struct EpiCtx {
     const uint32_t slot = auxc % kAuxRing, par = (auxc / kAuxRing) & 1;
     mbar_wait(B.aux_full + slot, par);
     ++auxc;
+    st(520);
     return read16(sAux + slot * kPanel, r, part);
   }
   __device__ __forceinline__ void aux_release(int n) {     // the n most recently taken slots
@@ -136,7 +182,8 @@ struct EpiCtx {
       for (int k = n; k >= 1; --k) mbar_arrive(B.aux_empty + ((auxc - k) % kAuxRing));
   }
   __device__ __forceinline__ void stg_put(const float (&v)[16]) {
-    const uint32_t slot = stgc % kStgRing, par = (stgc / kStgRing) & 1;
+    constexpr uint32_t kS = kStgRing > 0 ? kStgRing : 1;
+    const uint32_t slot = stgc % kS, par = (stgc / kS) & 1;
     mbar_wait(B.stg_empty + slot, par ^ 1);
     write16(sStg + slot * kPanel, r, part, v);
     fence_proxy_async();
@@ -167,17 +214,21 @@ __device__ __forceinline__ void pe_cols(float xv, float gv, int dd, int d_in, in
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_constant__ FzArgs a, const __grid_constant__ FzMaps tm) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + oA;
-  uint8_t* sW = smem + oW;
-  uint8_t* sAux = smem + oAux;
-  uint8_t* sStg = smem + oStg;
-  float* sBias = reinterpret_cast<float*>(smem + oBias);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBars);
+  using L = Lay<MODE>;
+  constexpr int kWRing = Cfg<MODE>::kW, kAuxRing = Cfg<MODE>::kAux, kStgRing = Cfg<MODE>::kStg;
+  uint8_t* sA = smem + L::oA;
+  uint8_t* sW = smem + L::oW;
+  uint8_t* sAux = smem + L::oAux;
+  uint8_t* sStg = smem + L::oStg;
+  float* sBias = reinterpret_cast<float*>(smem + L::oBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBars);
   Bars B;
-  B.w_full = bars; B.w_empty = bars + 3; B.aux_full = bars + 6; B.aux_empty = bars + 10; B.a_ready = bars + 14;
-  B.acc_full = bars + 18; B.stg_full = bars + 20; B.stg_empty = bars + 22; B.a_free = bars + 24; B.a_init = bars + 25;
-  B.tile_done = bars + 26; B.h_stored = bars + 27; B.epi_done = bars + 28;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  B.w_full = bars; B.w_empty = bars + kMaxRing; B.aux_full = bars + 2 * kMaxRing; B.aux_empty = bars + 3 * kMaxRing;
+  B.a_ready = bars + 4 * kMaxRing; B.acc_full = B.a_ready + 4; B.stg_full = B.acc_full + 2; B.stg_empty = B.stg_full + 2;
+  B.a_free = B.stg_empty + 2; B.a_init = B.a_free + 1; B.tile_done = B.a_free + 2; B.h_stored = B.a_free + 3;
+  B.epi_done = B.a_free + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(B.a_free + 5);
+  static_assert((4 * kMaxRing + 4 + 2 + 2 + 2 + 5) * 8 + 8 <= kBarBytes, "barrier block too small");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -202,22 +253,23 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int ntiles = (int)((a.P + 127) / 128);
   const int top = a.n_lin - 1;            // 8
+  const int tile_first = blockIdx.x, tile_step = gridDim.x;
+  const int ntiles = (int)((a.P + 127) / 128);
 
   if (warp == kWProd) {
     // ================================================================== weight producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
         for (int jb = 0; jb < a.n_jobs; ++jb) {
           const FzJob J = a.jobs[jb];
-          const int nch = J.Kp >> 5;
-          const uint32_t cbytes = (uint32_t)J.Np * 64;
+          const int nch = J.Kp >> 6;
+          const uint32_t cbytes = (uint32_t)J.Np * 128;
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + J.w_off);
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(B.w_empty + stage, phase ^ 1);
+            mbar_wait_park(B.w_empty + stage, phase ^ 1);
             mbar_arrive_expect_tx(B.w_full + stage, cbytes);
             bulk_g2s(sW + stage * kWStage, src + (size_t)c * cbytes, cbytes, B.w_full + stage);
             if (++stage == kWRing) { stage = 0; phase ^= 1; }
@@ -230,35 +282,42 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, aph = 0, initph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      Stamp st; st.init(a.dbg, 0);
+      const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA), 16, 1024);
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
         for (int jb = 0; jb < a.n_jobs; ++jb) {
           const FzJob J = a.jobs[jb];
-          const int nch = J.Kp >> 5;
+          const int nch = J.Kp >> 6;
+          st(100 + jb);
           const uint32_t idesc = idesc_bf16(128, J.Np, 0, 0);
           const uint32_t b_lbo = (uint32_t)J.Np * 16;
           const uint32_t d_tmem = tmem_base + J.acc * 256;
-          if (J.wait_a == 2) { mbar_wait(B.a_init, initph); initph ^= 1; }
+          // descriptors: the 14-bit start-address field (16-byte units) is the only part that moves
+          const uint64_t bdesc0 = smem_desc(smem_u32(sW), b_lbo, 128);
+          const uint32_t b_kstep = (2 * b_lbo) >> 4;                       // one K = 16 step inside a chunk
+          if (J.wait_a == 2) { mbar_wait_park(B.a_init, initph); initph ^= 1; }
           for (int c = 0; c < nch; ++c) {
-            if (J.wait_a == 1 && !(c & 1)) {
-              const int j = c >> 1;
-              mbar_wait(B.a_ready + j, (aph >> j) & 1);
-              aph ^= 1u << j;
+            if (J.wait_a == 1) {
+              mbar_wait_park(B.a_ready + c, (aph >> c) & 1);
+              aph ^= 1u << c;
+              st(200 + c);
             }
-            mbar_wait(B.w_full + stage, phase);
+            mbar_wait_park(B.w_full + stage, phase);
+            st(300 + c);
             tc_fence_after();
-            const uint32_t sAa = smem_u32(sA + (c >> 1) * kPanel) + (c & 1) * 64, sWa = smem_u32(sW + stage * kWStage);
+            const uint64_t ad = adesc0 + (uint64_t)(c * (kPanel >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(stage * (kWStage >> 4));
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              umma_bf16(d_tmem, smem_desc_sw128(sAa + ks * 32, 16, 1024), smem_desc(sWa + ks * 2 * b_lbo, b_lbo, 128), idesc,
-                        (c | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(d_tmem, ad + ks * 2, bd + ks * b_kstep, idesc, (c | ks) != 0);
             umma_commit(B.w_empty + stage);
             if (++stage == kWRing) { stage = 0; phase ^= 1; }
           }
           if (J.commit) umma_commit(B.acc_full + (J.commit - 1));
+          st(400 + jb);
         }
         // the last A-write of the tile has no MMA consumer: keep the panel parities in step
         if (MODE == FZ_TAN || (MODE == FZ_ADJ && !a.want_e)) {
-          for (int j = 0; j < 4; ++j) { mbar_wait(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; }
+          for (int j = 0; j < 4; ++j) { mbar_wait_park(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; }
         }
         if (MODE == FZ_ADJ) umma_commit(B.tile_done);
       }
@@ -267,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
     // ================================================================== TMA-store issuer
     if (lane == 0) {
       uint32_t aph = 0, stgc = 0;
-      auto wait_panel = [&](int j) { mbar_wait(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; };
+      auto wait_panel = [&](int j) { mbar_wait_park(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; };
       auto store_tile = [&](const CUtensorMap* map, int row0, int layer, int npan, bool do_store) {
         for (int j = 0; j < npan; ++j) {
           wait_panel(j);
@@ -277,15 +336,16 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
         mbar_arrive(B.a_free);
       };
       auto store_stg = [&](const CUtensorMap* map, int c0, int row0, int layer) {
-        const uint32_t slot = stgc % kStgRing, par = (stgc / kStgRing) & 1;
-        mbar_wait(B.stg_full + slot, par);
+        constexpr uint32_t kS = kStgRing > 0 ? kStgRing : 1;
+        const uint32_t slot = stgc % kS, par = (stgc / kS) & 1;
+        mbar_wait_park(B.stg_full + slot, par);
         tma_store_3d(map, sStg + slot * kPanel, c0, row0, layer);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(B.stg_empty + slot);
         ++stgc;
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
         const int row0 = tile * 128;
         if (MODE == FZ_FWD) {
           store_tile(&tm.in0, row0, 0, 1, true);                                  // PE
@@ -319,15 +379,15 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
       uint32_t auxc = 0, t_local = 0;
       auto load_aux = [&](const CUtensorMap* map, int j, int row0, int layer) {
         const uint32_t slot = auxc % kAuxRing, par = (auxc / kAuxRing) & 1;
-        mbar_wait(B.aux_empty + slot, par ^ 1);
+        mbar_wait_park(B.aux_empty + slot, par ^ 1);
         mbar_arrive_expect_tx(B.aux_full + slot, kPanel);
         tma_load_3d(sAux + slot * kPanel, map, j * 64, row0, layer, B.aux_full + slot);
         ++auxc;
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+      for (int tile = tile_first; tile < ntiles; tile += tile_step, ++t_local) {
         const int row0 = tile * 128;
         if (MODE == FZ_FWD) {
-          mbar_wait(B.h_stored, t_local & 1);
+          mbar_wait_park(B.h_stored, t_local & 1);
           for (int l = top - 1; l >= 1; --l)
             for (int j = 0; j < 4; ++j) load_aux(&tm.H, j, row0, l - 1);          // H_l
         } else if (MODE == FZ_TAN) {
@@ -336,10 +396,10 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
         } else {
           // next tile's upstream feature gradient into the A panels: the previous tile's MMAs and stores are done with them
           if (t_local > 0) {
-            mbar_wait(B.tile_done, (t_local - 1) & 1);
-            mbar_wait(B.epi_done, (t_local - 1) & 1);      // ... and its epilogue with the TMEM accumulators
+            mbar_wait_park(B.tile_done, (t_local - 1) & 1);
+            mbar_wait_park(B.epi_done, (t_local - 1) & 1);      // ... and its epilogue with the TMEM accumulators
             const uint32_t evs = t_local * (uint32_t)top;                         // A-write events so far
-            mbar_wait(B.a_free, (evs - 1) & 1);
+            mbar_wait_park(B.a_free, (evs - 1) & 1);
           }
           mbar_arrive_expect_tx(B.a_init, 4 * kPanel);
           for (int j = 0; j < 4; ++j) tma_load_3d(sA + j * kPanel, &tm.in0, j * 64, row0, 0, B.a_init);
@@ -353,13 +413,14 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
     }
   } else {
     // ================================================================== epilogue warps 0..15
-    EpiCtx E;
+    EpiCtx<kAuxRing, kStgRing> E;
     E.sA = sA; E.sAux = sAux; E.sStg = sStg; E.B = B;
     E.q = warp & 3; E.part = warp >> 2; E.lane = lane; E.r = E.q * 32 + lane;
     E.ev = 0; E.auxc = 0; E.stgc = 0; E.accp = 0; E.tmem_base = tmem_base;
     const int r = E.r, part = E.part;
     const float* w0 = a.Wflat + a.w_top_off;       // row 0 of the last layer (d sdf / d H_top)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    E.st.init((warp == 0 && lane == 0) ? a.dbg : nullptr, 1);
+    for (int tile = tile_first; tile < ntiles; tile += tile_step) {
       const int64_t m = (int64_t)tile * 128 + r;
       const bool ok = m < a.P;
       const int64_t mm = ok ? m : 0;
@@ -405,10 +466,21 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
             tmem_ld16(taddr + n0, v);
             float z2[MODE == FZ_TAN ? 16 : 1];
             if (n0 + 16 <= n_out) {
+              if constexpr (MODE == FZ_FWD) {
+                float bz[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(bz + 4 * i) = *reinterpret_cast<const float4*>(bias + n0 + 4 * i);
+                if (to_skip) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = kInvSqrt2 * softplus_poly(v[i] + bz[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = softplus_poly(v[i] + bz[i]);
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 if (MODE == FZ_FWD) {
-                  v[i] = alpha * softplus_poly(v[i] + bias[n0 + i]);
                 } else {
                   const float e100 = ex2(fmaf(pk_get(hp, i), hc, 6.643856189774724f));   // 100 exp(-100 h)
                   const float sp = fmaf(e100, -0.01f, 1.0f);
@@ -498,10 +570,15 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
             float v[16];
             tmem_ld16(taddr + n0, v);
             if (n0 + 16 <= nsplit) {
+              if (split) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float sv = alpha * v[i];
-                v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv);
+                for (int i = 0; i < 16; ++i) {
+                  const float sv = kInvSqrt2 * v[i];
+                  v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(-v[i], ex2(pk_get(hp, i) * hc), v[i]);
               }
             } else {
 #pragma unroll
@@ -562,10 +639,15 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
               for (int i = 0; i < 16; ++i) v[i] = fmaf(dsdf, __ldg(w0 + n0 + i), v[i]);
             }
             if (n0 + 16 <= nsplit) {
+              if (split) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float sv = alpha * v[i];
-                v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv + pk_get(dp, i));
+                for (int i = 0; i < 16; ++i) {
+                  const float sv = kInvSqrt2 * v[i];
+                  v[i] = fmaf(-sv, ex2(pk_get(hp, i) * hc), sv + pk_get(dp, i));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(-v[i], ex2(pk_get(hp, i) * hc), v[i] + pk_get(dp, i));
               }
             } else {
 #pragma unroll
@@ -625,12 +707,12 @@ template <int MODE>
 static int launch_t(const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sdf_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    COPE_REQUIRE(e == cudaSuccess, "sdf_fused: cannot raise dynamic shared memory to %d: %s", kSmem, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(sdf_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MODE>::kSmem);
+    COPE_REQUIRE(e == cudaSuccess, "sdf_fused: cannot raise dynamic shared memory to %d: %s", Lay<MODE>::kSmem, cudaGetErrorString(e));
     attr_set = true;
   }
   const int ntiles = (int)((a.P + 127) / 128);
-  sdf_fused_kernel<MODE><<<std::min(ntiles, 148), kThreads, kSmem, s>>>(a, maps);
+  sdf_fused_kernel<MODE><<<std::min(ntiles, 148), kThreads, Lay<MODE>::kSmem, s>>>(a, maps);
   COPE_CHECK_LAUNCH("sdf_fused");
   return 0;
 }
@@ -638,12 +720,32 @@ static int launch_t(const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
 int launch_sdf_fused(int mode, const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
   if (a.P <= 0) return 0;
   COPE_REQUIRE(a.n_jobs > 0 && a.n_jobs <= kFzMaxJobs, "sdf_fused: bad job list (%d)", a.n_jobs);
-  switch (mode) {
-    case FZ_FWD: return launch_t<FZ_FWD>(a, maps, s);
-    case FZ_TAN: return launch_t<FZ_TAN>(a, maps, s);
-    case FZ_ADJ: return launch_t<FZ_ADJ>(a, maps, s);
+  // Profiling aid, off unless COPE_FZ_TIMELINE=<mode> is set: CTA 0 stamps clock64() per pipeline event and the
+  // launch is followed by a synchronising dump to $COPE_FZ_TIMELINE_FILE (the ONLY place this library syncs).
+  FzArgs b = a;
+  static long long* tl = nullptr;
+  const char* tl_env = getenv("COPE_FZ_TIMELINE");
+  const bool timeline = tl_env && atoi(tl_env) == mode;
+  if (timeline) {
+    if (!tl) cudaMalloc(&tl, 2 * 4096 * sizeof(long long));
+    cudaMemsetAsync(tl, 0, 2 * 4096 * sizeof(long long), s);
+    b.dbg = tl;
   }
-  COPE_REQUIRE(false, "sdf_fused: unknown mode %d", mode);
+  int rc = -1;
+  switch (mode) {
+    case FZ_FWD: rc = launch_t<FZ_FWD>(b, maps, s); break;
+    case FZ_TAN: rc = launch_t<FZ_TAN>(b, maps, s); break;
+    case FZ_ADJ: rc = launch_t<FZ_ADJ>(b, maps, s); break;
+    default: COPE_REQUIRE(false, "sdf_fused: unknown mode %d", mode);
+  }
+  if (timeline && rc == 0) {
+    static long long host[2 * 4096];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
+    const char* fn = getenv("COPE_FZ_TIMELINE_FILE");
+    if (FILE* f = fopen(fn ? fn : "fz_timeline.bin", "wb")) { fwrite(host, 1, sizeof(host), f); fclose(f); }
+  }
+  return rc;
 }
 
 }  // namespace cope

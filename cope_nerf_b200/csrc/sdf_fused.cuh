@@ -44,6 +44,7 @@ struct FzArgs {
   const float* d_sdf; int d_sdf_ld;
   float* eb0; float* eb1;    // [P x 64] fp32 (want_e)
   int has_d, store_out, want_e;
+  long long* dbg;            // optional timeline buffer (profiling builds): CTA 0 stamps clock64() per role
 };
 
 // 3-D tensor maps (64 x 128 x 1 boxes, 128B swizzle) over bf16 [layers][P][ld] buffers

@@ -25,6 +25,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -13,6 +13,7 @@
 //
 // Shared-memory operand layout: no swizzle, 8 x 16 B core matrices (see tc_common.cuh::smem_desc).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -538,7 +539,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (a.db != nullptr && col < a.Mp) a.part[tc_wgrad_part_floats_c() - (int64_t)148 * 256 + (size_t)blockIdx.x * 256 + col] = csum;
+      if (a.db != nullptr && col < a.Mp) {
+        if (a.atomic) { if (col < a.m_valid) atomicAdd(a.db + col, csum); }
+        else a.part[tc_wgrad_part_floats_c() - (int64_t)148 * 256 + (size_t)blockIdx.x * 256 + col] = csum;
+      }
     }
     // ---- partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
     const int q = warp & 3, half = warp >> 2;
@@ -546,15 +550,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float* part = a.part + (size_t)blockIdx.x * a.Mp * a.Np;
+    const bool vec_ok = (a.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
     for (int mb = 0; mb < nmb; ++mb) {
       const int m = mb * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + mb * 256 + ((uint32_t)(q * 32) << 16);
       for (int c = half; c < nch; c += 2) {
         float v[16];
         tmem_ld16(taddr + c * 16, v);
-        float4* o = reinterpret_cast<float4*>(part + (size_t)m * a.Np + c * 16);
+        if (a.atomic) {
+          // L2 reductions straight into dW: 148 CTAs x one tile each, no partial round trip through HBM
+          if (m < a.m_valid) {
+            float* o = a.dW + (size_t)m * a.ldw + c * 16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) {
+              const int n = c * 16 + 4 * i;
+              if (vec_ok && n + 4 <= a.n_valid) {
+                atomicAdd(reinterpret_cast<float4*>(o + 4 * i), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (n + k < a.n_valid) atomicAdd(o + 4 * i + k, v[4 * i + k]);
+              }
+            }
+          }
+        } else {
+          float4* o = reinterpret_cast<float4*>(part + (size_t)m * a.Np + c * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
       }
     }
   }
@@ -564,30 +587,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
 }
 
 // dW[m, n] += sum_c part[c][m][n] ;  db[m] += sum_c colpart[c][m]
+// One thread owns 4 consecutive n of one row (float4 loads) and keeps 8 partial tiles in flight; the tail block sums
+// the bias-gradient column partials.  Np % 4 == 0; n_valid is handled per element.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Mp, int Np, int m_valid, int n_valid,
                                     float* __restrict__ dW, int ldw, float* __restrict__ db) {
+  const int nq = (n_valid + 3) >> 2;                       // float4 groups per row
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nw = m_valid * n_valid;
-  if (i >= nw) {
-    const int m = i - nw;
+  const int nw = m_valid * nq * 4;
+  const int nw_pad = (nw + 31) & ~31;                      // whole warps: the shuffles below never meet the bias tail
+  if (i >= nw_pad) {
+    const int m = i - nw_pad;
     if (db == nullptr || m >= m_valid) return;
     const float* p = part + (tc_wgrad_part_floats_c() - (int64_t)148 * 256) + m;
-    float s = 0.0f;
-    for (int c = 0; c < nparts; ++c) s += p[(size_t)c * 256];
-    db[m] += s;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int c = 0;
+    for (; c + 4 <= nparts; c += 4) {
+      s0 += p[(size_t)c * 256]; s1 += p[(size_t)(c + 1) * 256]; s2 += p[(size_t)(c + 2) * 256]; s3 += p[(size_t)(c + 3) * 256];
+    }
+    for (; c < nparts; ++c) s0 += p[(size_t)c * 256];
+    db[m] += (s0 + s1) + (s2 + s3);
     return;
   }
-  const int m = i / n_valid, n = i - m * n_valid;
-  const float* p = part + (size_t)m * Np + n;
-  const size_t stride = (size_t)Mp * Np;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  int c = 0;
-  for (; c + 4 <= nparts; c += 4) {
-    s0 += p[(size_t)c * stride]; s1 += p[(size_t)(c + 1) * stride];
-    s2 += p[(size_t)(c + 2) * stride]; s3 += p[(size_t)(c + 3) * stride];
+  // 4 lanes share one float4 of the output: lane k sums partial tiles k, k+4, ... (8 loads in flight each)
+  const bool live = i < nw;
+  const int g = live ? i >> 2 : 0, sub = i & 3;
+  const int m = g / nq, n = (g - m * nq) * 4;
+  if (!live) nparts = 0;
+  const float4* p = reinterpret_cast<const float4*>(part + (size_t)m * Np + n);
+  const size_t stride = (size_t)Mp * Np / 4;
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  int c = sub;
+  for (; c + 28 < nparts; c += 32) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (size_t)(c + 4 * u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
   }
-  for (; c < nparts; ++c) s0 += p[(size_t)c * stride];
-  dW[(size_t)m * ldw + n] += (s0 + s1) + (s2 + s3);
+  for (; c < nparts; c += 4) {
+    const float4 v = __ldcs(p + (size_t)c * stride);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (live && sub == 0) {
+    float* o = dW + (size_t)m * ldw + n;
+    const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (n + k < n_valid) o[k] += r[k];
+  }
 }
 
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
@@ -615,9 +667,14 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
   int grid = (int)std::min<int64_t>(148, std::max<int64_t>(1, nchunks / 2));
   const int64_t per = (nchunks + grid - 1) / grid;
   grid = (int)((nchunks + per - 1) / per);                   // every CTA owns >= 1 chunk
-  tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(a, maps);
+  // default: L2 reductions into dW (fp32 add order varies run to run); COPE_WGRAD_DETERMINISTIC=1 keeps the per-CTA
+  // partial tiles + fixed-order reduction kernel
+  TcWgradArgs b = a;
+  b.atomic = getenv("COPE_WGRAD_DETERMINISTIC") == nullptr;
+  tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(b, maps);
   COPE_CHECK_LAUNCH("tc_wgrad");
-  const int n = a.m_valid * a.n_valid + (a.db ? a.m_valid : 0);
+  if (b.atomic) return 0;
+  const int n = ((a.m_valid * ((a.n_valid + 3) / 4) * 4 + 31) & ~31) + (a.db ? a.m_valid : 0);
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw, a.db);
   COPE_CHECK_LAUNCH("wgrad_reduce");
   return 0;

@@ -54,6 +54,7 @@ struct TcWgradArgs {
   float* dW; int ldw;
   float* part;                 // workspace: tc_wgrad_part_floats() floats (per-CTA partial tiles + column sums)
   float* db;                   // optional: db[m] += sum_p X[0][p, m]  (bias gradient, fused column sum of pair 0's X)
+  int atomic;                  // set by launch_tc_wgrad: CTAs add their tile straight into dW / db with L2 reductions
 };
 int64_t tc_wgrad_part_floats();
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);

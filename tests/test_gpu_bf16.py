@@ -240,5 +240,8 @@ def test_fused_chains_partial_tile(monkeypatch, n):
     monkeypatch.delenv("COPE_NO_FUSED")
     for k in a:
         assert torch.isfinite(a[k]).all(), k
-        lim = 0.999 if n >= 128 else 0.99      # a handful of points: the bf16 rounding noise of single rows is not averaged out
+        # The upstream gradients are i.i.d. zero-mean per point, so the reductions over points (dW, and ddirs through
+        # the colour net) are almost pure cancellation and amplify the ~0.5 % rounding-point differences of the two
+        # paths (same effect as in test_bf16_fields_backward_full_size); per-point outputs are held to 0.999.
+        lim = 0.999 if (n >= 128 and k in ("sdf", "grad", "rgb", "dx", "eb")) else 0.99
         assert cos_sim(a[k], b[k]) > lim, (k, n, cos_sim(a[k], b[k]), rel_err(a[k], b[k]))
