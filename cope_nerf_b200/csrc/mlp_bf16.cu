@@ -833,7 +833,18 @@ int64_t color_saved_floats_bf16(const MlpShape& m, int64_t P) {
 int64_t color_ws_floats_bf16(const MlpShape& m, int64_t P) {
   ColB c;
   if (make_colb(m, -1, &c)) return -1;
-  return ((int64_t)c.w_total + P * (2 * (int64_t)c.LD + 128) + 1) / 2 + P * 64 + tc_wgrad_part_floats() + 1024;
+  return ((int64_t)c.w_total + P * ((int64_t)c.top * c.LD + 128) + 1) / 2 + P * 64 + tc_wgrad_part_floats() + 1024;
+}
+
+static bool color_fused_enabled(const MlpShape& m, const ColB& c) {
+  const char* e = getenv("COPE_NO_FUSED");
+  if (e && (strstr(e, "col") || strstr(e, "all") || !strcmp(e, "1"))) return false;
+  return c.LD == 256 && c.CK == 320 && color_fused_supported(m, c.d_feat, c.rest);
+}
+static void cz_job(CzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a, int commit, int drain) {
+  FzJob& j = a->jobs[a->n_jobs++];
+  j.w_off = (uint32_t)w_off; j.Np = (uint16_t)Np; j.Kp = (uint16_t)Kp; j.acc = (uint8_t)acc; j.wait_a = (uint8_t)wait_a;
+  j.commit = (uint8_t)commit; j.pad = (uint8_t)drain;
 }
 
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
@@ -846,6 +857,23 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
   ColSavedB sv = col_saved_b(c, P, saved);
   bf16* wp = reinterpret_cast<bf16*>(ws);
   if (int rc = pack_color(m, c, Wflat, wp, true, false, s)) return rc;
+  if (feat_in_cin && color_fused_enabled(m, c)) {
+    // ---- fused chain: tail of the input built in the kernel, 4 ReLU layers + sigmoid, h_l TMA-stored for the backward
+    CzArgs a{};
+    a.P = P; a.Wflat = Wflat; a.wp = wp; a.n_lin = m.n_lin; a.d_out = m.d_out;
+    for (int l = 0; l < m.n_lin; ++l) a.b_off[l] = m.b_off[l];
+    a.x = x; a.dirs = dirs; a.dirs_group = dirs_group; a.Lv = Lv; a.normals = normals; a.rgb = rgb; a.rgb_saved = sv.rgb;
+    cz_job(&a, c.wf_off[0], r16(m.out[0]), c.CK, 0, 3, 1, 0);
+    for (int l = 1; l < c.top; ++l) cz_job(&a, c.wf_off[l], r16(m.out[l]), r64(m.in[l]), l & 1, 1, (l & 1) + 1, 0);
+    cz_job(&a, c.wf_off[c.top], r16(m.out[c.top]), r64(m.in[c.top]), c.top & 1, 1, (c.top & 1) + 1, 0);
+    CzMaps maps{};
+    const uint64_t Pu = (uint64_t)P, CK = (uint64_t)c.CK, LD = (uint64_t)c.LD;
+    if (int rc = make_tmap3(sv.cin, (uint64_t)c.d_feat, Pu, 1, CK, Pu * CK, &maps.feat)) return rc;
+    if (int rc = make_tmap3(sv.cin + c.d_feat, 64, Pu, 1, CK, Pu * CK, &maps.tail)) return rc;
+    if (int rc = make_tmap3(sv.H, LD, Pu, (uint64_t)c.top, LD, Pu * LD, &maps.H)) return rc;
+    maps.DZ = maps.H;
+    return launch_color_fused(CZ_FWD, a, maps, s);
+  }
   color_pack_bf16_kernel<<<g1(P * ((feat_in_cin ? c.CK - c.d_feat : c.CK) / 8)), 256, 0, s>>>(
       x, dirs, dirs_group, Lv, normals, feat, feat_ld, c.d_feat, P, sv.cin, c.CK, feat_in_cin ? c.d_feat : 0);
   COPE_CHECK_LAUNCH("color_pack_bf16");
@@ -868,11 +896,59 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
   if (P <= 0) return 0;
   ColSavedB sv = col_saved_b(c, P, const_cast<float*>(saved));
   bf16* wp = reinterpret_cast<bf16*>(ws);
-  bf16* B[2] = {wp + c.w_total, wp + c.w_total + (int64_t)P * c.LD};
-  bf16* dzt = B[1] + (int64_t)P * c.LD;                        // [P x 128]
+  bf16* DZ = wp + c.w_total;                                   // dz_l, l = 0..top-1 (fused chain); the layer-by-layer
+  bf16* B[2] = {DZ, DZ + (int64_t)P * c.LD};                   // path ping-pongs between the first two
+  bf16* dzt = DZ + (int64_t)c.top * P * c.LD;                  // [P x 128]
   float* rest = reinterpret_cast<float*>(dzt + (int64_t)P * 128);
   float* part = rest + P * 64;
   if (int rc = pack_color(m, c, Wflat, wp, false, true, s)) return rc;
+  if (!dfeat && color_fused_enabled(m, c)) {
+    // ---- fused adjoint chain (stores every dz_l), then the weight gradients from the stored tiles
+    const int F = c.d_feat, R = c.rest, top = c.top;
+    const bool want_rest = dx || ddirs || dnormals;
+    CzArgs a{};
+    a.P = P; a.Wflat = Wflat; a.wp = wp; a.n_lin = m.n_lin; a.d_out = m.d_out;
+    a.d_rgb = d_rgb; a.rgb_in = sv.rgb; a.rest = want_rest ? rest : nullptr; a.want_dfeat = dfeat_b16 != nullptr;
+    cz_job(&a, c.wt_off[top], r16(m.in[top]), r64(m.out[top]), 0, 1, 1, 2);
+    for (int l = top - 1; l >= 1; --l) {
+      const int st = top - l;
+      cz_job(&a, c.wt_off[l], r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1, 0);
+    }
+    cz_job(&a, c.wt0_rest_off, 64, r64(m.out[0]), 1, 1, 0, 0);
+    cz_job(&a, c.wt_off[0], r16(F), r64(m.out[0]), 0, 0, 1, 0xF);
+    CzMaps maps{};
+    const uint64_t Pu = (uint64_t)P, LD = (uint64_t)c.LD;
+    if (int rc = make_tmap3(dzt, 128, Pu, 1, 128, Pu * 128, &maps.tail)) return rc;
+    if (int rc = make_tmap3(sv.H, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.H)) return rc;
+    if (int rc = make_tmap3(DZ, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.DZ)) return rc;
+    if (dfeat_b16) {
+      if (int rc = make_tmap3(dfeat_b16, (uint64_t)r16(F), Pu, 1, (uint64_t)dfeat_b16_ld, Pu * (uint64_t)dfeat_b16_ld, &maps.feat)) return rc;
+    } else {
+      maps.feat = maps.DZ;
+    }
+    if (int rc = launch_color_fused(CZ_BWD, a, maps, s)) return rc;
+    for (int l = top; l >= 0; --l) {
+      TcWgradArgs w{};
+      w.P = P; w.Mp = r128(m.out[l]); w.m_valid = m.out[l]; w.n_pairs = 1; w.part = part;
+      w.X[0] = l == top ? dzt : DZ + (int64_t)l * P * c.LD; w.ldx[0] = l == top ? 128 : c.LD;
+      w.db = dWflat + m.b_off[l];
+      if (l > 0) {
+        w.Np = r16(m.in[l]); w.n_valid = m.in[l]; w.Y[0] = sv.h(l); w.ldy[0] = c.LD; w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l];
+        if (int rc = launch_tc_wgrad(w, s)) return rc;
+      } else {
+        w.Np = r16(F); w.n_valid = F; w.Y[0] = sv.cin; w.ldy[0] = c.CK; w.dW = dWflat + m.w_off[0] + R; w.ldw = m.in[0];
+        if (int rc = launch_tc_wgrad(w, s)) return rc;
+        w.db = nullptr;
+        w.Np = 64; w.n_valid = R; w.Y[0] = sv.cin + r64(F); w.dW = dWflat + m.w_off[0];
+        if (int rc = launch_tc_wgrad(w, s)) return rc;
+      }
+    }
+    if (want_rest) {
+      color_unpack_rest_kernel<<<g1(P * 11), 256, 0, s>>>(rest, dirs, dirs_group, Lv, P, dx, ddirs, dnormals);
+      COPE_CHECK_LAUNCH("color_unpack_rest");
+    }
+    return 0;
+  }
   sigmoid_bwd_bf16_kernel<<<g1(P * 128), 256, 0, s>>>(d_rgb, sv.rgb, m.d_out, dzt, 128, P);
   COPE_CHECK_LAUNCH("sigmoid_bwd_bf16");
   const bf16* dz = dzt;

@@ -19,18 +19,15 @@
 
 #include <algorithm>
 
+#include "chain_common.cuh"
 #include "tc_common.cuh"
 
 namespace cope {
 using namespace tc;
+using namespace chain;
 
 namespace {
 
-constexpr int kEpiWarps = 16;
-constexpr int kWProd = 16, kMma = 17, kStore = 18, kAuxW = 19;
-constexpr int kThreads = 20 * 32;
-constexpr int kPanel = 128 * 128;        // 128 rows x 64 bf16
-constexpr int kWStage = 256 * 64 * 2;    // N = 256 x K = 64: one weight chunk per activation panel
 // Shared-memory rings, sized per pass (everything next to the 64 KB activation tile).  Weight chunks are 32 KB
 // (N = 256 x K = 64): chunk c multiplies activation panel c, so the issuer pays one barrier round trip per FOUR
 // tcgen05.mma; an L2 -> SM bulk copy takes ~1100 cycles, which two slots cover while the epilogue paces the step.
@@ -38,23 +35,10 @@ template <int MODE> struct Cfg;
 template <> struct Cfg<FZ_FWD> { static constexpr int kW = 3, kAux = 2, kStg = 1, kBias = (COPE_MAX_LIN * 256 + 64) * 4; };
 template <> struct Cfg<FZ_TAN> { static constexpr int kW = 2, kAux = 5, kStg = 1, kBias = 0; };
 template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 2, kAux = 6, kStg = 0, kBias = 0; };
-constexpr int kMaxRing = 8;
-constexpr int kBarBytes = 512;
-template <int MODE> struct Lay {
-  static constexpr int oA = 0;
-  static constexpr int oW = oA + 4 * kPanel;
-  static constexpr int oAux = oW + Cfg<MODE>::kW * kWStage;
-  static constexpr int oStg = oAux + Cfg<MODE>::kAux * kPanel;
-  static constexpr int oBias = oStg + Cfg<MODE>::kStg * kPanel;
-  static constexpr int oBars = oBias + Cfg<MODE>::kBias;
-  static constexpr int kSmem = oBars + kBarBytes;
-  static_assert(kSmem <= 232448, "fused chain: shared memory budget");
-  static_assert(Cfg<MODE>::kW <= kMaxRing && Cfg<MODE>::kAux <= kMaxRing, "ring too deep for the barrier block");
-};
+template <int MODE> using Lay = ChainLay<4, Cfg<MODE>::kW, Cfg<MODE>::kAux, Cfg<MODE>::kStg, Cfg<MODE>::kBias>;
 
 constexpr float kC2 = -kSoftplusBeta * 1.4426950408889634f;   // exp(-100 h) = 2^(kC2 h)
 
-__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // softplus(beta=100)(a) = max(a, 0) + log1p(u) / 100, u = exp(-100 |a|): ONE MUFU; log1p(u)/u on (0, 1] is a degree-3
 // minimax polynomial (max rel. error 4.1e-4 of a term that is itself <= 0.7 % of the bf16-rounded activation scale).
 // Above torch's threshold (100 a > 20) u < 2.1e-9 and the result equals a in fp32.
@@ -65,133 +49,6 @@ __device__ __forceinline__ float softplus_poly(float a) {
   q = fmaf(u, q, 0.9996203753455154e-2f);
   return fmaf(u, q, fmaxf(a, 0.0f));
 }
-
-// byte offset of 16-byte chunk c8 (8 bf16) of row r inside one 128B-swizzled panel
-__device__ __forceinline__ uint32_t pan_off(int r, int c8) { return (uint32_t)r * 128 + (uint32_t)((c8 ^ (r & 7)) << 4); }
-// scalar element k (0..255) of row r inside the 4-panel tile
-__device__ __forceinline__ void put_elem(uint8_t* tile, int r, int k, float v) {
-  *reinterpret_cast<bf16*>(tile + (k >> 6) * kPanel + pan_off(r, (k & 63) >> 3) + (k & 7) * 2) = __float2bfloat16(v);
-}
-__device__ __forceinline__ void write16(uint8_t* panel, int r, int part, const float (&v)[16]) {
-  *reinterpret_cast<uint4*>(panel + pan_off(r, part * 2)) =
-      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-  *reinterpret_cast<uint4*>(panel + pan_off(r, part * 2 + 1)) =
-      make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-}
-struct Pk16 { uint32_t w[8]; };   // 16 bf16
-__device__ __forceinline__ Pk16 read16(const uint8_t* panel, int r, int part) {
-  const uint4 a = *reinterpret_cast<const uint4*>(panel + pan_off(r, part * 2));
-  const uint4 b = *reinterpret_cast<const uint4*>(panel + pan_off(r, part * 2 + 1));
-  Pk16 p;
-  p.w[0] = a.x; p.w[1] = a.y; p.w[2] = a.z; p.w[3] = a.w; p.w[4] = b.x; p.w[5] = b.y; p.w[6] = b.z; p.w[7] = b.w;
-  return p;
-}
-__device__ __forceinline__ float pk_get(const Pk16& p, int i) {
-  const uint32_t w = p.w[i >> 1];
-  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
-}
-
-__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_u32(src)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// timeline stamps (CTA 0 only, when a.dbg != nullptr): region `role` holds (tag << 48 | clock) entries
-struct Stamp {
-  long long* p; int n;
-  __device__ __forceinline__ void init(long long* base, int role) { p = (base && blockIdx.x == 0) ? base + role * 4096 : nullptr; n = 1; }
-  __device__ __forceinline__ void operator()(int tag) {
-    if (p && n < 4096) { p[n++] = ((long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFll); p[0] = n; }
-  }
-};
-
-// mbarrier wait for the single-thread roles (producers, MMA issuer, store issuer): they sit on the same schedulers as
-// the epilogue warps, so a failed probe parks the thread (suspend-time hint) instead of re-issuing the probe at once
-__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-#pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(20000u)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-
-struct Bars {
-  uint64_t *w_full, *w_empty, *aux_full, *aux_empty, *a_ready, *acc_full, *stg_full, *stg_empty, *a_free, *a_init, *tile_done,
-      *h_stored, *epi_done;
-};
-
-// epilogue-side view of the rings
-template <int kAuxRing, int kStgRing>
-struct EpiCtx {
-  uint8_t *sA, *sAux, *sStg;
-  Bars B;
-  int r, q, part, lane;
-  uint32_t ev, auxc, stgc, accp;
-  uint32_t tmem_base;
-
-  __device__ __forceinline__ void begin_event() {          // about to overwrite A panels: the previous event's TMA stores
-    if (ev > 0) mbar_wait(B.a_free, (ev - 1) & 1);         // must have finished reading them
-    ++ev;
-    st(510);
-  }
-  Stamp st;
-  __device__ __forceinline__ void panel_done(int j) {
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(B.a_ready + j);
-    st(600 + j);
-  }
-  __device__ __forceinline__ uint32_t wait_acc(int b) {
-    mbar_wait(B.acc_full + b, (accp >> b) & 1);
-    accp ^= 1u << b;
-    tc_fence_after();
-    st(500 + b);
-    return tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
-  }
-  // wait for the next auxiliary panel and pull this thread's 16 values; the slot is handed back (aux_release) only after
-  // the values have been CONSUMED: releasing right after the loads were issued let the refill overtake them
-  __device__ __forceinline__ Pk16 aux_take() {
-    const uint32_t slot = auxc % kAuxRing, par = (auxc / kAuxRing) & 1;
-    mbar_wait(B.aux_full + slot, par);
-    ++auxc;
-    st(520);
-    return read16(sAux + slot * kPanel, r, part);
-  }
-  __device__ __forceinline__ void aux_release(int n) {     // the n most recently taken slots
-    __syncwarp();
-    if (lane == 0)
-      for (int k = n; k >= 1; --k) mbar_arrive(B.aux_empty + ((auxc - k) % kAuxRing));
-  }
-  __device__ __forceinline__ void stg_put(const float (&v)[16]) {
-    constexpr uint32_t kS = kStgRing > 0 ? kStgRing : 1;
-    const uint32_t slot = stgc % kS, par = (stgc / kS) & 1;
-    mbar_wait(B.stg_empty + slot, par ^ 1);
-    write16(sStg + slot * kPanel, r, part, v);
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(B.stg_full + slot);
-    ++stgc;
-  }
-};
 
 // positional-encoding columns of input dimension dd (this thread's), value or Jacobian-vector product:
 //   TAN == false: col dd = x, sin block k = sin(2^k x), cos block k = cos(2^k x)
@@ -223,23 +80,11 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
   float* sBias = reinterpret_cast<float*>(smem + L::oBias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBars);
   Bars B;
-  B.w_full = bars; B.w_empty = bars + kMaxRing; B.aux_full = bars + 2 * kMaxRing; B.aux_empty = bars + 3 * kMaxRing;
-  B.a_ready = bars + 4 * kMaxRing; B.acc_full = B.a_ready + 4; B.stg_full = B.acc_full + 2; B.stg_empty = B.stg_full + 2;
-  B.a_free = B.stg_empty + 2; B.a_init = B.a_free + 1; B.tile_done = B.a_free + 2; B.h_stored = B.a_free + 3;
-  B.epi_done = B.a_free + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(B.a_free + 5);
-  static_assert((4 * kMaxRing + 4 + 2 + 2 + 2 + 5) * 8 + 8 <= kBarBytes, "barrier block too small");
+  B.carve(bars);
+  uint32_t* tmem_slot = B.tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kWRing; ++s) { mbar_init(B.w_full + s, 1); mbar_init(B.w_empty + s, 1); }
-    for (int s = 0; s < kAuxRing; ++s) { mbar_init(B.aux_full + s, 1); mbar_init(B.aux_empty + s, kEpiWarps); }
-    for (int j = 0; j < 4; ++j) mbar_init(B.a_ready + j, kEpiWarps);
-    for (int s = 0; s < 2; ++s) { mbar_init(B.acc_full + s, 1); mbar_init(B.stg_full + s, kEpiWarps); mbar_init(B.stg_empty + s, 1); }
-    mbar_init(B.a_free, 1); mbar_init(B.a_init, 1); mbar_init(B.tile_done, 1); mbar_init(B.h_stored, 1);
-    mbar_init(B.epi_done, kEpiWarps);
-    fence_barrier_init();
-  }
+  if (threadIdx.x == 0) B.init(kWRing, kAuxRing, 4);
   if (MODE == FZ_FWD) {
     for (int i = threadIdx.x; i < a.n_lin * 256; i += kThreads) {
       const int l = i >> 8, n = i & 255;

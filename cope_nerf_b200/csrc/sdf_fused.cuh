@@ -63,3 +63,42 @@ bool sdf_fused_supported(const MlpShape& m);
 int launch_sdf_fused(int mode, const FzArgs& a, const FzMaps& maps, cudaStream_t s);
 
 }  // namespace cope
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused colour-network chains (color_fused.cu): same engine, 5 activation panels for the 320-wide first layer
+namespace cope {
+
+enum CzMode : int {
+  CZ_FWD = 0,   // [feat | x | PE(dirs) | normals | x_lo] -> 4 ReLU layers (TMA-store h_1..h_4) -> sigmoid -> rgb
+  CZ_BWD = 1,   // dz_top -> ReLU-masked adjoints dz_3..dz_0 (TMA-stored for the weight gradients) -> d_feat (bf16) + d(x, PE, normals)
+};
+
+struct CzArgs {
+  int64_t P;
+  const float* Wflat;
+  const __nv_bfloat16* wp;
+  FzJob jobs[kFzMaxJobs];
+  int n_jobs;
+  int n_lin, d_out;
+  int64_t b_off[COPE_MAX_LIN];
+  // FWD: the 64-column tail of the input [x_hi(4) | PE_Lv(dirs) | normals(4) | x_lo(4) | 0] is built in the kernel
+  const float* x; const float* dirs; int dirs_group; int Lv; const float* normals;
+  float* rgb; float* rgb_saved;
+  // BWD
+  const float* d_rgb; const float* rgb_in;
+  float* rest;               // [P x 64] fp32: gradient w.r.t. the input tail, or null
+  int want_dfeat;
+  long long* dbg;
+};
+
+struct CzMaps {
+  CUtensorMap feat;     // FWD: feature block of the colour input [P x 256] (load)     BWD: d_feat [P x 256] (store)
+  CUtensorMap tail;     // FWD: tail block of the colour input [P x 64] (store)        BWD: dz_top [P x 128] (store)
+  CUtensorMap H;        // hidden activations h_1..h_4, layer index l-1 (FWD store, BWD load)
+  CUtensorMap DZ;       // BWD: adjoints dz_0..dz_3 (store)
+};
+
+bool color_fused_supported(const MlpShape& m, int d_feat, int rest_cols);
+int launch_color_fused(int mode, const CzArgs& a, const CzMaps& maps, cudaStream_t s);
+
+}  // namespace cope
