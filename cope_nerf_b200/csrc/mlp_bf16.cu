@@ -545,13 +545,15 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
       if (a.want_e) fz_job(&a, b.wt_off[0], 64, r64(m.out[0]), top & 1, 1, (top & 1) + 1);
       if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, s)) return rc;
       if (pass == 0) {
-        // ---- weight / bias gradients from the stored adjoints
+        // ---- weight / bias gradients from the stored adjoints: all layers in ONE launch
+        TcWgradArgs wg[COPE_MAX_LIN];
+        int nw = 0;
         {
           TcWgradArgs w{};
           w.P = P; w.Mp = r128(featW); w.Np = r16(m.in[top]); w.m_valid = featW; w.n_valid = m.in[top];
           w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
           w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part; w.db = dWflat + m.b_off[top] + 1;
-          if (int rc = launch_tc_wgrad(w, s)) return rc;
+          wg[nw++] = w;
           if (d_sdf) {
             if (int rc = wcolsum(sv.h(top), LD, d_sdf, d_sdf_ld, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
             sum_strided_kernel<<<(unsigned)std::min<int64_t>(296, ceil_div(P, 256)), 256, 0, s>>>(d_sdf, d_sdf_ld, P, dWflat + m.b_off[top]);
@@ -565,8 +567,9 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
           w.X[0] = ZBall + (int64_t)l * P * LD; w.ldx[0] = LD; w.Y[0] = sv.in(l); w.ldy[0] = sv.ld_in(l);
           w.X[1] = sv.dl(l); w.ldx[1] = LD; w.Y[1] = Tl(l); w.ldy[1] = ldT(l); w.n_pairs = 2;
           w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part; w.db = dWflat + m.b_off[l];
-          if (int rc = launch_tc_wgrad(w, s)) return rc;
+          wg[nw++] = w;
         }
+        if (int rc = launch_tc_wgrad_batch(wg, nw, s)) return rc;
       } else {
         pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, eb0, 64, b.skip > 0 ? eb1 : nullptr, 64, dx, m.d_in, dx_accumulate);
         COPE_CHECK_LAUNCH("pe_vjp");
@@ -927,6 +930,8 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
       maps.feat = maps.DZ;
     }
     if (int rc = launch_color_fused(CZ_BWD, a, maps, s)) return rc;
+    TcWgradArgs wg[COPE_MAX_LIN + 1];
+    int nw = 0;
     for (int l = top; l >= 0; --l) {
       TcWgradArgs w{};
       w.P = P; w.Mp = r128(m.out[l]); w.m_valid = m.out[l]; w.n_pairs = 1; w.part = part;
@@ -934,15 +939,16 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
       w.db = dWflat + m.b_off[l];
       if (l > 0) {
         w.Np = r16(m.in[l]); w.n_valid = m.in[l]; w.Y[0] = sv.h(l); w.ldy[0] = c.LD; w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l];
-        if (int rc = launch_tc_wgrad(w, s)) return rc;
+        wg[nw++] = w;
       } else {
         w.Np = r16(F); w.n_valid = F; w.Y[0] = sv.cin; w.ldy[0] = c.CK; w.dW = dWflat + m.w_off[0] + R; w.ldw = m.in[0];
-        if (int rc = launch_tc_wgrad(w, s)) return rc;
+        wg[nw++] = w;
         w.db = nullptr;
         w.Np = 64; w.n_valid = R; w.Y[0] = sv.cin + r64(F); w.dW = dWflat + m.w_off[0];
-        if (int rc = launch_tc_wgrad(w, s)) return rc;
+        wg[nw++] = w;
       }
     }
+    if (int rc = launch_tc_wgrad_batch(wg, nw, s)) return rc;
     if (want_rest) {
       color_unpack_rest_kernel<<<g1(P * 11), 256, 0, s>>>(rest, dirs, dirs_group, Lv, P, dx, ddirs, dnormals);
       COPE_CHECK_LAUNCH("color_unpack_rest");

@@ -436,13 +436,24 @@ constexpr int kWgChunkP = 64;            // points per pipeline stage
 constexpr int kWgBoxBytes = 64 * kWgChunkP * 2;   // one TMA box: 64 columns x 64 points, 128B-swizzled (8 KB)
 
 struct WgMaps { CUtensorMap x[2], y[2]; };
+// several weight-gradient problems in ONE launch: problem i owns CTAs [cta0[i], cta0[i+1]); far fewer (and fatter) point
+// slices per problem than one launch each, so the per-CTA tile flush is paid ~18 instead of 148 times per layer
+constexpr int kWgMaxProb = 12;
+struct WgBatch { TcWgradArgs p[kWgMaxProb]; int cta0[kWgMaxProb + 1]; int n; };
+struct WgBatchMaps { WgMaps m[kWgMaxProb]; };
 // workspace = 148 partial tiles [256 x 256] + 148 partial column-sum rows [256]
 __host__ __device__ constexpr int64_t tc_wgrad_part_floats_c() { return (int64_t)148 * 256 * 256 + (int64_t)148 * 256; }
 int64_t tc_wgrad_part_floats() { return tc_wgrad_part_floats_c(); }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradArgs a, const __grid_constant__ WgMaps maps) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgBatch batch,
+                                                                 const __grid_constant__ WgBatchMaps bmaps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int pi = 0;
+  while (pi + 1 < batch.n && (int)blockIdx.x >= batch.cta0[pi + 1]) ++pi;
+  const TcWgradArgs& a = batch.p[pi];
+  const WgMaps& maps = bmaps.m[pi];
+  const int slice = (int)blockIdx.x - batch.cta0[pi], nslices = batch.cta0[pi + 1] - batch.cta0[pi];
   // stage = X tile (Mp/64 boxes) followed by Y tile (Np/64 boxes); box b of a tile holds columns [64b, 64b+64)
   const int xb = a.Mp >> 6, yb = a.Np >> 6;
   const uint32_t xbytes = xb * kWgBoxBytes, ybytes = yb * kWgBoxBytes;
@@ -465,8 +476,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
 
   // this CTA's slice of points (multiples of the stage size); the host sizes the grid so every CTA has work
   const int64_t nchunks_total = (a.P + kWgChunkP - 1) / kWgChunkP;
-  const int64_t per = (nchunks_total + gridDim.x - 1) / gridDim.x;
-  const int64_t ch0 = (int64_t)blockIdx.x * per, ch1 = min(nchunks_total, ch0 + per);
+  const int64_t per = (nchunks_total + nslices - 1) / nslices;
+  const int64_t ch0 = (int64_t)slice * per, ch1 = min(nchunks_total, ch0 + per);
   const int nmb = a.Mp / 128;
   const bool have_work = ch0 < ch1;
 
@@ -541,7 +552,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
       }
       if (a.db != nullptr && col < a.Mp) {
         if (a.atomic) { if (col < a.m_valid) atomicAdd(a.db + col, csum); }
-        else a.part[tc_wgrad_part_floats_c() - (int64_t)148 * 256 + (size_t)blockIdx.x * 256 + col] = csum;
+        else a.part[tc_wgrad_part_floats_c() - (int64_t)148 * 256 + (size_t)slice * 256 + col] = csum;
       }
     }
     // ---- partial tile of this CTA -> part[blockIdx.x][Mp][Np] (plain stores; wgrad_reduce_kernel sums them)
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(const TcWgradAr
     const int nch = a.Np / 16;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float* part = a.part + (size_t)blockIdx.x * a.Mp * a.Np;
+    float* part = a.part + (size_t)slice * a.Mp * a.Np;
     const bool vec_ok = (a.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
     for (int mb = 0; mb < nmb; ++mb) {
       const int m = mb * 128 + q * 32 + lane;
@@ -642,42 +653,118 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, 
   }
 }
 
-int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
-  if (a.P <= 0 || a.n_pairs <= 0) return 0;
+static int wgrad_check(const TcWgradArgs& a) {
   COPE_REQUIRE((a.Mp == 128 || a.Mp == 256) && a.Np % 64 == 0 && a.Np >= 64 && a.Np <= 256,
                "tc_wgrad: Mp=%d Np=%d unsupported (Mp in {128,256}, Np multiple of 64)", a.Mp, a.Np);
-  COPE_REQUIRE(a.part != nullptr, "tc_wgrad: partial-sum workspace missing");
   for (int i = 0; i < a.n_pairs; ++i)
     COPE_REQUIRE(a.ldx[i] % 8 == 0 && a.ldy[i] % 8 == 0 && a.ldx[i] >= a.Mp && a.ldy[i] >= a.Np,
                  "tc_wgrad: operand %d leading dims (%d,%d) must cover the padded tile (%d,%d)", i, a.ldx[i], a.ldy[i], a.Mp, a.Np);
+  return 0;
+}
+static int wgrad_maps(const TcWgradArgs& a, WgMaps* maps) {
+  for (int i = 0; i < 2; ++i) {
+    const int q = i < a.n_pairs ? i : 0;
+    if (int rc = make_tmap(a.X[q], (uint64_t)a.ldx[q], (uint64_t)a.P, (uint64_t)a.ldx[q], kWgChunkP, &maps->x[i])) return rc;
+    if (int rc = make_tmap(a.Y[q], (uint64_t)a.ldy[q], (uint64_t)a.P, (uint64_t)a.ldy[q], kWgChunkP, &maps->y[i])) return rc;
+  }
+  return 0;
+}
+static int wgrad_attr() {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     COPE_REQUIRE(e == cudaSuccess, "tc_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t smem = (size_t)kWgStages * ((a.Mp >> 6) + (a.Np >> 6)) * kWgBoxBytes + 256;
-  WgMaps maps;
-  for (int i = 0; i < 2; ++i) {
-    const int q = i < a.n_pairs ? i : 0;
-    if (int rc = make_tmap(a.X[q], (uint64_t)a.ldx[q], (uint64_t)a.P, (uint64_t)a.ldx[q], kWgChunkP, &maps.x[i])) return rc;
-    if (int rc = make_tmap(a.Y[q], (uint64_t)a.ldy[q], (uint64_t)a.P, (uint64_t)a.ldy[q], kWgChunkP, &maps.y[i])) return rc;
-  }
+  return 0;
+}
+static size_t wgrad_smem(const TcWgradArgs& a) { return (size_t)kWgStages * ((a.Mp >> 6) + (a.Np >> 6)) * kWgBoxBytes + 256; }
+
+int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
+  if (a.P <= 0 || a.n_pairs <= 0) return 0;
+  if (int rc = wgrad_check(a)) return rc;
+  COPE_REQUIRE(a.part != nullptr, "tc_wgrad: partial-sum workspace missing");
+  if (int rc = wgrad_attr()) return rc;
+  WgBatch* batch = new WgBatch();
+  WgBatchMaps* maps = new WgBatchMaps();
+  int rc = wgrad_maps(a, &maps->m[0]);
   const int64_t nchunks = (a.P + kWgChunkP - 1) / kWgChunkP;
   int grid = (int)std::min<int64_t>(148, std::max<int64_t>(1, nchunks / 2));
   const int64_t per = (nchunks + grid - 1) / grid;
   grid = (int)((nchunks + per - 1) / per);                   // every CTA owns >= 1 chunk
   // default: L2 reductions into dW (fp32 add order varies run to run); COPE_WGRAD_DETERMINISTIC=1 keeps the per-CTA
   // partial tiles + fixed-order reduction kernel
-  TcWgradArgs b = a;
-  b.atomic = getenv("COPE_WGRAD_DETERMINISTIC") == nullptr;
-  tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(b, maps);
-  COPE_CHECK_LAUNCH("tc_wgrad");
-  if (b.atomic) return 0;
+  // (rows of dW that are not 16-byte aligned would fall back to scalar reductions, which are slower than the reduce kernel)
+  batch->p[0] = a;
+  batch->p[0].atomic = getenv("COPE_WGRAD_DETERMINISTIC") == nullptr && (a.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
+  batch->cta0[0] = 0; batch->cta0[1] = grid; batch->n = 1;
+  const bool atomic = batch->p[0].atomic != 0;
+  if (rc == 0) {
+    tc_wgrad_kernel<<<grid, kTcThreads, wgrad_smem(a), s>>>(*batch, *maps);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tc_wgrad: launch failed: %s", cudaGetErrorString(e)); rc = -2; }
+  }
+  delete batch;
+  delete maps;
+  if (rc) return rc;
+  if (atomic) return 0;
   const int n = ((a.m_valid * ((a.n_valid + 3) / 4) * 4 + 31) & ~31) + (a.db ? a.m_valid : 0);
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(a.part, grid, a.Mp, a.Np, a.m_valid, a.n_valid, a.dW, a.ldw, a.db);
   COPE_CHECK_LAUNCH("wgrad_reduce");
   return 0;
+}
+
+// All problems in one launch (L2 reductions into dW / db); CTAs are shared out in proportion to the bytes each problem
+// streams.  COPE_WGRAD_DETERMINISTIC=1 falls back to one launch per problem with the fixed-order reduction.
+int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (getenv("COPE_WGRAD_DETERMINISTIC") != nullptr || n > kWgMaxProb) {
+    for (int i = 0; i < n; ++i)
+      if (int rc = launch_tc_wgrad(probs[i], s)) return rc;
+    return 0;
+  }
+  if (int rc = wgrad_attr()) return rc;
+  WgBatch* batch = new WgBatch();
+  WgBatchMaps* maps = new WgBatchMaps();
+  int rc = 0, m = 0;
+  double w[kWgMaxProb], wsum = 0.0;
+  size_t smem = 0;
+  for (int i = 0; i < n && rc == 0; ++i) {
+    const TcWgradArgs& a = probs[i];
+    if (a.P <= 0 || a.n_pairs <= 0) continue;
+    rc = wgrad_check(a);
+    if (rc == 0) rc = wgrad_maps(a, &maps->m[m]);
+    batch->p[m] = a;
+    batch->p[m].atomic = 1;
+    w[m] = (double)a.P * (a.Mp + a.Np) * a.n_pairs + 2.0e6;      // streamed elements + a fixed cost for the tile flush
+    wsum += w[m];
+    smem = std::max(smem, wgrad_smem(a));
+    ++m;
+  }
+  if (rc == 0 && m > 0) {
+    int total = 0, nct[kWgMaxProb];
+    for (int i = 0; i < m; ++i) {
+      const int64_t nchunks = (batch->p[i].P + kWgChunkP - 1) / kWgChunkP;
+      nct[i] = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)(148.0 * w[i] / wsum)));
+      total += nct[i];
+    }
+    for (int i = 0; total < 148 && i < 8 * m; ++i) {           // hand the left-over SMs to the heaviest problems
+      const int k = i % m;
+      const int64_t nchunks = (batch->p[k].P + kWgChunkP - 1) / kWgChunkP;
+      if (w[k] * m >= wsum && nct[k] < nchunks) { ++nct[k]; ++total; }
+    }
+    batch->cta0[0] = 0;
+    for (int i = 0; i < m; ++i) batch->cta0[i + 1] = batch->cta0[i] + nct[i];
+    batch->n = m;
+    tc_wgrad_kernel<<<batch->cta0[m], kTcThreads, smem, s>>>(*batch, *maps);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tc_wgrad_batch: launch failed: %s", cudaGetErrorString(e)); rc = -2; }
+  }
+  delete batch;
+  delete maps;
+  return rc;
 }
 
 // ================================================================================================ packing
