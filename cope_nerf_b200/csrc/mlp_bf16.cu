@@ -108,31 +108,57 @@ __global__ void bcast_sp_bf16_kernel(const float* __restrict__ w, const bf16* __
   *reinterpret_cast<uint4*>(D + p * ldd + c0) = q;
 }
 
-// out[c] += sum_p w[p*ldw] * X[p, c]   (w == null -> 1).  One thread per column PAIR, 4 independent row streams.
-__global__ void wcolsum_bf16_kernel(const bf16* __restrict__ X, int ld, const float* __restrict__ w, int ldw, int64_t P,
-                                    int n, int rows_per_block, float* __restrict__ out) {
+// out[c] += sum_p w[p*ldw] * X[p, c]   (w == null -> 1), n <= 256 columns (n % 8 == 0).  One warp reads whole 512-byte rows
+// (16 bytes per lane), 8 warps per block take interleaved rows, 4 rows in flight per warp; block partials meet in shared
+// memory and leave as one atomic per column.
+__global__ void __launch_bounds__(256) wcolsum_bf16_kernel(const bf16* __restrict__ X, int ld, const float* __restrict__ w, int ldw,
+                                                           int64_t P, int n, int rows_per_block, float* __restrict__ out) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
-  for (int c = threadIdx.x * 2; c < n; c += blockDim.x * 2) {
-    float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
-    int64_t p = p0;
-    for (; p + 4 <= p1; p += 4) {
+  const int c0 = lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < n) {
+    int64_t p = p0 + warp;
+    for (; p + 24 < p1; p += 32) {
+      uint4 q[4];
+      float wv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t q = *reinterpret_cast<const uint32_t*>(X + (p + u) * ld + c);
-        const float wv = w ? w[(p + u) * ldw] : 1.0f;
-        a0[u] += wv * tc::bf16_lo(q);
-        a1[u] += wv * tc::bf16_hi(q);
+        q[u] = __ldcs(reinterpret_cast<const uint4*>(X + (p + 8 * u) * ld + c0));
+        wv[u] = w ? w[(p + 8 * u) * ldw] : 1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t ww[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] = fmaf(wv[u], tc::bf16_lo(ww[k]), acc[2 * k]);
+          acc[2 * k + 1] = fmaf(wv[u], tc::bf16_hi(ww[k]), acc[2 * k + 1]);
+        }
       }
     }
-    for (; p < p1; ++p) {
-      const uint32_t q = *reinterpret_cast<const uint32_t*>(X + p * ld + c);
+    for (; p < p1; p += 8) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(X + p * ld + c0));
       const float wv = w ? w[p * ldw] : 1.0f;
-      a0[0] += wv * tc::bf16_lo(q);
-      a1[0] += wv * tc::bf16_hi(q);
+      const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] = fmaf(wv, tc::bf16_lo(ww[k]), acc[2 * k]);
+        acc[2 * k + 1] = fmaf(wv, tc::bf16_hi(ww[k]), acc[2 * k + 1]);
+      }
     }
-    atomicAdd(out + c, (a0[0] + a0[1]) + (a0[2] + a0[3]));
-    if (c + 1 < n) atomicAdd(out + c + 1, (a1[0] + a1[1]) + (a1[2] + a1[3]));
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[warp][c0 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c < n) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][c];
+    atomicAdd(out + c, s);
   }
 }
 __global__ void colsum_f32_strided_kernel(const float* __restrict__ X, int ld, int64_t P, int n, int rows_per_block,
@@ -186,7 +212,9 @@ __global__ void zero_cols_bf16_kernel(bf16* __restrict__ dst, int ld, int64_t P,
 
 static int wcolsum(const bf16* X, int ld, const float* w, int ldw, int64_t P, int n, float* out, cudaStream_t s) {
   if (P <= 0 || n <= 0) return 0;
-  wcolsum_bf16_kernel<<<g1(P, 128), 128, 0, s>>>(X, ld, w, ldw, P, n, 128, out);
+  COPE_REQUIRE(n <= 256 && n % 8 == 0 && ld % 8 == 0, "wcolsum: n=%d (<= 256, multiple of 8) ld=%d (multiple of 8)", n, ld);
+  const int rows = 256;
+  wcolsum_bf16_kernel<<<(unsigned)ceil_div(P, rows), 256, 0, s>>>(X, ld, w, ldw, P, n, rows, out);
   COPE_CHECK_LAUNCH("wcolsum_bf16");
   return 0;
 }

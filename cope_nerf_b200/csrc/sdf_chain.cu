@@ -121,22 +121,25 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, aph = 0;     // aph: bit j = parity to wait for on a_ready[j]
+      // descriptors: only the 14-bit start-address field (16-byte units) moves between MMAs
+      const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA), 16, 1024);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l <= top; ++l) {
           const int nkc = a.Kp[l] >> 6;
           const uint32_t idesc = idesc_bf16(128, a.Np[l], 0, 0);
           const uint32_t b_lbo = (uint32_t)a.Np[l] * 16;
           const uint32_t d_tmem = tmem_base + (l & 1) * 256;
+          const uint64_t bdesc0 = smem_desc(smem_u32(sW), b_lbo, 128);
+          const uint32_t b_kstep = (2 * b_lbo) >> 4;
           for (int c = 0; c < nkc; ++c) {
             ch_wait_park(a_ready + c, (aph >> c) & 1);
             aph ^= 1u << c;
             ch_wait_park(w_full + stage, phase);
             tc_fence_after();
-            const uint32_t sAa = smem_u32(sA + c * kPanelBytes), sWa = smem_u32(sW + stage * kWChunkBytes);
+            const uint64_t ad = adesc0 + (uint64_t)(c * (kPanelBytes >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(stage * (kWChunkBytes >> 4));
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(d_tmem, smem_desc_sw128(sAa + ks * 32, 16, 1024), smem_desc(sWa + ks * 2 * b_lbo, b_lbo, 128), idesc,
-                        (c | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(d_tmem, ad + ks * 2, bd + ks * b_kstep, idesc, (c | ks) != 0);
             umma_commit(w_empty + stage);
             if (++stage == kWRing) { stage = 0; phase ^= 1; }
           }
