@@ -75,15 +75,36 @@ def main():
             L.call("cope_merge_z", z112, new_z, s112, new_z, N, 112, 16, zo, so, st)
         x = torch.cat([torch.randn(P, 3, device=dev) * 0.6, torch.zeros(P, 1, device=dev)], -1)
         flat = rnd.sdf_network.flat_weights().detach()
+        # render-MLP stage through the C ABI (fused chains + batched weight gradients): SDF value + gradient + colour,
+        # forward and backward incl. the double backward, 6 F_sdf + 3 F_col FLOP per point
+        mlp = None
+        if P <= 16384 * 128:
+            sn, cn = rnd.sdf_network, rnd.color_network
+            cflat = cn.flat_weights().detach()
+            o_sdf, o_grad, o_rgb = f(P, 1), f(P, 4), f(P, 3)
+            sdf_saved = f(L.query("cope_sdf_saved_floats", sn.desc, P, 1, C.PREC_BF16))
+            col_saved = f(L.query("cope_color_saved_floats", cn.desc, P, C.PREC_BF16))
+            ws = f(L.query("cope_render_mlp_ws_floats", sn.desc, cn.desc, P, C.PREC_BF16))
+            dirs_pp = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=-1)
+            g_sdf, g_grad0, g_rgb = torch.randn(P, 1, device=dev) * 1e-3, torch.randn(P, 4, device=dev) * 1e-3, torch.randn(P, 3, device=dev) * 1e-3
+            dWs, dWc, dx, ddirs, g_grad = torch.zeros_like(flat), torch.zeros_like(cflat), torch.zeros(P, 4, device=dev), f(P, 3), f(P, 4)
+
+            def mlp():
+                L.call("cope_render_mlp_fwd", sn.desc, flat, cn.desc, cflat, x, dirs_pp, S, cn.multires_view, P, o_sdf, o_grad, o_rgb,
+                       sdf_saved, col_saved, ws, C.PREC_BF16, st)
+                g_grad.copy_(g_grad0)
+                L.call("cope_render_mlp_bwd", sn.desc, flat, cn.desc, cflat, x, dirs_pp, S, cn.multires_view, P, sdf_saved, col_saved,
+                       g_sdf, g_grad, g_rgb, dWs, dWc, dx, ddirs, ws, C.PREC_BF16, st)
         rows = [
             ("composite_fwd", comp_fwd, N * (S * 36 + 44), "hbm"),                # z,dists,sdf 12 + grad 16 + rgb 12 in; w 4 out
             ("composite_bwd", comp_bwd, N * (S * 84 + 60), "hbm"),                # 40 in + d_w 4 + d_grad rw 32 + d_sdf 4 + d_rgb 12 - z
             ("upsample", ups, N * ((S - 16) * 8 + 64), "hbm"),
             ("merge_z", mrg, N * (2 * (112 + 16) * 4 + 2 * S * 4), "hbm"),
             ("sdf_query_chain", lambda: rnd.sdf_network.query_flat(flat, x), P * 918016, "tensor"),
+            ("render_mlp_fwd_bwd", mlp, P * (6 * 1049088 + 3 * 543744), "tensor"),
         ]
         for name, fn, work, bound in rows:
-            if name == "sdf_query_chain" and N > 65536:
+            if fn is None or (name == "sdf_query_chain" and N > 65536):
                 continue
             t = timeit(fn)
             if bound == "hbm":

@@ -564,7 +564,6 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
       fz_common(m, b, Wflat, wp, x, P, &a);
       a.d_sdf = d_sdf; a.d_sdf_ld = d_sdf_ld; a.eb0 = eb0; a.eb1 = eb1;
       a.has_d = pass == 0; a.store_out = pass == 0; a.want_e = pass == 1;
-      if (const char* dbg = getenv("COPE_DBG_ADJ")) { const int f = atoi(dbg); if (pass == 1) { if (f & 1) a.has_d = 1; if (f & 2) a.store_out = 1; } if (pass == 0 && (f & 4)) a.want_e = 1; }
       fz_job(&a, b.wt_off[top], r16(m.in[top]), r64(featW), 0, 2, 1);
       for (int l = top - 1; l >= 1; --l) {
         const int st = top - l;

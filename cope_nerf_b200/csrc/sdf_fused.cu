@@ -194,9 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
         const int row0 = tile * 128;
         if (MODE == FZ_FWD) {
           store_tile(&tm.in0, row0, 0, 1, true);                                  // PE
-          for (int l = 0; l < top; ++l) store_tile(&tm.H, row0, l, 4, true);      // H_{l+1}
-          bulk_wait0();                                                           // H tiles globally visible:
-          mbar_arrive(B.h_stored);                                                // the sweep may load them back
+          for (int l = 0; l < top; ++l) {
+            store_tile(&tm.H, row0, l, 4, true);                                  // H_{l+1}
+            if (l == top - 2) {                 // H_1..H_{top-1} written (H_top is never reloaded): while the last value
+              bulk_wait0();                     // layer and the output layer run, make them globally visible and let the
+              mbar_arrive(B.h_stored);          // auxiliary producer start loading them back for the reverse sweep
+            }
+          }
           if (a.has_feat)
             for (int j = 0; j < 4; ++j) store_stg(&tm.out, j * 64, row0, 0);      // feature -> colour input slot
           for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, true); // delta_l
@@ -425,6 +429,16 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaf(-v[i], ex2(pk_get(hp, i) * hc), v[i]);
               }
+            } else if (n0 >= nsplit && ((n0 - nsplit) & 3) == 0) {
+              // PE part of the skip input: gradient w.r.t. the encoding, fp32, four 16-byte stores
+              if (ok) {
+                float4* o = reinterpret_cast<float4*>(a.ge1 + m * 64 + (n0 - nsplit));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  o[i] = make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.0f;
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -494,6 +508,15 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaf(-v[i], ex2(pk_get(hp, i) * hc), v[i] + pk_get(dp, i));
               }
+            } else if (n0 >= nsplit && ((n0 - nsplit) & 3) == 0) {
+              if (ok && a.want_e) {
+                float4* o = reinterpret_cast<float4*>(a.eb1 + m * 64 + (n0 - nsplit));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  o[i] = make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.0f;
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
