@@ -43,6 +43,7 @@ _SIGS = {
     "cope_embed_fwd": (_i, [_f, _l, _i, _i, _f, _f]),
     "cope_sdf_saved_floats": (_l, [_D, _l, _i, _i]),
     "cope_sdf_ws_floats": (_l, [_D, _l, _i]),
+    "cope_sdf_query_ws_floats": (_l, [_D, _l, _i]),
     "cope_sdf_query": (_i, [_D, _f, _f, _l, _f, _f, _i, _f]),
     "cope_sdf_fwd": (_i, [_D, _f, _f, _l, _f, _i, _f, _i, _f, _f, _f, _i, _f]),
     "cope_sdf_bwd": (_i, [_D, _f, _f, _l, _f, _f, _i, _f, _i, _f, _f, _f, _i, _f, _i, _f]),

@@ -315,6 +315,16 @@ int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P) {
   return (bf + 1) / 2 + P * 4 * 64 + tc_wgrad_part_floats() + 1024;
 }
 
+// workspace of the sdf-only query: packed weights (the fused chain needs nothing else); the layer-by-layer fallback adds the
+// PE and three activation buffers
+int64_t sdf_query_ws_floats_bf16(const MlpShape& m, int64_t P) {
+  SdfB b;
+  if (make_sdfb(m, &b)) return -1;
+  int64_t bf = (int64_t)b.w_total;
+  if (!sdf_chain_supported(m) || getenv("COPE_NO_CHAIN")) bf += P * (64 + 3 * (int64_t)b.LD);
+  return (bf + 1) / 2 + 1024;
+}
+
 // ------------------------------------------------------------------------------------------- SDF forward
 static int sdf_layers_fwd(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P,
                           const bf16* pe, bf16* const* hbuf /* hbuf[l] = input buffer of layer l (l>=1) */, float* sdf,

@@ -200,6 +200,13 @@ int64_t cope_sdf_ws_floats(const cope_mlp_desc* d, int64_t P, int prec) {
   return P * ((int64_t)(m.n_lin + 6) * ldw + 4 * m.pe_w);
 }
 
+int64_t cope_sdf_query_ws_floats(const cope_mlp_desc* d, int64_t P, int prec) {
+  MlpShape m;
+  if (make_shape(d, &m)) return -1;
+  if (prec == COPE_PREC_BF16) return sdf_query_ws_floats_bf16(m, P);
+  return P * ((int64_t)m.pe_w + 3 * (int64_t)m.ldh) + 64;
+}
+
 int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws,
                    int prec, cope_stream_t s_) {
   MlpShape m;

@@ -209,7 +209,7 @@ class SDFNetwork(_MlpBase):
         P = x.shape[0]
         x = x.contiguous().float()
         out = torch.empty(P, 1, dtype=torch.float32, device=x.device)
-        ws = L.scratch(L.query("cope_sdf_ws_floats", self.desc, P, self.precision), x.device)
+        ws = L.scratch(L.query("cope_sdf_query_ws_floats", self.desc, P, self.precision), x.device)
         L.call("cope_sdf_query", self.desc, L.ptr(flat), L.ptr(x), P, L.ptr(out), L.ptr(ws), self.precision,
                L.stream())
         return out

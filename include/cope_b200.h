@@ -76,6 +76,8 @@ int64_t cope_sdf_saved_floats(const cope_mlp_desc* d, int64_t P, int with_grad, 
 /* floats of scratch workspace needed by query / fwd / bwd */
 int64_t cope_sdf_ws_floats(const cope_mlp_desc* d, int64_t P, int prec);
 
+/* floats of workspace needed by cope_sdf_query alone (much smaller than the training workspace) */
+int64_t cope_sdf_query_ws_floats(const cope_mlp_desc* d, int64_t P, int prec);
 /* sdf only, no state kept: SDFNetwork.sdf under no_grad (neus_renderer.py:499, :292). sdf_out [P] */
 int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, int64_t P, float* sdf_out,
                    float* ws, int prec, cope_stream_t s);
