@@ -32,14 +32,39 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
+def eval_image(rnd, pk, dev, h, w, chunk):
+    """BASELINE.json configs[3]: full-image evaluation render (rgb + depth + normals, no backward) of an h x w frame,
+    ScanNet shapes (484 x 648, configs/Scannet/scene0079_00.yaml:11-12), through training.render_image."""
+    from bench import camera
+    f = 0.8 * w
+    K = torch.tensor([[2 * f / w, 0, 0, 0], [0, -2 * f / h, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)[None]
+    world = torch.eye(4, device=dev)
+    world[:3, 3] = torch.tensor([0.02, -0.03, 0.05], device=dev)
+    S = torch.eye(4, device=dev)[None]
+    t0 = torch.zeros(1, device=dev)
+    fn = lambda: C.training.render_image(rnd, world, K, S, h, w, t0, (0.01, 5.0), chunk=chunk)
+    t = timeit(fn, iters=3, warm=1)
+    rays = h * w
+    flop = rays * 440_983_552          # SURVEY.md 8d: 112 F_sdfq + 128 (2 F_sdf + F_col) per evaluation ray
+    print(json.dumps({"kernel": "eval_image_render", "height": h, "width": w, "rays": rays, "chunk": chunk, "ms": t * 1e3,
+                      "rays_per_s": rays / t, "achieved": flop / t / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                      "frac": flop / t / 1e12 / pk["bf16_sustained"], "bound": "tensor", "peak_source": pk["src"],
+                      "note": "pose -> rays -> 64+64 hierarchical sampling -> SDF value + gradient -> colour -> compositing -> "
+                              "normal / arg-max-depth maps; every result stays on the device"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, nargs="*", default=[4096, 16384, 65536, 262144])
+    ap.add_argument("--eval-image", type=int, nargs=2, default=[484, 648], metavar=("H", "W"))
+    ap.add_argument("--eval-chunk", type=int, default=16384)
     args = ap.parse_args()
     dev = torch.device("cuda")
     pk = peaks()
     torch.manual_seed(678)
     rnd = C.training.build_networks(device=dev, precision=C.PREC_BF16)
+    if args.eval_image[0] > 0:
+        eval_image(rnd, pk, dev, args.eval_image[0], args.eval_image[1], args.eval_chunk)
     S = 128
     for N in args.rays:
         P = N * S

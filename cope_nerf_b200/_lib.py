@@ -54,6 +54,9 @@ _SIGS = {
     "cope_render_mlp_ws_floats": (_l, [_D, _D, _l, _i]),
     "cope_render_mlp_fwd": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _f, _f, _i, _f]),
     "cope_dbg_render_bwd_eb_offset": (_l, [_D, _D, _l]),
+    "cope_render_mlp_infer_ws_floats": (_l, [_D, _D, _l, _i]),
+    "cope_render_mlp_infer": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _i, _f]),
+    "cope_eval_reduce": (_i, [_f, _f, _f, _f, _l, _i, _f, _f, _f]),
     "cope_render_mlp_bwd": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _f]),
     "cope_ray_points": (_i, [_f, _f, _f, _f, _f, _f, _i, _l, _i, _i, _f, _f, _f, _f]),
     "cope_ray_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),

@@ -147,10 +147,12 @@ __global__ void __launch_bounds__(kThreads, 1) color_fused_kernel(const __grid_c
         const int row0 = tile * 128;
         if (MODE == CZ_FWD) {
           wait_panel(4);                                                          // input tail -> saved colour input
-          tma_store_3d(&tm.tail, sA + 4 * kPanel, 0, row0, 0);
-          bulk_commit(); bulk_wait_read0();
+          if (!a.infer) {
+            tma_store_3d(&tm.tail, sA + 4 * kPanel, 0, row0, 0);
+            bulk_commit(); bulk_wait_read0();
+          }
           mbar_arrive(B.a_free);
-          for (int l = 0; l < top; ++l) store_tile(&tm.H, row0, l, true);         // h_{l+1}
+          for (int l = 0; l < top; ++l) store_tile(&tm.H, row0, l, !a.infer);     // h_{l+1}
         } else {
           wait_panel(0); wait_panel(1);                                           // dz_top, zero-padded to 128 columns
           tma_store_3d(&tm.tail, sA, 0, row0, 0);

@@ -370,7 +370,7 @@ static void fz_job(FzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a,
 // ge0 / ge1 (gradient w.r.t. the PE)
 static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P,
                          const SdfSavedB& sv, float* sdf, int sdf_ld, bf16* feat_b16, int feat_b16_ld, float* ge0, float* ge1,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool infer) {
   FzArgs a{};
   fz_common(m, b, Wflat, wp, x, P, &a);
   const int top = b.top;
@@ -381,12 +381,13 @@ static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, c
     const int st = top + 1 + (top - 1 - l);
     fz_job(&a, b.wt_off[l], l == 0 ? 64 : r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
   }
-  a.sdf = sdf; a.sdf_ld = sdf_ld; a.has_feat = feat_b16 != nullptr; a.ge0 = ge0; a.ge1 = ge1;
+  a.sdf = sdf; a.sdf_ld = sdf_ld; a.has_feat = feat_b16 != nullptr; a.ge0 = ge0; a.ge1 = ge1; a.infer = infer;
   FzMaps maps{};
   const uint64_t LD = (uint64_t)b.LD, Pu = (uint64_t)P;
   if (int rc = make_tmap3(sv.pe, 64, Pu, 1, 64, Pu * 64, &maps.in0)) return rc;
   if (int rc = make_tmap3(sv.H, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.H)) return rc;
-  if (int rc = make_tmap3(sv.D, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.D)) return rc;
+  if (infer) maps.D = maps.H;      // never stored: the saved block has no delta stack in inference
+  else if (int rc = make_tmap3(sv.D, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.D)) return rc;
   if (feat_b16) {
     if (int rc = make_tmap3(feat_b16, (uint64_t)b.featN, Pu, 1, (uint64_t)feat_b16_ld, Pu * (uint64_t)feat_b16_ld, &maps.out)) return rc;
   } else {
@@ -417,7 +418,7 @@ int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_
 }
 
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
-                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, bf16* feat_b16, int feat_b16_ld) {
+                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, bf16* feat_b16, int feat_b16_ld, bool infer) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   if (P <= 0) return 0;
@@ -427,7 +428,7 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   float* ge1 = ge0 + P * 64;
   if (int rc = pack_sdf(m, b, Wflat, wp, true, grad != nullptr, s)) return rc;
   if (grad && !feat && fused_enabled(m, b, "fwd")) {
-    if (int rc = sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, feat_b16, feat_b16_ld, ge0, ge1, s)) return rc;
+    if (int rc = sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, feat_b16, feat_b16_ld, ge0, ge1, s, infer)) return rc;
     pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, ge0, 64, b.skip > 0 ? ge1 : nullptr, 64, grad, m.d_in, 0);
     COPE_CHECK_LAUNCH("pe_vjp");
     return 0;
@@ -889,7 +890,7 @@ static void cz_job(CzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a,
 
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
                    const float* normals, const float* feat, int feat_ld, int64_t P, float* rgb, float* saved, float* ws,
-                   cudaStream_t s, bool feat_in_cin) {
+                   cudaStream_t s, bool feat_in_cin, bool infer) {
   ColB c;
   if (make_colb(m, Lv, &c)) return -1;
   COPE_REQUIRE(m.skip < 0, "bf16 colour path: skip connections are not supported");
@@ -902,7 +903,8 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
     CzArgs a{};
     a.P = P; a.Wflat = Wflat; a.wp = wp; a.n_lin = m.n_lin; a.d_out = m.d_out;
     for (int l = 0; l < m.n_lin; ++l) a.b_off[l] = m.b_off[l];
-    a.x = x; a.dirs = dirs; a.dirs_group = dirs_group; a.Lv = Lv; a.normals = normals; a.rgb = rgb; a.rgb_saved = sv.rgb;
+    a.x = x; a.dirs = dirs; a.dirs_group = dirs_group; a.Lv = Lv; a.normals = normals; a.rgb = rgb; a.rgb_saved = infer ? nullptr : sv.rgb;
+    a.infer = infer;
     cz_job(&a, c.wf_off[0], r16(m.out[0]), c.CK, 0, 3, 1, 0);
     for (int l = 1; l < c.top; ++l) cz_job(&a, c.wf_off[l], r16(m.out[l]), r64(m.in[l]), l & 1, 1, (l & 1) + 1, 0);
     cz_job(&a, c.wf_off[c.top], r16(m.out[c.top]), r64(m.in[c.top]), c.top & 1, 1, (c.top & 1) + 1, 0);

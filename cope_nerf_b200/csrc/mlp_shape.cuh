@@ -46,7 +46,7 @@ int64_t sdf_query_ws_floats_bf16(const MlpShape& m, int64_t P);
 int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s);
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
                  int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, __nv_bfloat16* feat_b16 = nullptr,
-                 int feat_b16_ld = 0);
+                 int feat_b16_ld = 0, bool infer = false);
 int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, const float* saved, const float* d_sdf,
                  int d_sdf_ld, const float* d_feat, int d_feat_ld, const float* dgrad, float* dWflat, float* dx,
                  int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws = false);
@@ -56,7 +56,7 @@ int64_t color_saved_floats_bf16(const MlpShape& m, int64_t P);
 int64_t color_ws_floats_bf16(const MlpShape& m, int64_t P);
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
                    const float* normals, const float* feat, int feat_ld, int64_t P, float* rgb, float* saved, float* ws,
-                   cudaStream_t s, bool feat_in_cin = false);
+                   cudaStream_t s, bool feat_in_cin = false, bool infer = false);
 int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int dirs_group, int Lv, int64_t P,
                    const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs, float* dnormals,
                    float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, __nv_bfloat16* dfeat_b16 = nullptr,

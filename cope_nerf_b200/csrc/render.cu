@@ -525,3 +525,48 @@ int cope_composite_bwd(const float* sdf, const float* grad, const float* rgb, co
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------ evaluation-render reductions
+// model/training.py:236-262: one warp per ray; weighted normal sum + arg-max-weight sample depth in the camera frame
+namespace cope {
+__global__ void eval_reduce_kernel(const float* __restrict__ w, const float4* __restrict__ grad, const float4* __restrict__ pts,
+                                   const float* __restrict__ M, int64_t N, int S, float* __restrict__ nrm, float* __restrict__ dhw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= N) return;
+  float ax = 0.0f, ay = 0.0f, az = 0.0f, best = -1.0f;
+  int besti = 0;
+  for (int s = lane; s < S; s += 32) {
+    const float wv = w[n * S + s];
+    const float4 g = grad[n * S + s];
+    ax = fmaf(wv, g.x, ax); ay = fmaf(wv, g.y, ay); az = fmaf(wv, g.z, az);
+    if (wv > best) { best = wv; besti = s; }          // first maximum within the lane (torch.max returns the first index)
+  }
+  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) {
+    nrm[n * 3 + 0] = M[0] * ax + M[1] * ay + M[2] * az;
+    nrm[n * 3 + 1] = M[4] * ax + M[5] * ay + M[6] * az;
+    nrm[n * 3 + 2] = M[8] * ax + M[9] * ay + M[10] * az;
+    const float4 p = pts[n * S + besti];
+    dhw[n] = -(M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
+  }
+}
+}  // namespace cope
+
+extern "C" int cope_eval_reduce(const float* weights, const float* grad, const float* pts, const float* world_mat, int64_t N, int S,
+                                float* normal_out, float* depth_hw_out, cope_stream_t s) {
+  using namespace cope;
+  if (N <= 0) return 0;
+  COPE_REQUIRE(S > 0 && weights && grad && pts && world_mat && normal_out && depth_hw_out, "eval_reduce: null argument");
+  eval_reduce_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, as_stream(s)>>>(weights, reinterpret_cast<const float4*>(grad),
+                                                                        reinterpret_cast<const float4*>(pts), world_mat, N, S,
+                                                                        normal_out, depth_hw_out);
+  COPE_CHECK_LAUNCH("eval_reduce");
+  return 0;
+}

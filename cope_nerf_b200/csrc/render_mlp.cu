@@ -45,6 +45,36 @@ int cope_render_mlp_fwd(const cope_mlp_desc* sd, const float* sdfW, const cope_m
   return cope_color_fwd(cd, colW, x, dirs, dirs_group, Lv, grad, feat, F, P, rgb, col_saved, rest, prec, s_);
 }
 
+/* ---- inference: same outputs as cope_render_mlp_fwd, nothing kept for a backward pass (full-image rendering, eval.py) */
+int64_t cope_render_mlp_infer_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
+  const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
+  const int64_t a = cope_sdf_saved_floats(sd, P, prec == COPE_PREC_BF16 ? 0 : 1, prec), b = cope_color_saved_floats(cd, P, prec);
+  if (w < 0 || a < 0 || b < 0) return -1;
+  return w + a + b + 256;
+}
+
+int cope_render_mlp_infer(const cope_mlp_desc* sd, const float* sdfW, const cope_mlp_desc* cd, const float* colW, const float* x,
+                          const float* dirs, int dirs_group, int Lv, int64_t P, float* sdf, float* grad, float* rgb, float* ws,
+                          int prec, cope_stream_t s_) {
+  MlpShape ms, mc;
+  if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
+  if (P <= 0) return 0;
+  const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
+  const int64_t a = cope_sdf_saved_floats(sd, P, prec == COPE_PREC_BF16 ? 0 : 1, prec);
+  COPE_REQUIRE(w >= 0 && a >= 0, "render_mlp_infer: unsupported network shape");
+  float* sdf_saved = ws + ((w + 63) / 64) * 64;
+  float* col_saved = sdf_saved + ((a + 63) / 64) * 64;
+  if (prec == COPE_PREC_BF16) {
+    cudaStream_t s = as_stream(s_);
+    int ld = 0;
+    __nv_bfloat16* cin = color_cin_slot(mc, Lv, P, col_saved, &ld);
+    COPE_REQUIRE(cin != nullptr, "render_mlp_infer: colour network shape not supported on the bf16 path");
+    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld, true)) return rc;
+    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true, true);
+  }
+  return cope_render_mlp_fwd(sd, sdfW, cd, colW, x, dirs, dirs_group, Lv, P, sdf, grad, rgb, sdf_saved, col_saved, ws, prec, s_);
+}
+
 int cope_render_mlp_bwd(const cope_mlp_desc* sd, const float* sdfW, const cope_mlp_desc* cd, const float* colW, const float* x,
                         const float* dirs, int dirs_group, int Lv, int64_t P, const float* sdf_saved, const float* col_saved,
                         const float* d_sdf, float* d_grad, const float* d_rgb, float* dW_sdf, float* dW_col, float* dx,

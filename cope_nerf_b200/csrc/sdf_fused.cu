@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
           }
           if (a.has_feat)
             for (int j = 0; j < 4; ++j) store_stg(&tm.out, j * 64, row0, 0);      // feature -> colour input slot
-          for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, true); // delta_l
+          for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, !a.infer); // delta_l
         } else if (MODE == FZ_TAN) {
           store_tile(&tm.in0, row0, 0, 1, true);                                  // T_0
           for (int l = 0; l < top; ++l) {

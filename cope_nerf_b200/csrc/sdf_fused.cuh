@@ -39,6 +39,7 @@ struct FzArgs {
   int64_t w_top_off;         // float offset of row 0 of the last layer inside Wflat
   // FWD
   float* sdf; int sdf_ld; int has_feat;
+  int infer;                 // FWD: no backward will follow: the reverse-sweep deltas are not stored
   float* ge0; float* ge1;    // [P x 64] fp32 gradients w.r.t. the PE (layer 0 / skip layer)
   // ADJ
   const float* d_sdf; int d_sdf_ld;
@@ -84,6 +85,7 @@ struct CzArgs {
   // FWD: the 64-column tail of the input [x_hi(4) | PE_Lv(dirs) | normals(4) | x_lo(4) | 0] is built in the kernel
   const float* x; const float* dirs; int dirs_group; int Lv; const float* normals;
   float* rgb; float* rgb_saved;
+  int infer;                 // FWD: no backward will follow: neither the input tail nor the hidden activations are stored
   // BWD
   const float* d_rgb; const float* rgb_in;
   float* rest;               // [P x 64] fp32: gradient w.r.t. the input tail, or null

@@ -139,6 +139,43 @@ class _RenderCoreFn(torch.autograd.Function):
                 None, None)
 
 
+def _render_core_infer(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far, n_coarse,
+                       cos_anneal, eval_mode):
+    """render_core (model/neus_renderer.py:307-450) without an autograd node: the MLP stage goes through
+    cope_render_mlp_infer, which keeps nothing for a backward pass.  Same 14 outputs as _RenderCoreFn.forward."""
+    sdf_net, col_net = rnd.sdf_network, rnd.color_network
+    dev = z.device
+    N, S = z.shape
+    P = N * S
+    s = L.stream()
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    rays_d_norm = rays_d_norm.contiguous().float()
+    z = z.contiguous()
+    near, far = near.contiguous().float(), far.contiguous().float()
+    tstep = time_step.reshape(-1)[:1].contiguous().float()
+    prec = sdf_net.precision
+    if prec != col_net.precision:
+        raise L.CopeError("SDF and colour networks must use the same precision inside NeuSRenderer")
+    pts = _f32(P, 4, device=dev)
+    dists, mid_z = _f32(N, S, device=dev), _f32(N, S, device=dev)
+    L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
+           n_coarse, N, S, 1, L.ptr(pts), L.ptr(dists), L.ptr(mid_z), s)
+    sdf, grad, rgb = _f32(P, 1, device=dev), _f32(P, 4, device=dev), _f32(P, 3, device=dev)
+    ws = L.scratch(L.query("cope_render_mlp_infer_ws_floats", sdf_net.desc, col_net.desc, P, prec), dev)
+    L.call("cope_render_mlp_infer", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
+           col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(ws), prec, s)
+    weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
+    color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
+    wsum, wmax, inv_s = _f32(N, 1, device=dev), _f32(N, 1, device=dev), _f32(1, device=dev)
+    L.call("cope_composite_fwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
+           L.ptr(rays_d_norm), L.ptr(variance), float(cos_anneal), int(eval_mode), N, S, L.ptr(weights),
+           L.ptr(color), L.ptr(depth), L.ptr(wz), L.ptr(cdf), L.ptr(wsum), L.ptr(wmax), L.ptr(inv_s), s)
+    normals = grad[:, :3].reshape(N, S, 3).contiguous()
+    flows = grad[:, 3:].clone().reshape(N, S, 1)
+    points = pts[:, :3].reshape(N, S, 3).contiguous()
+    return color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z, grad, pts
+
+
 class NeuSRenderer(nn.Module):
     """model/neus_renderer.py:107-584.  Constructor kwargs = the `neus_renderer` config section plus the five
     networks, as train.py:46-52 passes them."""
@@ -246,10 +283,19 @@ class NeuSRenderer(nn.Module):
         sdf_flat = self.sdf_network.flat_weights()
         col_flat = self.color_network.flat_weights()
         z, n_coarse = self.sample_z(rays_o, rays_d, time_step, near, far, eval, sdf_flat, it)
-        (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
-            _RenderCoreFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
-                                time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
+        extra = {}
+        if not torch.is_grad_enabled():
+            # inference (torch.no_grad(): render_eval / render_visdata, model/training.py:210-283): nothing kept for backward
+            (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z, grad4, pts4) = \
+                _render_core_infer(self, sdf_flat.detach(), col_flat.detach(), self.deviation_network.variance.detach(), rays_o,
+                                   rays_d, ray_d_norm, time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
+            extra = {'_grad4': grad4, '_pts4': pts4}      # packed (x,y,z,t) views for cope_eval_reduce
+        else:
+            (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
+                _RenderCoreFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
+                                    time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
         return {
+            **extra,
             'sdf': sdf,
             'color_fine': color,
             'depth_pred': depth,

@@ -103,3 +103,39 @@ def render_train_step(renderer, pose, cam_id, pixels, camera_mat, scale_mat, rgb
     loss, parts = neus_losses(out, rgb_gt, rgb_weight, eikonal_weight)
     (loss * loss_scale).backward()
     return loss.detach(), out, (o, d, dn)
+
+
+def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, depth_range, cos_anneal_ratio=1.0, it=1,
+                 chunk=8192, rays=None):
+    """Full-image evaluation render (model/training.py:157-283 render_visdata / eval.py:133-157 render_eval, the
+    rgb / depth / normal part) without the reference's 1024-ray chunks and per-chunk device -> host copies: the image is
+    rendered in `chunk`-ray launches, every result stays on the device.
+
+    Returns a dict of device tensors over all h*w pixels (row-major):
+      rgb (HW,3), depth_pred (HW,1) [= sum w z / |d|, eval mode], weighted_z_vals (HW,1),
+      depth_highest_weight (HW,) [-z of the arg-max-weight sample in the camera frame], normal (HW,3) [sum w n, rotated
+      into the camera frame by world_mat[:3,:3]].
+    `rays` = (first, count) restricts the render to a contiguous pixel range (multi-GPU: one range per rank)."""
+    from . import _lib as L
+    from .common import get_world_cameraOrigin_cameraRay, pixels_from_indices
+    dev = world_mat.device
+    first, count = rays if rays is not None else (0, h * w)
+    out = dict(rgb=torch.empty(count, 3, device=dev), depth_pred=torch.empty(count, 1, device=dev),
+               weighted_z_vals=torch.empty(count, 1, device=dev), depth_highest_weight=torch.empty(count, device=dev),
+               normal=torch.empty(count, 3, device=dev))
+    wm = world_mat.detach().contiguous().float()
+    with torch.no_grad():
+        for c0 in range(0, count, chunk):
+            n = min(chunk, count - c0)
+            idx = torch.arange(first + c0, first + c0 + n, device=dev)
+            pix = pixels_from_indices(idx, h, w)
+            o, d, dn = get_world_cameraOrigin_cameraRay(pix, camera_mat, world_mat, scale_mat)
+            near, far = near_far_from_sphere(o, d, depth_range)
+            ro = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=True)
+            S = ro['weights'].shape[1]
+            L.call("cope_eval_reduce", L.ptr(ro['weights']), L.ptr(ro['_grad4']), L.ptr(ro['_pts4']), L.ptr(wm), n, S,
+                   L.ptr(out['normal'][c0:c0 + n]), L.ptr(out['depth_highest_weight'][c0:c0 + n]), L.stream())
+            out['rgb'][c0:c0 + n] = ro['color_fine']
+            out['depth_pred'][c0:c0 + n] = ro['depth_pred']
+            out['weighted_z_vals'][c0:c0 + n] = ro['weighted_z_vals']
+    return out

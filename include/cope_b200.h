@@ -124,6 +124,14 @@ int cope_render_mlp_bwd(const cope_mlp_desc* sdf_desc, const float* sdfW, const 
                         const float* col_saved, const float* d_sdf, float* d_grad, const float* d_rgb, float* dW_sdf,
                         float* dW_col, float* dx, float* ddirs_pp, float* ws, int prec, cope_stream_t s);
 
+/* Inference form of cope_render_mlp_fwd (full-image rendering: model/training.py:210-283, eval.py:133-157): same sdf / grad /
+ * rgb, nothing is kept for a backward pass (on the bf16 path the reverse-sweep deltas, the colour net's hidden activations
+ * and its input tail are never written to HBM).  `ws` holds cope_render_mlp_infer_ws_floats floats. */
+int64_t cope_render_mlp_infer_ws_floats(const cope_mlp_desc* sdf_desc, const cope_mlp_desc* col_desc, int64_t P, int prec);
+int cope_render_mlp_infer(const cope_mlp_desc* sdf_desc, const float* sdfW, const cope_mlp_desc* col_desc, const float* colW,
+                          const float* x, const float* dirs, int dirs_group, int Lv, int64_t P, float* sdf, float* grad,
+                          float* rgb, float* ws, int prec, cope_stream_t s);
+
 /* test hook (bf16 path): float offset, inside the `ws` of cope_render_mlp_bwd, of the two [P x 64] fp32 buffers that hold
  * the value-path gradient w.r.t. the positional encoding (layer 0 / skip layer) before the PE backward folds them into dx */
 int64_t cope_dbg_render_bwd_eb_offset(const cope_mlp_desc* sdf_desc, const cope_mlp_desc* col_desc, int64_t P);
@@ -215,6 +223,11 @@ int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* B
 int64_t cope_tc_wgrad_ws_floats(void);
 int cope_tc_wgrad(int64_t P, int Mp, int Np, int m_valid, int n_valid, const void* X, int ldx, const void* Y, int ldy,
                   float* dW, int ldw, float* ws, cope_stream_t s);
+
+/* ---- per-ray image reductions of the evaluation render (model/training.py:236-262): normal[n] = R * sum_s w[n,s] * grad[n,s,:3]
+ * and depth_hw[n] = -(world_mat @ [pts[n, argmax_s w], 1]).z, world_mat = device pointer to a row-major 4x4 (R = its 3x3). */
+int cope_eval_reduce(const float* weights, const float* grad, const float* pts, const float* world_mat, int64_t N, int S,
+                     float* normal_out, float* depth_hw_out, cope_stream_t s);
 
 #ifdef __cplusplus
 }

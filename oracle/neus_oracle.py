@@ -22,7 +22,7 @@ __all__ = [
     "render",
     "vec2skew", "so3_exp", "make_c2w", "pose_forward", "camera_matrix", "pixel_grid", "patch_indices",
     "ray_generation", "near_far", "cos_anneal_ratio", "eikonal_loss", "rgb_l1_loss", "sdf_flow_loss",
-    "train_step", "DEFAULT_CFG",
+    "train_step", "render_image", "DEFAULT_CFG",
 ]
 
 # configs/default.yaml:103-156 (no scene config overrides any of these shapes)
@@ -447,3 +447,31 @@ def train_step(P, pose, pixels, camera_mat, scale_mat, rgb_gt, t, depth_range, c
     l_eik = eikonal_loss(out["normals"])
     loss = rgb_weight * l_rgb + eikonal_weight * l_eik
     return loss, dict(out=out, rays_o=o, rays_d=d, rays_d_norm=dn, loss_rgb=l_rgb, loss_eikonal=l_eik)
+
+
+def render_image(P, world_mat, camera_mat, scale_mat, h, w, t, depth_range, cos_anneal=1.0, chunk=1024, cfg=None):
+    """Evaluation image render, restating model/training.py:210-283 (render_visdata: the rgb / depth / weighted-z /
+    depth_highest_weight / normal part; the optical-flow part belongs to the MotionNetwork and is out of scope).
+    1024-ray chunks as the reference (:210); each chunk: rays (:213), near/far (:217), renderer(eval=True) (:220),
+    arg-max-weight depth (:236-243), normal = sum_s normals * weights (:256-262)."""
+    _, sc = pixel_grid(h, w)
+    rgb, depth, wz, dhw, nrm = [], [], [], [], []
+    with torch.no_grad():
+        for i in range(0, h * w, chunk):
+            pix = sc[:, i:i + chunk]
+            if pix.shape[1] == 0:
+                break                                   # the reference's range(0, n // 1024 + 1) yields an empty last chunk
+            o, d, dn = ray_generation(pix, camera_mat, world_mat, scale_mat)
+            near, far = near_far(o, d, depth_range)
+            out = render(P, o, d, dn, t, near, far, cfg=cfg, cos_anneal=cos_anneal, eval_mode=True)
+            wts = out["weights"]
+            n = wts.shape[0]
+            _, mi = torch.max(wts, dim=1)
+            pts = out["sampled_points"].reshape(-1, 3)
+            pc = (world_mat @ torch.cat([pts, torch.ones_like(pts[:, [0]])], dim=-1).T).T[:, :3].view(n, wts.shape[1], 3)
+            dhw.append(-pc[:, :, -1][torch.arange(n), mi])
+            nn_ = (out["normals"] * wts[:, :, None]).sum(dim=1)
+            nrm.append((world_mat[:3, :3] @ nn_.T).T)
+            rgb.append(out["color_fine"]); depth.append(out["depth_pred"]); wz.append(out["weighted_z_vals"])
+    return dict(rgb=torch.cat(rgb), depth_pred=torch.cat(depth), weighted_z_vals=torch.cat(wz),
+                depth_highest_weight=torch.cat(dhw), normal=torch.cat(nrm))

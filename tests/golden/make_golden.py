@@ -324,7 +324,47 @@ def main():
     close(pose2["r"].grad, pr2.r.grad, 2e-4, "step dr"); close(pose2["t"].grad, pr2.t.grad, 2e-4, "step dt")
     G["step_small"] = npd(st)
 
+    # ---------------------------------------------------------------- evaluation image render (render_visdata)
+    # model/training.py:210-262 replayed with the imported renderer / ray generation; the reduction lines are the
+    # reference's own (:236-243 arg-max-weight depth, :256-262 weighted normal sum), chunked like the reference (:210)
+    Hs, Ws, ch = 12, 16, 64
+    Ke = O.camera_matrix(0.8 * Ws, 0.8 * Ws, Ws, Hs).unsqueeze(0)
+    world_e = pr(2).detach()
+    _, pix_e = R.common.arange_pixels((Hs, Ws), 1)
+    ev = dict(rgb=[], depth_pred=[], weighted_z_vals=[], depth_highest_weight=[], normal=[])
+    with torch.no_grad():
+        for i in range(0, pix_e.shape[1] // ch + 1):
+            pixels_i = pix_e[:, i * ch:(i + 1) * ch, :]
+            if pixels_i.shape[1] == 0:
+                continue
+            ray_o_i, ray_d_i, rays_d_norm_i = TT.get_world_cameraOrigin_cameraRay(None, pixels_i, Ke, world_e, Sc)
+            near_e, far_e = TT.near_far_from_sphere(types.SimpleNamespace(depth_range=[0.01, 5.0]), ray_o_i, ray_d_i)
+            render_out = rnd(ray_o_i, ray_d_i, rays_d_norm_i, tt, near_e, far_e, background_rgb=None, cos_anneal_ratio=1.0,
+                             it=1, eval=True)
+            pts = render_out['sampled_points'].view(-1, 3)
+            weights = render_out['weights']
+            _, max_idx = torch.max(weights, dim=1)
+            max_idx = torch.stack([torch.from_numpy(np.arange(len(weights))), max_idx.detach().cpu()])
+            pc_transform = world_e @ (torch.cat([pts, torch.ones_like(pts[:, [0]])], dim=-1)).T
+            pc_transform = pc_transform.T[:, :3].view(weights.shape[0], weights.shape[1], 3)
+            depth_highest_weight = -pc_transform[:, :, -1][tuple(max_idx)]
+            n_samples = rnd.n_samples + rnd.n_importance
+            normal_i = render_out['normals'] * render_out['weights'][:, :n_samples, None]
+            normal_i = normal_i.sum(dim=1)
+            normal_i = (world_e[:3, :3] @ normal_i.T).T
+            ev['rgb'].append(render_out['color_fine']); ev['depth_pred'].append(render_out['depth_pred'])
+            ev['weighted_z_vals'].append(render_out['weighted_z_vals'])
+            ev['depth_highest_weight'].append(depth_highest_weight); ev['normal'].append(normal_i)
+    ev = {k: torch.cat(v, dim=0) for k, v in ev.items()}
+    oe = O.render_image(P, world_e, Ke, Sc, Hs, Ws, tt, [0.01, 5.0], cos_anneal=1.0, chunk=ch)
+    for k in ev:
+        close(oe[k], ev[k], 2e-5, f"eval image {k}")
+    G["eval_image_small"] = npd(dict(ev, world=world_e, K=Ke, H=Hs, W=Ws, chunk=ch, t=tt))
+
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     for name, d in G.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **d)
         print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB, {len(d)} arrays)")

@@ -245,3 +245,30 @@ def test_fused_chains_partial_tile(monkeypatch, n):
         # paths (same effect as in test_bf16_fields_backward_full_size); per-point outputs are held to 0.999.
         lim = 0.999 if (n >= 128 and k in ("sdf", "grad", "rgb", "dx", "eb")) else 0.99
         assert cos_sim(a[k], b[k]) > lim, (k, n, cos_sim(a[k], b[k]), rel_err(a[k], b[k]))
+
+
+def test_bf16_eval_image_render_full_size():
+    """Chunk-free evaluation render with the full-size nets: the bf16 inference chains (no tile kept for a backward) against
+    the strict fp32 path and against the bf16 autograd forward of the same rays."""
+    torch.manual_seed(678)
+    r16 = C.training.build_networks(device=DEV, precision=C.PREC_BF16)
+    r32 = C.training.build_networks(device=DEV, precision=C.PREC_FP32)
+    r32.load_state_dict(r16.state_dict())
+    H, W = 20, 28
+    K = cu(O.camera_matrix(0.8 * W, 0.8 * W, W, H).unsqueeze(0))
+    world = torch.eye(4, device=DEV)
+    world[:3, 3] = torch.tensor([0.02, -0.03, 0.05], device=DEV)
+    S = torch.eye(4, device=DEV).unsqueeze(0)
+    t0 = torch.zeros(1, device=DEV)
+    a = C.training.render_image(r16, world, K, S, H, W, t0, (0.01, 5.0), chunk=200)
+    b = C.training.render_image(r32, world, K, S, H, W, t0, (0.01, 5.0), chunk=H * W)
+    for k in ("rgb", "depth_pred", "weighted_z_vals", "normal"):
+        assert torch.isfinite(a[k]).all(), k
+        assert cos_sim(a[k], b[k]) > COS, (k, cos_sim(a[k], b[k]))
+    # same rays through the autograd forward (saves everything) give the same image
+    from cope_nerf_b200.common import get_world_cameraOrigin_cameraRay, pixels_from_indices
+    idx = torch.arange(H * W, device=DEV)
+    o, d, dn = get_world_cameraOrigin_cameraRay(pixels_from_indices(idx, H, W), K, world, S)
+    near, far = C.training.near_far_from_sphere(o, d, (0.01, 5.0))
+    out = r16(o, d, dn, t0, near, far, cos_anneal_ratio=1.0, it=1, eval=True)
+    assert_close(a["rgb"], out["color_fine"].detach(), 2e-3, "rgb infer vs autograd forward")

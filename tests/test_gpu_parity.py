@@ -346,3 +346,40 @@ def test_empty_and_ragged_batches():
         assert out["color_fine"].shape == (n, 3) and torch.isfinite(out["color_fine"]).all()
     y = r.sdf_network(torch.zeros(0, 4, device=DEV))
     assert y.shape == (0, 65)
+
+
+# ------------------------------------------------------------------------------------------------ eval image render
+def _render_image(r, g, chunk, rays=None):
+    H, W = int(g["H"]), int(g["W"])
+    return C.training.render_image(r, cu(g["world"]), cu(g["K"]), torch.eye(4, device=DEV).unsqueeze(0), H, W, cu(g["t"]),
+                                   (0.01, 5.0), cos_anneal_ratio=1.0, it=1, chunk=chunk, rays=rays)
+
+
+def test_eval_image_render_golden(small_params):
+    """Chunk-free evaluation render (cope_render_mlp_infer + cope_composite_fwd + cope_eval_reduce) against the fixture the
+    imported reference produced (model/training.py:210-262), strict fp32 path."""
+    g = load_golden("eval_image_small")
+    r = renderer_from(small_params, SMALL_CFG)
+    out = _render_image(r, g, chunk=int(g["H"]) * int(g["W"]))
+    for k in ("rgb", "depth_pred", "weighted_z_vals", "depth_highest_weight", "normal"):
+        assert out[k].shape == g[k].shape, k
+        assert_close(out[k], g[k], 2e-4, k)
+    # chunk size and ray ranges (multi-GPU sharding of an image) do not change a pixel
+    out64 = _render_image(r, g, chunk=64)
+    half = int(g["H"]) * int(g["W"]) // 2
+    lo, hi = _render_image(r, g, chunk=50, rays=(0, half)), _render_image(r, g, chunk=50, rays=(half, half))
+    for k in out:
+        assert torch.equal(out64[k], out[k]), k
+        assert torch.equal(torch.cat([lo[k], hi[k]]), out[k]), k
+
+
+def test_eval_render_matches_autograd_path(small_params):
+    """The inference entry point returns what the training forward returns (same kernels, nothing saved)."""
+    g = load_golden("render_small")
+    r = renderer_from(small_params, SMALL_CFG)
+    a = [cu(g[k]) for k in ("rays_o", "rays_d", "rays_d_norm", "t", "near", "far")]
+    with torch.no_grad():
+        o_inf = r(*a, cos_anneal_ratio=0.3, it=1, eval=True)
+    o_ag = r(*a, cos_anneal_ratio=0.3, it=1, eval=True)
+    for k in KEYS:
+        assert_close(o_inf[k], o_ag[k], 1e-6, k)

@@ -135,3 +135,19 @@ def test_full_step_parameter_gradients(small_params):
         for k, v in P[tag].items():
             assert_close(v.grad, g[f"grad.{tag}.{k}"], 2e-4, f"{tag}.{k}")
     assert_close(pose["r"].grad, g["dr"], 2e-4, "dr"); assert_close(pose["t"].grad, g["dt"], 2e-4, "dt")
+
+
+def test_eval_image_render(small_params):
+    """Evaluation image render (model/training.py:210-262 replayed with the imported reference in make_golden.py):
+    rgb, depth, weighted z, arg-max-weight depth and the weighted normal map, in the reference's chunking."""
+    g = load_golden("eval_image_small")
+    H, W, ch = int(g["H"]), int(g["W"]), int(g["chunk"])
+    out = O.render_image(small_params, g["world"], g["K"], torch.eye(4).unsqueeze(0), H, W, g["t"], [0.01, 5.0], cos_anneal=1.0,
+                         chunk=ch)
+    for k in ("rgb", "depth_pred", "weighted_z_vals", "depth_highest_weight", "normal"):
+        assert out[k].shape == g[k].shape
+        assert_close(out[k], g[k], 2e-5, k)
+    # chunking is only a memory device: one chunk == the reference's chunks
+    out1 = O.render_image(small_params, g["world"], g["K"], torch.eye(4).unsqueeze(0), H, W, g["t"], [0.01, 5.0], cos_anneal=1.0,
+                          chunk=H * W)
+    assert_close(out1["rgb"], g["rgb"], 2e-5, "rgb one chunk")
