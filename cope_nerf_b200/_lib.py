@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcope_b200.so")
 MAX_LIN = 12
 PREC_FP32, PREC_BF16 = 0, 1
+ACT_SOFTPLUS100, ACT_LEAKY_RELU = 0, 1
 
 _f = C.c_void_p      # device pointers travel as integers
 _i, _l, _fl = C.c_int, C.c_int64, C.c_float
@@ -19,12 +20,14 @@ _i, _l, _fl = C.c_int, C.c_int64, C.c_float
 
 class MlpDesc(C.Structure):
     _fields_ = [("n_lin", C.c_int32), ("d_in", C.c_int32), ("multires", C.c_int32), ("skip_layer", C.c_int32),
-                ("dims_in", C.c_int32 * MAX_LIN), ("dims_out", C.c_int32 * MAX_LIN)]
+                ("dims_in", C.c_int32 * MAX_LIN), ("dims_out", C.c_int32 * MAX_LIN),
+                ("activation", C.c_int32), ("act_param", C.c_float)]
 
     @staticmethod
-    def make(dims_in, dims_out, d_in, multires, skip_layer):
+    def make(dims_in, dims_out, d_in, multires, skip_layer, activation=0, act_param=0.0):
         d = MlpDesc()
         d.n_lin, d.d_in, d.multires, d.skip_layer = len(dims_in), d_in, multires, skip_layer
+        d.activation, d.act_param = activation, act_param
         for k, (a, b) in enumerate(zip(dims_in, dims_out)):
             d.dims_in[k], d.dims_out[k] = a, b
         return d
@@ -57,6 +60,10 @@ _SIGS = {
     "cope_render_mlp_infer_ws_floats": (_l, [_D, _D, _l, _i]),
     "cope_render_mlp_infer": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _i, _f]),
     "cope_eval_reduce": (_i, [_f, _f, _f, _f, _l, _i, _f, _f, _f]),
+    "cope_pose_integrate_fwd": (_i, [_f, _f, _i, _i, _f, _f]),
+    "cope_pose_integrate_bwd": (_i, [_f, _f, _i, _i, _f, _f, _f, _f]),
+    "cope_pose_chain_fwd": (_i, [_f, _i, _f, _f]),
+    "cope_pose_chain_bwd": (_i, [_f, _f, _i, _f, _f, _f]),
     "cope_render_mlp_bwd": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _f]),
     "cope_ray_points": (_i, [_f, _f, _f, _f, _f, _f, _i, _l, _i, _i, _f, _f, _f, _f]),
     "cope_ray_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),

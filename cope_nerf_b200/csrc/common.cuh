@@ -47,6 +47,13 @@ __device__ __forceinline__ float softplus100_d1(float z) {
   float e = expf(bz);
   return e / (e + 1.0f);
 }
+// hidden activation selected by cope_mlp_desc::activation (softplus(beta=100) or LeakyReLU(slope))
+__device__ __forceinline__ float act_fwd(int act, float slope, float z) {
+  return act == COPE_ACT_LEAKY_RELU ? (z > 0.0f ? z : slope * z) : softplus100(z);
+}
+__device__ __forceinline__ float act_d1(int act, float slope, float z) {
+  return act == COPE_ACT_LEAKY_RELU ? (z > 0.0f ? 1.0f : slope) : softplus100_d1(z);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -86,6 +93,7 @@ struct GemmArgs {
   float* C2; int ldc2;         // aux output
   int nsplit;                  // column split for skip-layer epilogues (>= N: no split)
   int split_k;                 // >1 only with EPI_ATOMIC
+  int act; float act_slope;    // activation of the *_SOFTPLUS / *_SIGP / BWD epilogues (COPE_ACT_*; default softplus(beta=100))
 };
 
 int launch_gemm(bool transA, bool transB, const GemmArgs& a, cudaStream_t s);

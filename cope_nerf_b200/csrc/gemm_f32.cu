@@ -67,12 +67,12 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, int m, int n, float 
     case EPI_BIAS_SOFTPLUS: {
       float z = acc + a.bias[n];
       if (a.C2) a.C2[(int64_t)m * a.ldc2 + n] = z;
-      a.C[ci] = a.alpha * softplus100(z);
+      a.C[ci] = a.alpha * act_fwd(a.act, a.act_slope, z);
     } break;
     case EPI_BIAS_RELU: a.C[ci] = fmaxf(acc + a.bias[n], 0.0f); break;
     case EPI_BIAS_SIGMOID: a.C[ci] = sigmoidf_(acc + a.bias[n]); break;
     case EPI_MUL_SIGP:
-      if (n < a.nsplit) a.C[ci] = a.alpha * acc * softplus100_d1(a.Z[(int64_t)m * a.ldz + n]);
+      if (n < a.nsplit) a.C[ci] = a.alpha * acc * act_d1(a.act, a.act_slope, a.Z[(int64_t)m * a.ldz + n]);
       else a.C2[(int64_t)m * a.ldc2 + (n - a.nsplit)] = a.alpha * acc;
       break;
     case EPI_TANGENT: {
@@ -82,7 +82,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, int m, int n, float 
     } break;
     case EPI_BWD:
       if (n < a.nsplit) {
-        float v = a.alpha * acc * softplus100_d1(a.Z[(int64_t)m * a.ldz + n]);
+        float v = a.alpha * acc * act_d1(a.act, a.act_slope, a.Z[(int64_t)m * a.ldz + n]);
         if (a.D) v += a.D[(int64_t)m * a.ldd + n];
         a.C[ci] = v;
       } else if (a.C2) {

@@ -227,6 +227,7 @@ struct SdfB {
   size_t wtop_sdf_off;                                          // packed 16-row block holding row 0 of the last layer
 };
 static int make_sdfb(const MlpShape& m, SdfB* b) {
+  COPE_REQUIRE(m.act == COPE_ACT_SOFTPLUS100, "bf16 path: only the softplus(beta=100) SDF network is supported (activation %d)", m.act);
   b->n_lin = m.n_lin; b->top = m.n_lin - 1; b->skip = m.skip; b->pe_w = m.pe_w; b->d_in = m.d_in; b->L = m.L;
   b->skw = m.skip > 0 ? m.in[m.skip] - m.pe_w : 0;
   b->pe_k = r64(m.pe_w + m.d_in);

@@ -91,12 +91,12 @@ __global__ void pe_jvp_kernel(const float* __restrict__ x, int64_t P, int d, int
 
 // D[p, n] = w[n] * softplus'(Z[p, n])   (top of the reverse sweep: a_last = row 0 of the last W)
 __global__ void bcast_sigp_kernel(const float* __restrict__ w, const float* __restrict__ Z, int ldz,
-                                  float* __restrict__ D, int ldd, int64_t P, int n) {
+                                  float* __restrict__ D, int ldd, int64_t P, int n, int act, float slope) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * n) return;
   int64_t p = i / n;
   int c = (int)(i - p * n);
-  D[p * ldd + c] = w[c] * softplus100_d1(Z[p * ldz + c]);
+  D[p * ldd + c] = w[c] * act_d1(act, slope, Z[p * ldz + c]);
 }
 
 // out[c] += sum_p X[p, c]
@@ -230,7 +230,7 @@ int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, i
     GemmArgs g = gemm_args((int)P, last ? 1 : m.out[l], m.in[l], in, ldin, Wflat + m.w_off[l], m.in[l], out,
                            last ? 1 : m.ldh);
     g.bias = Wflat + m.b_off[l];
-    if (!last) { g.epi = EPI_BIAS_SOFTPLUS; g.alpha = (l + 1 == m.skip) ? kInvSqrt2 : 1.0f; }
+    if (!last) { g.epi = EPI_BIAS_SOFTPLUS; g.alpha = (l + 1 == m.skip) ? kInvSqrt2 : 1.0f; g.act = m.act; g.act_slope = m.act_slope; }
     if (int rc = launch_gemm(false, true, g, s)) return rc;
     in = out; ldin = m.ldh;
   }
@@ -256,7 +256,7 @@ int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
                            last ? sdf : sv.h(l + 1), last ? sdf_ld : m.ldh);
     g.bias = Wflat + m.b_off[l];
     if (!last) {
-      g.epi = EPI_BIAS_SOFTPLUS; g.alpha = (l + 1 == m.skip) ? kInvSqrt2 : 1.0f;
+      g.epi = EPI_BIAS_SOFTPLUS; g.alpha = (l + 1 == m.skip) ? kInvSqrt2 : 1.0f; g.act = m.act; g.act_slope = m.act_slope;
       g.C2 = sv.z(l); g.ldc2 = m.ldh;
     } else {
       g.nsplit = 1; g.C2 = feat; g.ldc2 = feat_ld;
@@ -268,7 +268,7 @@ int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
   // ---- reverse sweep: grad = d y[:,0] / d x
   const int top = m.n_lin - 1;
   bcast_sigp_kernel<<<grid1d(P * m.out[top - 1]), 256, 0, s>>>(Wflat + m.w_off[top], sv.z(top - 1), m.ldh,
-                                                              sv.dl(top - 1), m.ldh, P, m.out[top - 1]);
+                                                              sv.dl(top - 1), m.ldh, P, m.out[top - 1], m.act, m.act_slope);
   COPE_CHECK_LAUNCH("bcast_sigp");
   float* ge0 = ws;                    // a_0            [P x pe_w]
   float* ge1 = ws + P * m.pe_w;       // a_skip pe part [P x pe_w]
@@ -277,7 +277,7 @@ int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
     GemmArgs g = gemm_args((int)P, m.in[l], m.out[l], sv.dl(l), m.ldh, Wflat + m.w_off[l], m.in[l],
                            l > 0 ? sv.dl(l - 1) : ge0, l > 0 ? m.ldh : m.pe_w);
     if (l > 0) {
-      g.epi = EPI_MUL_SIGP; g.Z = sv.z(l - 1); g.ldz = m.ldh;
+      g.epi = EPI_MUL_SIGP; g.Z = sv.z(l - 1); g.ldz = m.ldh; g.act = m.act; g.act_slope = m.act_slope;
       if (l == m.skip) { g.alpha = kInvSqrt2; g.nsplit = skw; g.C2 = ge1; g.ldc2 = m.pe_w; }
     }
     if (int rc = launch_gemm(false, false, g, s)) return rc;
@@ -293,6 +293,8 @@ int cope_sdf_bwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
                  float* dWflat, float* dx, int dx_accumulate, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
+  COPE_REQUIRE(m.act == COPE_ACT_SOFTPLUS100 || (dgrad == nullptr && prec == COPE_PREC_FP32),
+               "sdf_bwd: activation %d has no second-order / tensor-core path", m.act);
   if (prec == COPE_PREC_BF16)
     return sdf_bwd_bf16(m, Wflat, x, P, saved, d_sdf, d_sdf_ld, d_feat, d_feat_ld, dgrad, dWflat, dx, dx_accumulate, ws,
                         as_stream(s_));
@@ -369,7 +371,7 @@ int cope_sdf_bwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
       GemmArgs g = gemm_args((int)P, m.in[l], m.out[l], zb, ldzb, Wflat + m.w_off[l], m.in[l], l > 0 ? nxt : eb0,
                              l > 0 ? (int)ldw : m.pe_w);
       if (l > 0) {
-        g.epi = EPI_BWD; g.Z = sv.z(l - 1); g.ldz = m.ldh;
+        g.epi = EPI_BWD; g.Z = sv.z(l - 1); g.ldz = m.ldh; g.act = m.act; g.act_slope = m.act_slope;
         if (with2) { g.D = zb2(l - 1); g.ldd = m.ldh; }
         if (l == m.skip) { g.alpha = kInvSqrt2; g.nsplit = skw; g.C2 = want_e ? eb1 : nullptr; g.ldc2 = m.pe_w; }
       }

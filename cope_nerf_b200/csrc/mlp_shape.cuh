@@ -11,6 +11,7 @@ namespace cope {
 // ------------------------------------------------------------------------------------------- layouts
 struct MlpShape {
   int n_lin, d_in, L, pe_w, skip, ldh, d_out;
+  int act; float act_slope;
   int64_t w_off[COPE_MAX_LIN], b_off[COPE_MAX_LIN], n_flat;
   int in[COPE_MAX_LIN], out[COPE_MAX_LIN];
 };
@@ -18,6 +19,8 @@ struct MlpShape {
 inline int make_shape(const cope_mlp_desc* d, MlpShape* s) {
   COPE_REQUIRE(d && d->n_lin >= 2 && d->n_lin <= COPE_MAX_LIN, "mlp desc: n_lin out of range");
   s->n_lin = d->n_lin; s->d_in = d->d_in; s->L = d->multires; s->skip = d->skip_layer;
+  COPE_REQUIRE(d->activation == COPE_ACT_SOFTPLUS100 || d->activation == COPE_ACT_LEAKY_RELU, "mlp desc: unknown activation %d", d->activation);
+  s->act = d->activation; s->act_slope = d->act_param;
   s->pe_w = d->d_in * (1 + 2 * d->multires);
   int64_t off = 0;
   int ldh = 0;

@@ -43,7 +43,13 @@ typedef struct {
   int32_t skip_layer;            /* layer whose input is cat([h, pe])/sqrt(2) (4 for SDF), -1 = none     */
   int32_t dims_in[COPE_MAX_LIN]; /* K of each layer                                                      */
   int32_t dims_out[COPE_MAX_LIN];/* N of each layer (layer skip_layer-1 emits dims_in[skip]-pe_width)    */
+  int32_t activation;            /* hidden activation of the cope_sdf_* family: COPE_ACT_SOFTPLUS100 (SDFNetwork) or
+                                    COPE_ACT_LEAKY_RELU (MotionNetwork, model/neus_fields.py:140); strict fp32 path only */
+  float act_param;               /* negative slope of COPE_ACT_LEAKY_RELU (0.2)                           */
 } cope_mlp_desc;
+
+#define COPE_ACT_SOFTPLUS100 0
+#define COPE_ACT_LEAKY_RELU 1
 
 int cope_version(void);
 const char* cope_last_error(void);
@@ -223,6 +229,19 @@ int cope_tc_gemm(int M, int N, int K, const void* A_bf16, int lda, const void* B
 int64_t cope_tc_wgrad_ws_floats(void);
 int cope_tc_wgrad(int64_t P, int Mp, int Np, int m_valid, int n_valid, const void* X, int ldx, const void* Y, int ldy,
                   float* dW, int ldw, float* ws, cope_stream_t s);
+
+/* ---- continuous pose model (MotionNetwork, model/neus_fields.py:142-183) -------------------------
+ * The network itself is a cope_sdf_fwd / cope_sdf_bwd MLP with activation = COPE_ACT_LEAKY_RELU (strict fp32 path).
+ * cope_pose_integrate_*: wv [F * n_sub x 6] = (angular velocity, velocity) at the n_sub time samples of each of the F
+ * consecutive frame pairs, dt [F] = the time interval of each pair; rel [F x 16] row-major 4x4 relative poses
+ * (compute_consecutive_relative_pose, :142-160).  Backward: d_wv and d_dt [F] (may be NULL) OVERWRITTEN.
+ * cope_pose_chain_*: w2c [(F+1) x 16], w2c_0 = I, w2c_{i+1} = rel_i @ w2c_i (compute_w2c_mappings, :172-183);
+ * backward: d_w2c [(F+1) x 16] -> d_rel [F x 16] OVERWRITTEN. */
+int cope_pose_integrate_fwd(const float* wv, const float* dt, int F, int n_sub, float* rel, cope_stream_t s);
+int cope_pose_integrate_bwd(const float* wv, const float* dt, int F, int n_sub, const float* d_rel, float* d_wv, float* d_dt,
+                            cope_stream_t s);
+int cope_pose_chain_fwd(const float* rel, int F, float* w2c, cope_stream_t s);
+int cope_pose_chain_bwd(const float* rel, const float* w2c, int F, const float* d_w2c, float* d_rel, cope_stream_t s);
 
 /* ---- per-ray image reductions of the evaluation render (model/training.py:236-262): normal[n] = R * sum_s w[n,s] * grad[n,s,:3]
  * and depth_hw[n] = -(world_mat @ [pts[n, argmax_s w], 1]).z, world_mat = device pointer to a row-major 4x4 (R = its 3x3). */

@@ -23,6 +23,8 @@ __all__ = [
     "vec2skew", "so3_exp", "make_c2w", "pose_forward", "camera_matrix", "pixel_grid", "patch_indices",
     "ray_generation", "near_far", "cos_anneal_ratio", "eikonal_loss", "rgb_l1_loss", "sdf_flow_loss",
     "train_step", "render_image", "DEFAULT_CFG",
+    "MOTION_CFG", "init_motion_params", "motion_forward", "euler_xyz_to_matrix", "consecutive_relative_pose",
+    "relative_camera_pose", "w2c_mappings",
 ]
 
 # configs/default.yaml:103-156 (no scene config overrides any of these shapes)
@@ -475,3 +477,115 @@ def render_image(P, world_mat, camera_mat, scale_mat, h, w, t, depth_range, cos_
             rgb.append(out["color_fine"]); depth.append(out["depth_pred"]); wz.append(out["weighted_z_vals"])
     return dict(rgb=torch.cat(rgb), depth_pred=torch.cat(depth), weighted_z_vals=torch.cat(wz),
                 depth_highest_weight=torch.cat(dhw), normal=torch.cat(nrm))
+
+
+# --------------------------------------------------------------------------- continuous pose model (MotionNetwork)
+MOTION_CFG = dict(d_out=6, d_in=1, d_hidden=256, n_layers=4, skip_in=(2,), multires=6, bias=0.5, scale=1.0,
+                  geometric_init=False, weight_norm=True)           # configs/default.yaml:113-123
+
+
+def init_motion_params(d_in=1, d_out=6, d_hidden=256, n_layers=4, skip_in=(2,), multires=6, bias=0.5, scale=1.0,
+                       geometric_init=False, weight_norm=True, inside_outside=False):
+    """model/neus_fields.py:79-138: one nn.Linear per layer (default init; the geometric branch as in the SDF net but with
+    3-wide coordinate blocks, :114-133), weight-normed."""
+    dims = [d_in] + [d_hidden] * n_layers + [d_out]
+    if multires > 0:
+        dims[0] = embed_dim(d_in, multires)
+    n_lin = len(dims) - 1
+    p = {}
+    for l in range(n_lin):
+        out_dim = dims[l + 1] - dims[0] if (l + 1) in skip_in else dims[l + 1]
+        lin = torch.nn.Linear(dims[l], out_dim)
+        w, b = lin.weight.data, lin.bias.data
+        if geometric_init:
+            if l == n_lin - 1:
+                sign = -1.0 if inside_outside else 1.0
+                torch.nn.init.normal_(w, mean=sign * np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                torch.nn.init.constant_(b, -sign * bias)
+            elif multires > 0 and l == 0:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.constant_(w[:, 3:], 0.0)
+                torch.nn.init.normal_(w[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            elif multires > 0 and l in skip_in:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                torch.nn.init.constant_(w[:, -(dims[0] - 3):], 0.0)
+            else:
+                torch.nn.init.constant_(b, 0.0)
+                torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+        g, v = _wn_split(w)
+        p[f"lin{l}.bias"] = b.clone()
+        p[f"lin{l}.weight_g"] = g
+        p[f"lin{l}.weight_v"] = v
+    return p
+
+
+def motion_forward(p, t, multires=6, skip_in=(2,), scale=1.0):
+    """model/neus_fields.py:185-201: PE(t) -> weight-normed linears with LeakyReLU(0.2), skip concat / sqrt2 -> 6 outputs
+    * scale -> (angular velocity, velocity)."""
+    e = embed(t, multires)
+    x = e
+    n = _n_lin(p)
+    for l in range(n):
+        if l in skip_in:
+            x = torch.cat([x, e], dim=1) / np.sqrt(2)
+        x = F.linear(x, wn_weight(p, l), p[f"lin{l}.bias"])
+        if l < n - 1:
+            x = F.leaky_relu(x, 0.2)
+    x = x * scale
+    return x[:, :3], x[:, 3:]
+
+
+def _axis_rot(axis, angle):
+    """utils_poses/pose_pytorch3d.py:62-75."""
+    c, s = torch.cos(angle), torch.sin(angle)
+    one, zero = torch.ones_like(angle), torch.zeros_like(angle)
+    if axis == "X":
+        flat = (one, zero, zero, zero, c, -s, zero, s, c)
+    elif axis == "Y":
+        flat = (c, zero, s, zero, one, zero, -s, zero, c)
+    else:
+        flat = (c, -s, zero, s, c, zero, zero, zero, one)
+    return torch.stack(flat, -1).reshape(angle.shape + (3, 3))
+
+
+def euler_xyz_to_matrix(a):
+    """utils_poses/pose_pytorch3d.py:8-19 with convention 'XYZ': Rx(a0) @ Ry(a1) @ Rz(a2)."""
+    return _axis_rot("X", a[..., 0]) @ _axis_rot("Y", a[..., 1]) @ _axis_rot("Z", a[..., 2])
+
+
+def consecutive_relative_pose(p, target_cam_idx, total_nb_images, nb_sample_timestep, **kw):
+    """model/neus_fields.py:142-160."""
+    ref = target_cam_idx + 1.0
+    time_step = target_cam_idx / (total_nb_images - 1) * 2 - 1
+    next_time_step = ref / (total_nb_images - 1) * 2 - 1
+    n = int(nb_sample_timestep * (ref - target_cam_idx))
+    lst = torch.linspace(time_step, next_time_step, n + 1)[:-1]
+    dt = lst[1] - lst[0]
+    ang, vel = motion_forward(p, lst.view(-1, 1), **kw)
+    R_list = euler_xyz_to_matrix(ang * dt)
+    V_list = vel * dt
+    R, T = torch.eye(3), torch.zeros(3)
+    for k in range(lst.shape[0]):
+        T = (R_list[k] @ T.view(3, 1) + V_list[k].view(3, 1)).view(3)
+        R = R @ R_list[k]
+    pose = torch.eye(4)
+    pose = torch.cat([torch.cat([R, T.view(3, 1)], dim=1), pose[3:]], dim=0)
+    return dt, pose
+
+
+def relative_camera_pose(p, target_cam_idx, final_ref_cam_idx, total_nb_images, nb_sample_timestep, **kw):
+    """model/neus_fields.py:162-168."""
+    out, dt = [], None
+    for cam in range(target_cam_idx, final_ref_cam_idx):
+        dt, pose = consecutive_relative_pose(p, cam, total_nb_images, nb_sample_timestep, **kw)
+        out.append(pose)
+    return dt, out
+
+
+def w2c_mappings(rel):
+    """model/neus_fields.py:172-183."""
+    w2c = [torch.eye(4)]
+    for r in rel:
+        w2c.append(r @ w2c[-1])
+    return torch.stack(w2c)

@@ -361,6 +361,46 @@ def main():
         close(oe[k], ev[k], 2e-5, f"eval image {k}")
     G["eval_image_small"] = npd(dict(ev, world=world_e, K=Ke, H=Hs, W=Ws, chunk=ch, t=tt))
 
+    # ---------------------------------------------------------------- continuous pose model (MotionNetwork)
+    # model/neus_fields.py:79-201 with configs/default.yaml:113-123: constructor RNG stream, forward, the pose integration
+    # over 7 consecutive pairs x 10 sub-steps, the w2c chain, and every parameter gradient of a random readout
+    mcfg = dict(d_out=6, d_in=1, d_hidden=64, n_layers=4, skip_in=[2], multires=6, bias=0.5, scale=1.0,
+                geometric_init=False, weight_norm=True)
+    torch.manual_seed(31)
+    mn = R.fields.MotionNetwork(**mcfg)
+    torch.manual_seed(31)
+    mp = O.init_motion_params(**{**mcfg, "skip_in": (2,)})
+    for k, v in mn.state_dict().items():
+        assert torch.equal(v, mp[k]), f"motion init {k}"
+    with torch.no_grad():                     # bigger weights in the output layer so that rotations are not ~identity
+        for k in ("lin4.weight_g", "lin4.bias"):
+            mn.state_dict()[k].mul_(6.0).add_(0.3)
+    mp = {k: v.detach().clone() for k, v in mn.state_dict().items()}
+    tq = torch.linspace(-1, 1, 23).view(-1, 1)
+    a_ref, v_ref = mn(tq)
+    a_o, v_o = O.motion_forward(mp, tq)
+    close(a_o, a_ref, 1e-6, "motion ang"); close(v_o, v_ref, 1e-6, "motion vel")
+    n_img, n_sub, first, last = 20, 10, 3, 10
+    dt_ref, rel_ref = mn.compute_relative_camera_pose(first, last, n_img, n_sub)
+    w2c_ref = mn.compute_w2c_mappings(rel_ref)
+    dt_o, rel_o = O.relative_camera_pose(mp, first, last, n_img, n_sub)
+    close(dt_o, dt_ref, 0, "motion dt")
+    close(torch.stack(rel_o), torch.stack(rel_ref), 1e-6, "motion rel")
+    close(O.w2c_mappings(rel_o), w2c_ref, 1e-6, "motion w2c")
+    torch.manual_seed(32)
+    wgt = torch.randn_like(w2c_ref)
+    mn.zero_grad()
+    (w2c_ref * wgt).sum().backward()
+    mg = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
+    (O.w2c_mappings(O.relative_camera_pose(mg, first, last, n_img, n_sub)[1]) * wgt).sum().backward()
+    mo = dict(t_query=tq, ang=a_ref, vel=v_ref, dt=dt_ref, rel=torch.stack(rel_ref), w2c=w2c_ref, wgt=wgt,
+              n_img=n_img, n_sub=n_sub, first=first, last=last)
+    for k, v in mn.named_parameters():
+        close(mg[k].grad, v.grad, 2e-5, f"motion grad {k}")
+        mo[f"grad.{k}"] = v.grad.clone()
+    mo.update({f"param.{k}": v for k, v in mp.items()})
+    G["motion_small"] = npd(mo)
+
     only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     for name, d in G.items():
         if only and name not in only:

@@ -383,3 +383,56 @@ def test_eval_render_matches_autograd_path(small_params):
     o_ag = r(*a, cos_anneal_ratio=0.3, it=1, eval=True)
     for k in KEYS:
         assert_close(o_inf[k], o_ag[k], 1e-6, k)
+
+
+# ------------------------------------------------------------------------------------------------ continuous pose model
+def _motion_net(g, d_hidden):
+    from cope_nerf_b200.motion import MotionNetwork
+    m = MotionNetwork(**dict(O.MOTION_CFG, d_hidden=d_hidden, skip_in=[2])).to(DEV)
+    if g is not None:
+        m.load_state_dict({k[len("param."):]: v for k, v in g.items() if k.startswith("param.")})
+    return m
+
+
+def test_motion_network_golden():
+    """MotionNetwork forward (cope_sdf_fwd with LeakyReLU), cope_pose_integrate / cope_pose_chain and their backward
+    against the fixture of the imported reference (model/neus_fields.py:142-201)."""
+    g = load_golden("motion_small")
+    m = _motion_net(g, 64)
+    a, v = m(cu(g["t_query"]))
+    assert_close(a, g["ang"], 1e-5, "ang"); assert_close(v, g["vel"], 1e-5, "vel")
+    n_img, n_sub, first, last = int(g["n_img"]), int(g["n_sub"]), int(g["first"]), int(g["last"])
+    dt, rel = m.compute_relative_camera_pose(first, last, n_img, n_sub)
+    assert isinstance(rel, list) and len(rel) == last - first and rel[0].shape == (4, 4)
+    w2c = m.compute_w2c_mappings(rel)
+    assert_close(dt, g["dt"], 0, "dt")
+    assert_close(torch.stack(rel), g["rel"], 1e-5, "rel"); assert_close(w2c, g["w2c"], 1e-5, "w2c")
+    (w2c * cu(g["wgt"])).sum().backward()
+    for k, p in m.named_parameters():
+        e = rel_err(p.grad, g[f"grad.{k}"])
+        assert e < 1e-3, (k, e)
+    # one pair through the single-pair entry point
+    dt1, pose = m.compute_consecutive_relative_pose(first, n_img, n_sub)
+    assert_close(pose, g["rel"][0], 1e-5, "consecutive pose"); assert_close(dt1, g["dt"], 1e-6)
+
+
+def test_motion_network_full_size_vs_oracle():
+    """Shipped configuration (configs/default.yaml:113-123: 256 hidden, skip at 2, PE 6): a whole sequence of 60 frame
+    pairs chained into world -> camera maps, forward and backward, against the CPU oracle."""
+    torch.manual_seed(41)
+    mp = O.init_motion_params(**O.MOTION_CFG)
+    mp["lin4.weight_g"] = mp["lin4.weight_g"] * 5.0
+    m = _motion_net(None, 256)
+    m.load_state_dict(mp)
+    n_img, n_sub = 61, 10
+    dt, rel = m.compute_relative_camera_pose(0, n_img - 1, n_img, n_sub)
+    w2c = m.compute_w2c_mappings(rel)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in mp.items()}
+    dto, relo = O.relative_camera_pose(Pg, 0, n_img - 1, n_img, n_sub)
+    w2co = O.w2c_mappings(relo)
+    assert_close(dt, dto, 0); assert_close(w2c, w2co, 2e-5, "w2c")
+    torch.manual_seed(42)
+    wgt = torch.randn_like(w2co)
+    (w2c * cu(wgt)).sum().backward(); (w2co * wgt).sum().backward()
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, Pg[k].grad) < 1e-3, (k, rel_err(p.grad, Pg[k].grad))

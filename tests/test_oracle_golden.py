@@ -151,3 +151,30 @@ def test_eval_image_render(small_params):
     out1 = O.render_image(small_params, g["world"], g["K"], torch.eye(4).unsqueeze(0), H, W, g["t"], [0.01, 5.0], cos_anneal=1.0,
                           chunk=H * W)
     assert_close(out1["rgb"], g["rgb"], 2e-5, "rgb one chunk")
+
+
+def _motion_params(g):
+    return {k[len("param."):]: v for k, v in g.items() if k.startswith("param.")}
+
+
+def test_motion_network_and_pose_integration():
+    """Continuous pose model (model/neus_fields.py:79-201): constructor RNG stream, forward, relative poses over 7 frame
+    pairs x 10 sub-steps, the w2c chain and every parameter gradient, against the imported reference (make_golden.py)."""
+    g = load_golden("motion_small")
+    P = _motion_params(g)
+    cfg = dict(O.MOTION_CFG, d_hidden=64)
+    torch.manual_seed(31)
+    init = O.init_motion_params(**cfg)
+    for k in ("lin0.weight_v", "lin2.weight_g", "lin3.bias"):      # lin4 was rescaled in the generator
+        assert torch.equal(init[k], P[k]), k
+    a, v = O.motion_forward(P, g["t_query"])
+    assert_close(a, g["ang"], 1e-6, "ang"); assert_close(v, g["vel"], 1e-6, "vel")
+    n_img, n_sub, first, last = int(g["n_img"]), int(g["n_sub"]), int(g["first"]), int(g["last"])
+    Pg = {k: x.clone().requires_grad_(True) for k, x in P.items()}
+    dt, rel = O.relative_camera_pose(Pg, first, last, n_img, n_sub)
+    w2c = O.w2c_mappings(rel)
+    assert_close(dt, g["dt"], 0, "dt")
+    assert_close(torch.stack(rel), g["rel"], 1e-6, "rel"); assert_close(w2c, g["w2c"], 1e-6, "w2c")
+    (w2c * g["wgt"]).sum().backward()
+    for k in P:
+        assert_close(Pg[k].grad, g[f"grad.{k}"], 2e-5, f"grad {k}")
