@@ -81,6 +81,12 @@ _SIGS = {
     "cope_tc_gemm": (_i, [_i, _i, _i, _f, _i, _f, _f, _i, _fl, _f, _i, _i, _f]),
     "cope_tc_wgrad_ws_floats": (_l, []),
     "cope_tc_wgrad": (_i, [_l, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _f, _f]),
+    "cope_step_losses_fwd": (_i, [_f] * 7 + [_l, _l, _fl, _fl, _fl, _f, _f, _f, _f]),
+    "cope_step_losses_bwd": (_i, [_f] * 6 + [_l, _l] + [_f] * 6 + [_f]),
+    "cope_weighted_points_fwd": (_i, [_f, _f, _l, _i, _f, _f]),
+    "cope_weighted_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),
+    "cope_flow_rgb_fwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f]),
+    "cope_flow_rgb_bwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }
 EXPORTS = tuple(_SIGS)

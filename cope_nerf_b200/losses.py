@@ -1,0 +1,201 @@
+"""Stage-1 auxiliary losses of the reference's training step (train.py:467-517) on libcope_b200.
+
+  * rgb L1 + eikonal + SDF-flow loss        -> `NeuSRenderer.forward_losses` (renderer._RenderStepFn, cope_step_losses_*), or
+                                               `step_losses` below on an existing output dict
+  * flow-RGB loss (train.py:480-517)         -> `weighted_points` (cope_weighted_points_*) + `flow_rgb_loss` (cope_flow_rgb_*)
+  * SDF-consistency loss (train.py:496-505)  -> `sdf_consistency_loss`: rigid map of the sampled points into the world frame
+                                               + `SDFNetwork.sdf` with gradients (cope_sdf_fwd / cope_sdf_bwd)
+
+Everything runs on the device without host synchronisation; there is no CPU fallback.
+"""
+import torch
+
+from . import _lib as L
+
+__all__ = ["step_losses", "weighted_points", "flow_rgb_loss", "sdf_consistency_loss", "projection_matrices", "rigid_inverse",
+           "stage1_losses"]
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+class _StepLossFn(torch.autograd.Function):
+    """rgb L1 + eikonal (+ SDF-flow) on tensors that already exist (the dict path of NeuSRenderer.forward)."""
+
+    @staticmethod
+    def forward(ctx, color, rgb_gt, grad4, pts4, weights, motion, w_sum_global, w_rgb, w_eik, w_flow):
+        N, P, dev = color.shape[0], grad4.shape[0], color.device
+        color, grad4 = color.contiguous().float(), grad4.contiguous().float()
+        rgb_gt = rgb_gt.contiguous().float()
+        mot = motion.detach().reshape(6).contiguous().float() if motion is not None else None
+        if mot is not None:
+            pts4, weights = pts4.contiguous().float(), weights.detach().reshape(-1).contiguous().float()
+        losses, coef, ws = _f32(4, device=dev), _f32(4, device=dev), _f32(8, device=dev)
+        L.call("cope_step_losses_fwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4) if mot is not None else None,
+               L.ptr(weights) if mot is not None else None, L.ptr(mot), L.ptr(w_sum_global), N, P, float(w_rgb), float(w_eik),
+               float(w_flow), L.ptr(losses), L.ptr(coef), L.ptr(ws), L.stream())
+        ctx.save_for_backward(color, rgb_gt, grad4, coef, *([pts4, weights, mot] if mot is not None else []))
+        ctx.has_motion = mot is not None
+        ctx.motion_shape = motion.shape if motion is not None else None
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _unused=None):
+        if g is None:
+            return (None,) * 10
+        color, rgb_gt, grad4, coef = ctx.saved_tensors[:4]
+        pts4 = weights = mot = None
+        if ctx.has_motion:
+            pts4, weights, mot = ctx.saved_tensors[4:7]
+        N, P, dev = color.shape[0], grad4.shape[0], color.device
+        d_color, d_grad4 = _f32(N, 3, device=dev), _f32(P, 4, device=dev)
+        d_pts4 = _f32(P, 4, device=dev) if (mot is not None and ctx.needs_input_grad[3]) else None
+        d_motion = torch.zeros(6, dtype=torch.float32, device=dev) if (mot is not None and ctx.needs_input_grad[5]) else None
+        L.call("cope_step_losses_bwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4), L.ptr(weights), L.ptr(mot), N, P,
+               L.ptr(coef), L.ptr(g.reshape(1).float()), L.ptr(d_color), L.ptr(d_grad4), L.ptr(d_pts4), L.ptr(d_motion),
+               L.stream())
+        if d_motion is not None:
+            d_motion = d_motion.reshape(ctx.motion_shape)
+        return d_color, None, d_grad4, d_pts4, None, d_motion, None, None, None, None
+
+
+def step_losses(out, rgb_gt, rgb_weight=1.0, eikonal_weight=0.1, sdf_weight=0.0, motion=None, w_sum_global=None):
+    """total, parts = losses of model/training.py:508 (rgb L1), train.py:526 (eikonal) and train.py:467-477 (SDF-flow, when
+    `motion` = (angular velocity | velocity) [6] is given) from a `NeuSRenderer.forward` output dict.
+    parts = [total, rgb, eikonal, sdf_flow] (no gradient)."""
+    return _StepLossFn.apply(out["color_fine"], rgb_gt, out["_grad4"], out["_pts4"], out["weights"], motion, w_sum_global,
+                             rgb_weight, eikonal_weight, sdf_weight)
+
+
+# ------------------------------------------------------------------------------------------------ flow-RGB
+class _WeightedPointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, pts4):
+        N, S = weights.shape
+        weights, pts4 = weights.contiguous().float(), pts4.contiguous().float()
+        wp = _f32(N, 4, device=weights.device)
+        L.call("cope_weighted_points_fwd", L.ptr(weights), L.ptr(pts4), N, S, L.ptr(wp), L.stream())
+        ctx.save_for_backward(weights, pts4)
+        return wp
+
+    @staticmethod
+    def backward(ctx, d_wp):
+        weights, pts4 = ctx.saved_tensors
+        N, S = weights.shape
+        d_w = _f32(N, S, device=weights.device) if ctx.needs_input_grad[0] else None
+        d_p = _f32(N * S, 4, device=weights.device) if ctx.needs_input_grad[1] else None
+        L.call("cope_weighted_points_bwd", L.ptr(weights), L.ptr(pts4), L.ptr(d_wp.contiguous()), N, S, L.ptr(d_w), L.ptr(d_p),
+               L.stream())
+        return d_w, d_p
+
+
+def weighted_points(weights, pts4):
+    """wp [N,4] = sum_s weights[n,s] * (pts4[n,s,:3], 1).  For any rigid map (R, T): sum_s w (R p + T) = R wp[:3] + T wp[3]
+    (train.py:488-489 evaluates the left-hand side for every reference frame)."""
+    return _WeightedPointsFn.apply(weights, pts4)
+
+
+class _FlowRgbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt, want_flow):
+        N, T = wp.shape[0], w2c.shape[0]
+        H, W = ref_imgs.shape[-2:]
+        dev = wp.device
+        args = [t.contiguous().float() for t in (wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt)]
+        flow = _f32(T, N, 2, device=dev) if want_flow else None
+        loss, ws = _f32(1, device=dev), _f32(2 * T + 1, device=dev)
+        L.call("cope_flow_rgb_fwd", *[L.ptr(a) for a in args], N, T, H, W, L.ptr(flow), L.ptr(loss), L.ptr(ws), L.stream())
+        ctx.save_for_backward(*args, ws)
+        ctx.dims = (N, T, H, W)
+        ctx.set_materialize_grads(False)
+        if flow is not None:
+            ctx.mark_non_differentiable(flow)
+        return loss.reshape(()), flow
+
+    @staticmethod
+    def backward(ctx, g, _unused=None):
+        if g is None:
+            return (None,) * 8
+        *args, ws = ctx.saved_tensors
+        N, T, H, W = ctx.dims
+        dev = ws.device
+        d_wp = _f32(N, 4, device=dev)
+        d_w2c = torch.zeros(T, 4, 4, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        L.call("cope_flow_rgb_bwd", *[L.ptr(a) for a in args], N, T, H, W, L.ptr(ws), L.ptr(g.reshape(1).float()), L.ptr(d_wp),
+               L.ptr(d_w2c), L.stream())
+        return d_wp, d_w2c, None, None, None, None, None, None
+
+
+def projection_matrices(scale_mat, ref_camera_mats):
+    """KS [T,3,3] = scale_mat[0,:3,:3] @ ref_camera_mat[t,:3,:3] (train.py:490)."""
+    return scale_mat[0, :3, :3].unsqueeze(0) @ ref_camera_mats[:, :3, :3]
+
+
+def flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt, return_flow=False):
+    """train.py:486-517 for T reference frames: wp [N,4] from `weighted_points`, w2c [T,4,4] world -> reference camera
+    (MotionNetwork.compute_w2c_mappings rows), KS [T,3,3] (`projection_matrices`), norm_pix / pix [N,2] the rays' normalised
+    and integer pixel coordinates (x, y), ref_imgs [T,3,H,W], rgb_gt [N,3].
+    Returns sum_t masked-L1(warped_t, rgb_gt) / 3 (and the predicted pixel flow [T,N,2])."""
+    loss, flow = _FlowRgbFn.apply(wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt, return_flow)
+    return (loss, flow) if return_flow else loss
+
+
+# ------------------------------------------------------------------------------------------------ SDF consistency
+def sdf_consistency_loss(sdf_network, pts, sdf, cw2, world_time_step):
+    """train.py:496-505: map the sampled points into the world frame with the rigid map cw2 [4,4], query the SDF there at
+    the world time step (with gradients, cope_sdf_fwd / cope_sdf_bwd) and compare with the SDF rendered at the query time."""
+    pts = pts.reshape(-1, 3)
+    pw = pts @ cw2[:3, :3].T + cw2[:3, 3]
+    x = torch.cat([pw, torch.full_like(pw[:, :1], float(world_time_step))], dim=1)
+    sdf_w = sdf_network.sdf(x)
+    return torch.mean(torch.abs(sdf_w - sdf.reshape(-1, 1)))
+
+
+def rigid_inverse(m):
+    """inverse of a rigid 4x4 map [R | T]: [R^T | -R^T T] (the reference calls torch.inverse, train.py:500; the chained
+    relative poses are products of rotations and translations, so this is the same matrix without an LU factorisation and
+    its host-side singularity check)."""
+    r, t = m[:3, :3], m[:3, 3:]
+    top = torch.cat([r.T, -(r.T @ t)], dim=1)
+    return torch.cat([top, m[3:].detach()], dim=0)
+
+
+def stage1_losses(out, rgb_gt, motion_network, sdf_network, query_time_step, image_idx, ref_image_idx_list, nb_valid,
+                  total_nb_images, nb_sample_timestep, ref_camera_mats, scale_mat, norm_pix, pix, ref_imgs, world_cam_idx,
+                  world_time_step, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True):
+    """The `not query_in_canonical_space` branch of train.py:467-517 on a NeuSRenderer output dict: SDF-flow loss,
+    flow-RGB loss over the valid reference frames and SDF-consistency loss.  Same control flow and argument meaning as the
+    reference (image / reference indices, number of valid next time steps, world camera / time step); the per-sample
+    arithmetic runs in cope_step_losses_*, cope_weighted_points_*, cope_flow_rgb_* and the SDF kernels.
+    Returns dict(sdf_loss, flow_rgb_loss, sdf_consistency_loss, flow_fw_pred [T,N,2] or None)."""
+    dev = rgb_gt.device
+    image_idx = int(image_idx)
+    refs = [int(r) for r in ref_image_idx_list]
+    tq = torch.as_tensor([float(query_time_step)], dtype=torch.float32, device=dev).view(-1, 1)
+    ang, vel = motion_network(tq)
+    motion = torch.cat([ang, vel], dim=1)
+    zero = torch.zeros((), dtype=torch.float32, device=dev)
+    res = dict(sdf_loss=step_losses(out, rgb_gt, 0.0, 0.0, 1.0, motion=motion)[0], flow_rgb_loss=zero,
+               sdf_consistency_loss=zero, flow_fw_pred=None)
+    if (use_flow_rgb or use_consistency) and refs[0] > image_idx:
+        if use_consistency and image_idx != world_cam_idx:
+            with torch.set_grad_enabled(consistency_pose_grad and torch.is_grad_enabled()):
+                lo, hi = min(world_cam_idx, image_idx), max(world_cam_idx, image_idx)
+                _, rel = motion_network.compute_relative_camera_pose(lo, hi, total_nb_images, nb_sample_timestep)
+                c2c_w = motion_network.compute_w2c_mappings(rel)[-1]
+                cw2 = rigid_inverse(c2c_w) if world_cam_idx <= image_idx else c2c_w
+            res["sdf_consistency_loss"] = sdf_consistency_loss(sdf_network, out["_pts4"][:, :3], out["sdf"], cw2,
+                                                               world_time_step)
+        if use_flow_rgb:
+            _, c2c = motion_network.compute_relative_camera_pose(image_idx, refs[nb_valid - 1], total_nb_images,
+                                                                 nb_sample_timestep)
+            sel = torch.as_tensor([r - image_idx for r in refs[:nb_valid]], device=dev)
+            w2c = motion_network.compute_w2c_mappings(c2c)[sel]
+            wp = weighted_points(out["weights"], out["_pts4"])
+            KS = projection_matrices(scale_mat, ref_camera_mats[:nb_valid])
+            res["flow_rgb_loss"], res["flow_fw_pred"] = flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs[:nb_valid], rgb_gt,
+                                                                      return_flow=True)
+    return res

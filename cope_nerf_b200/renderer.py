@@ -39,104 +39,179 @@ def sample_cdf(cdf, bins, n_samples, return_inds=False):
     return (out, inds) if return_inds else out
 
 
+def _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far, n_coarse,
+                  cos_anneal, eval_mode):
+    """render_core forward (model/neus_renderer.py:307-450): points -> fused SDF + colour MLPs -> compositing.
+    Returns (outputs, saved): outputs = (color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, dists, mid_z),
+    grad4 = packed (normal | sdf flow) [P,4], pts4 = packed (x,y,z,t) [P,4]."""
+    sdf_net, col_net = rnd.sdf_network, rnd.color_network
+    dev = z.device
+    N, S = z.shape
+    P = N * S
+    s = L.stream()
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    rays_d_norm = rays_d_norm.contiguous().float()
+    z = z.contiguous()
+    near, far = near.contiguous().float(), far.contiguous().float()
+    tstep = time_step.reshape(-1)[:1].contiguous().float()
+    prec_s, prec_c = sdf_net.precision, col_net.precision
+    if prec_s != prec_c:
+        raise L.CopeError("SDF and colour networks must use the same precision inside NeuSRenderer")
+
+    pts = _f32(P, 4, device=dev)
+    dists, mid_z = _f32(N, S, device=dev), _f32(N, S, device=dev)
+    L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
+           n_coarse, N, S, 1, L.ptr(pts), L.ptr(dists), L.ptr(mid_z), s)
+
+    sdf, grad, rgb = _f32(P, 1, device=dev), _f32(P, 4, device=dev), _f32(P, 3, device=dev)
+    sdf_saved = _f32(L.query("cope_sdf_saved_floats", sdf_net.desc, P, 1, prec_s), device=dev)
+    col_saved = _f32(L.query("cope_color_saved_floats", col_net.desc, P, prec_c), device=dev)
+    ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
+    L.call("cope_render_mlp_fwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
+           col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(ws),
+           prec_s, s)
+
+    weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
+    color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
+    wsum, wmax, inv_s = _f32(N, 1, device=dev), _f32(N, 1, device=dev), _f32(1, device=dev)
+    L.call("cope_composite_fwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
+           L.ptr(rays_d_norm), L.ptr(variance), float(cos_anneal), int(eval_mode), N, S, L.ptr(weights),
+           L.ptr(color), L.ptr(depth), L.ptr(wz), L.ptr(cdf), L.ptr(wsum), L.ptr(wmax), L.ptr(inv_s), s)
+    saved = (sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb, sdf_saved, col_saved)
+    return (color, depth, grad, weights, sdf, pts, wz, cdf, wsum, wmax, inv_s, dists, mid_z), saved
+
+
+def _core_backward(rnd, cfg, saved, need_rays, need_var, d_color, d_depth, d_grad, d_weights, d_sdf_up, d_pts):
+    """render_core backward: compositing -> colour net -> SDF net (first + second order) -> rays.
+    d_grad [P,4] / d_pts [P,4] are buffers OWNED by the caller's backward (accumulated into here), or None."""
+    (sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb, sdf_saved, col_saved) = saved
+    sdf_net, col_net = rnd.sdf_network, rnd.color_network
+    N, S, n_coarse, cos_anneal, eval_mode = cfg
+    P, dev, s = N * S, z.device, L.stream()
+    prec_s = sdf_net.precision
+    if d_grad is None:
+        d_grad = torch.zeros(P, 4, dtype=torch.float32, device=dev)
+    d_sdf, d_rgb = _f32(P, 1, device=dev), _f32(P, 3, device=dev)
+    d_var = torch.zeros(1, dtype=torch.float32, device=dev)
+    d_rays_d = _f32(N, 3, device=dev)
+    cg = lambda t: L.ptr(t.contiguous()) if t is not None else None
+    L.call("cope_composite_bwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
+           L.ptr(rays_d_norm), L.ptr(variance), cos_anneal, eval_mode, N, S, cg(d_color),
+           cg(d_depth), cg(d_weights), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb), L.ptr(d_var), L.ptr(d_rays_d), s)
+    if d_sdf_up is not None:
+        d_sdf = d_sdf + d_sdf_up.reshape(P, 1)
+
+    ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
+    d_col_flat = torch.zeros_like(col_flat)
+    d_sdf_flat = torch.zeros_like(sdf_flat)
+    d_dirs_pp = None
+    if need_rays:
+        if d_pts is None:
+            d_pts = torch.zeros(P, 4, dtype=torch.float32, device=dev)
+        d_dirs_pp = _f32(P, 3, device=dev)
+    else:
+        d_pts = None
+    L.call("cope_render_mlp_bwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
+           col_net.multires_view, P, L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb),
+           L.ptr(d_sdf_flat), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(ws), prec_s, s)
+    d_rays_o = None
+    if need_rays:
+        d_rays_o = _f32(N, 3, device=dev)
+        L.call("cope_ray_points_bwd", L.ptr(d_pts), L.ptr(mid_z), L.ptr(d_dirs_pp), N, S, L.ptr(d_rays_o),
+               L.ptr(d_rays_d), s)
+    else:
+        d_rays_d = None
+    d_variance = d_var.reshape(variance.shape) if need_var else None
+    return d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d
+
+
 class _RenderCoreFn(torch.autograd.Function):
     """render_core (model/neus_renderer.py:307-450) as one autograd node."""
 
     @staticmethod
     def forward(ctx, rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
                 n_coarse, cos_anneal, eval_mode):
-        sdf_net, col_net = rnd.sdf_network, rnd.color_network
-        dev = z.device
-        N, S = z.shape
-        P = N * S
-        s = L.stream()
-        rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
-        rays_d_norm = rays_d_norm.contiguous().float()
-        z = z.contiguous()
-        near, far = near.contiguous().float(), far.contiguous().float()
-        tstep = time_step.reshape(-1)[:1].contiguous().float()
-        prec_s, prec_c = sdf_net.precision, col_net.precision
-        if prec_s != prec_c:
-            raise L.CopeError("SDF and colour networks must use the same precision inside NeuSRenderer")
-
-        pts = _f32(P, 4, device=dev)
-        dists, mid_z = _f32(N, S, device=dev), _f32(N, S, device=dev)
-        L.call("cope_ray_points", L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(tstep), L.ptr(near), L.ptr(far),
-               n_coarse, N, S, 1, L.ptr(pts), L.ptr(dists), L.ptr(mid_z), s)
-
-        sdf, grad, rgb = _f32(P, 1, device=dev), _f32(P, 4, device=dev), _f32(P, 3, device=dev)
-        sdf_saved = _f32(L.query("cope_sdf_saved_floats", sdf_net.desc, P, 1, prec_s), device=dev)
-        col_saved = _f32(L.query("cope_color_saved_floats", col_net.desc, P, prec_c), device=dev)
-        ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
-        L.call("cope_render_mlp_fwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
-               col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(ws),
-               prec_s, s)
-
-        weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
-        color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
-        wsum, wmax, inv_s = _f32(N, 1, device=dev), _f32(N, 1, device=dev), _f32(1, device=dev)
-        L.call("cope_composite_fwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
-               L.ptr(rays_d_norm), L.ptr(variance), float(cos_anneal), int(eval_mode), N, S, L.ptr(weights),
-               L.ptr(color), L.ptr(depth), L.ptr(wz), L.ptr(cdf), L.ptr(wsum), L.ptr(wmax), L.ptr(inv_s), s)
-
-        ctx.rnd, ctx.cfg = rnd, (N, S, n_coarse, float(cos_anneal), int(eval_mode))
-        ctx.save_for_backward(sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb,
-                              sdf_saved, col_saved)
-        normals = grad[:, :3].reshape(N, S, 3).contiguous()
-        flows = grad[:, 3:].clone().reshape(N, S, 1)
-        points = pts[:, :3].reshape(N, S, 3).contiguous()
-        ctx.mark_non_differentiable(wz, cdf, wsum, wmax, inv_s, dists, mid_z)
-        return color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z
+        outs, saved = _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
+                                    n_coarse, cos_anneal, eval_mode)
+        ctx.rnd, ctx.cfg = rnd, (z.shape[0], z.shape[1], n_coarse, float(cos_anneal), int(eval_mode))
+        ctx.save_for_backward(*saved)
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None instead of freshly filled zero tensors
+        ctx.mark_non_differentiable(*outs[6:])    # wz, cdf, wsum, wmax, inv_s, dists, mid_z
+        return outs
 
     @staticmethod
-    def backward(ctx, d_color, d_depth, d_normals, d_flows, d_weights, d_sdf_up, d_points, *unused):
-        (sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb, sdf_saved,
-         col_saved) = ctx.saved_tensors
-        rnd = ctx.rnd
-        sdf_net, col_net = rnd.sdf_network, rnd.color_network
-        N, S, n_coarse, cos_anneal, eval_mode = ctx.cfg
-        P, dev, s = N * S, z.device, L.stream()
-        prec_s, prec_c = sdf_net.precision, col_net.precision
+    def backward(ctx, d_color, d_depth, d_grad4, d_weights, d_sdf_up, d_pts4, *unused):
         need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
-
-        # upstream of the analytic gradient (normals | sdf_flow), accumulated into by compositing + colour net
-        d_grad = torch.zeros(P, 4, dtype=torch.float32, device=dev)
-        if d_normals is not None:
-            d_grad[:, :3] = d_normals.reshape(P, 3)
-        if d_flows is not None:
-            d_grad[:, 3:] = d_flows.reshape(P, 1)
-        d_sdf, d_rgb = _f32(P, 1, device=dev), _f32(P, 3, device=dev)
-        d_var = torch.zeros(1, dtype=torch.float32, device=dev)
-        d_rays_d = torch.zeros(N, 3, dtype=torch.float32, device=dev)
-        cg = lambda t: L.ptr(t.contiguous()) if t is not None else None
-        L.call("cope_composite_bwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
-               L.ptr(rays_d_norm), L.ptr(variance), cos_anneal, eval_mode, N, S, cg(d_color),
-               cg(d_depth), cg(d_weights), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb), L.ptr(d_var), L.ptr(d_rays_d), s)
-        if d_sdf_up is not None:
-            d_sdf = d_sdf + d_sdf_up.reshape(P, 1)
-
-        ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
-        d_col_flat = torch.zeros_like(col_flat)
-        d_sdf_flat = torch.zeros_like(sdf_flat)
-        d_pts = d_dirs_pp = None
-        if need_rays:
-            d_pts = torch.zeros(P, 4, dtype=torch.float32, device=dev)
-            if d_points is not None:
-                d_pts[:, :3] = d_points.reshape(P, 3)
-            d_dirs_pp = _f32(P, 3, device=dev)
-        L.call("cope_render_mlp_bwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
-               col_net.multires_view, P, L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb),
-               L.ptr(d_sdf_flat), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(ws), prec_s, s)
-        d_rays_o = None
-        if need_rays:
-            d_rays_o = _f32(N, 3, device=dev)
-            L.call("cope_ray_points_bwd", L.ptr(d_pts), L.ptr(mid_z), L.ptr(d_dirs_pp), N, S, L.ptr(d_rays_o),
-                   L.ptr(d_rays_d), s)
-        else:
-            d_rays_d = None
-        d_variance = d_var.reshape(variance.shape) if ctx.needs_input_grad[3] else None
+        # the core accumulates into these: never into autograd's own buffers
+        d_grad = d_grad4.contiguous().clone() if d_grad4 is not None else None
+        d_pts = d_pts4.contiguous().clone() if (d_pts4 is not None and need_rays) else None
+        d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d = _core_backward(
+            ctx.rnd, ctx.cfg, ctx.saved_tensors, need_rays, ctx.needs_input_grad[3], d_color, d_depth, d_grad, d_weights,
+            d_sdf_up, d_pts)
         return (None, d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d, None, None, None, None, None, None,
                 None, None)
+
+
+class _RenderStepFn(torch.autograd.Function):
+    """render_core AND the step's loss reductions as one autograd node (the fused training path): forward =
+    _core_forward + cope_step_losses_fwd, backward = cope_step_losses_bwd + _core_backward.  No per-sample tensor
+    crosses autograd, and the ~60 elementwise launches of the torch loss expressions become two.
+    Losses: rgb L1 (model/training.py:508), eikonal (train.py:526) and, with `motion` = (angular velocity | velocity)
+    [6], the SDF-flow loss (train.py:467-477).  Returns (total, parts[4] = total / rgb / eikonal / sdf-flow, *core outputs)."""
+
+    @staticmethod
+    def forward(ctx, rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
+                n_coarse, cos_anneal, rgb_gt, motion, w_sum_global, w_rgb, w_eik, w_flow):
+        outs, saved = _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
+                                    n_coarse, cos_anneal, False)
+        color, depth, grad4, weights, sdf, pts4 = outs[:6]
+        N, S = z.shape
+        dev = z.device
+        rgb_gt = rgb_gt.contiguous().float()
+        mot = motion.detach().reshape(6).contiguous().float() if motion is not None else None
+        losses, coef, ws = _f32(4, device=dev), _f32(4, device=dev), _f32(8, device=dev)
+        L.call("cope_step_losses_fwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4) if mot is not None else None,
+               L.ptr(weights) if mot is not None else None, L.ptr(mot), L.ptr(w_sum_global), N, N * S,
+               float(w_rgb), float(w_eik), float(w_flow), L.ptr(losses), L.ptr(coef), L.ptr(ws), L.stream())
+        ctx.rnd, ctx.cfg = rnd, (N, S, n_coarse, float(cos_anneal), 0)
+        ctx.has_motion = mot is not None
+        ctx.save_for_backward(*saved, color, weights, rgb_gt, coef, *([mot] if mot is not None else []))
+        ctx.set_materialize_grads(False)
+        ctx.motion_shape = motion.shape if motion is not None else None
+        total = losses[0].clone()                 # a differentiable output must not alias the non-differentiable parts
+        ctx.mark_non_differentiable(losses, *outs)
+        return (total, losses, *outs)
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        n_saved = 14
+        saved = ctx.saved_tensors[:n_saved]
+        color, weights, rgb_gt, coef = ctx.saved_tensors[n_saved:n_saved + 4]
+        mot = ctx.saved_tensors[n_saved + 4] if ctx.has_motion else None
+        N, S = ctx.cfg[:2]
+        P, dev = N * S, color.device
+        need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        grad4, pts4 = saved[10], saved[8]
+        n_in = 19
+        if g_total is None:
+            return (None,) * n_in
+        d_color, d_grad = _f32(N, 3, device=dev), _f32(P, 4, device=dev)
+        d_pts = _f32(P, 4, device=dev) if (need_rays and mot is not None) else None
+        d_motion = torch.zeros(6, dtype=torch.float32, device=dev) if (mot is not None and ctx.needs_input_grad[14]) else None
+        L.call("cope_step_losses_bwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4) if mot is not None else None,
+               L.ptr(weights) if mot is not None else None, L.ptr(mot), N, P, L.ptr(coef),
+               L.ptr(g_total.reshape(1).float()), L.ptr(d_color), L.ptr(d_grad), L.ptr(d_pts), L.ptr(d_motion), L.stream())
+        d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d = _core_backward(
+            ctx.rnd, ctx.cfg, saved, need_rays, ctx.needs_input_grad[3], d_color, None, d_grad, None, None, d_pts)
+        if d_motion is not None:
+            d_motion = d_motion.reshape(ctx.motion_shape)
+        return (None, d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d, None, None, None, None, None, None, None,
+                None, d_motion, None, None, None, None)
+
+
+def _unpack_views(grad4, pts4, n):
+    """normals (N,S,3), sdf_flows (N,S,1), sampled_points (N,S,3) as strided views of the packed [P,4] tensors."""
+    return grad4[:, :3].reshape(n, -1, 3), grad4[:, 3:].reshape(n, -1, 1), pts4[:, :3].reshape(n, -1, 3)
 
 
 def _render_core_infer(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far, n_coarse,
@@ -174,6 +249,36 @@ def _render_core_infer(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d
     flows = grad[:, 3:].clone().reshape(N, S, 1)
     points = pts[:, :3].reshape(N, S, 3).contiguous()
     return color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z, grad, pts
+
+
+class _LazyOutputs(dict):
+    """Output dict of the fused training path: the per-key views / fills of `NeuSRenderer.forward` are only built when a
+    key is read (logging), so the timed step launches none of them."""
+
+    def __init__(self, n, color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, parts):
+        super().__init__()
+        nrm = lambda: _unpack_views(grad4, pts4, n)
+        self._make = {
+            'sdf': lambda: sdf, 'color_fine': lambda: color, 'depth_pred': lambda: depth, 'weighted_z_vals': lambda: wz,
+            's_val': lambda: (1.0 / inv_s).expand(n, 1).clone(), 'cdf_fine': lambda: cdf, 'weight_sum': lambda: wsum,
+            'weight_max': lambda: wmax, 'normals': lambda: nrm()[0], 'sdf_flows': lambda: nrm()[1],
+            'sampled_points': lambda: nrm()[2], 'weights': lambda: weights,
+            'inside_sphere': lambda: torch.ones_like(weights), 'weight_inside': lambda: wsum.reshape(n),
+            'weight_outside': lambda: torch.zeros(n, dtype=torch.float32, device=weights.device),
+            '_grad4': lambda: grad4, '_pts4': lambda: pts4, 'loss': lambda: parts[0], 'loss_rgb': lambda: parts[1],
+            'loss_eikonal': lambda: parts[2], 'loss_sdf': lambda: parts[3],
+        }
+
+    def __missing__(self, k):
+        v = self._make[k]()
+        self[k] = v
+        return v
+
+    def __contains__(self, k):
+        return k in self._make
+
+    def keys(self):
+        return self._make.keys()
 
 
 class NeuSRenderer(nn.Module):
@@ -275,6 +380,24 @@ class NeuSRenderer(nn.Module):
                                              sdf_flat=flat)
         return z, n_samples
 
+    def forward_losses(self, rays_o, rays_d, ray_d_norm, time_step, near, far, rgb_gt, cos_anneal_ratio=0.0, it=-1,
+                       rgb_weight=1.0, eikonal_weight=0.1, sdf_weight=0.0, motion=None, w_sum_global=None):
+        """Fused training path: `forward` (eval=False) AND the rgb / eikonal / SDF-flow loss reductions of
+        model/training.py:508, train.py:526, :467-477 as ONE autograd node (_RenderStepFn).  `motion` = the MotionNetwork's
+        (angular velocity | velocity) at the query time, a [6] tensor (None: no SDF-flow term).  Returns
+        (total_loss, dict) where the dict holds the same keys as `forward` (detached) plus loss_rgb / loss_eikonal /
+        loss_sdf."""
+        n = len(rays_o)
+        sdf_flat = self.sdf_network.flat_weights()
+        col_flat = self.color_network.flat_weights()
+        z, n_coarse = self.sample_z(rays_o, rays_d, time_step, near, far, False, sdf_flat, it)
+        (total, parts, color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
+            _RenderStepFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
+                                time_step, z, near, far, n_coarse, cos_anneal_ratio, rgb_gt, motion, w_sum_global,
+                                rgb_weight, eikonal_weight, sdf_weight)
+        out = _LazyOutputs(n, color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, parts)
+        return total, out
+
     def forward(self, rays_o, rays_d, ray_d_norm, time_step, near, far, perturb_overwrite=-1, background_rgb=None,
                 cos_anneal_ratio=0.0, it=-1, eval=False):
         if background_rgb is not None:
@@ -291,9 +414,11 @@ class NeuSRenderer(nn.Module):
                                    rays_d, ray_d_norm, time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
             extra = {'_grad4': grad4, '_pts4': pts4}      # packed (x,y,z,t) views for cope_eval_reduce
         else:
-            (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
+            (color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
                 _RenderCoreFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
                                     time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
+            normals, flows, points = _unpack_views(grad4, pts4, n)
+            extra = {'_grad4': grad4, '_pts4': pts4}      # the packed tensors behind normals / sdf_flows / sampled_points
         return {
             **extra,
             'sdf': sdf,

@@ -93,14 +93,24 @@ def neus_losses(out, rgb_gt, rgb_weight=0.33333, eikonal_weight=0.1):
 
 
 def render_train_step(renderer, pose, cam_id, pixels, camera_mat, scale_mat, rgb_gt, time_step, depth_range,
-                      cos_anneal_ratio=0.5, it=1, rgb_weight=0.33333, eikonal_weight=0.1, loss_scale=1.0):
-    """One training iteration without the optimiser: pose -> rays -> near/far -> NeuSRenderer.forward -> loss ->
-    backward (train.py:425-532 with the rgb + eikonal terms).  Returns (loss, outputs, rays)."""
+                      cos_anneal_ratio=0.5, it=1, rgb_weight=0.33333, eikonal_weight=0.1, loss_scale=1.0, fused=True,
+                      sdf_weight=0.0, motion=None):
+    """One training iteration without the optimiser: pose -> rays -> near/far -> NeuSRenderer -> loss -> backward
+    (train.py:425-532 with the rgb + eikonal terms, plus the SDF-flow term when `motion` is given).
+    fused=True renders and reduces the losses in one autograd node (NeuSRenderer.forward_losses); fused=False goes through
+    the reference-shaped output dict and the torch loss expressions.  Returns (loss, outputs, rays)."""
     world = pose(cam_id)
     o, d, dn = get_world_cameraOrigin_cameraRay(pixels, camera_mat, world, scale_mat)
     near, far = near_far_from_sphere(o, d, depth_range)
-    out = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=False)
-    loss, parts = neus_losses(out, rgb_gt, rgb_weight, eikonal_weight)
+    if fused:
+        loss, out = renderer.forward_losses(o, d, dn, time_step, near, far, rgb_gt, cos_anneal_ratio=cos_anneal_ratio, it=it,
+                                            rgb_weight=rgb_weight, eikonal_weight=eikonal_weight, sdf_weight=sdf_weight,
+                                            motion=motion)
+    else:
+        out = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=False)
+        loss, parts = neus_losses(out, rgb_gt, rgb_weight, eikonal_weight)
+        if motion is not None:
+            loss = loss + sdf_weight * sdf_flow_loss(out, motion.reshape(-1)[:3], motion.reshape(-1)[3:])
     (loss * loss_scale).backward()
     return loss.detach(), out, (o, d, dn)
 

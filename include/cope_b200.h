@@ -248,6 +248,38 @@ int cope_pose_chain_bwd(const float* rel, const float* w2c, int F, const float* 
 int cope_eval_reduce(const float* weights, const float* grad, const float* pts, const float* world_mat, int64_t N, int S,
                      float* normal_out, float* depth_hw_out, cope_stream_t s);
 
+/* ---- loss reductions of the training step (SURVEY.md 8 a17 + 8f rank 2), one forward + one backward launch per group -------
+ * cope_step_losses_*: rgb L1 (model/training.py:508), eikonal (train.py:526) and, when `motion` != NULL, the SDF-flow loss
+ * (train.py:467-477).  color / rgb_gt [N x 3]; grad4 [P x 4] = (d sdf/dx, d sdf/dy, d sdf/dz, d sdf/dt); pts4 [P x 4];
+ * weights [P] (treated as constants, as the reference detaches them); motion [6] = angular velocity | velocity (device);
+ * w_sum_global [1] or NULL = normaliser of the SDF-flow term when rays are sharded over ranks.
+ * losses [4] = (w_rgb l_rgb + w_eik l_eik + w_flow l_flow, l_rgb, l_eik, l_flow); coef [4] = the normalised loss weights the
+ * backward multiplies with (and sum w); ws >= 8 floats, zeroed by the callee.
+ * Backward: g [1] = dL/d losses[0] (device; NULL = 1); d_color [N x 3], d_grad4 [P x 4], d_pts4 [P x 4] (may be NULL)
+ * OVERWRITTEN; d_motion [6] ACCUMULATED (may be NULL). */
+int cope_step_losses_fwd(const float* color, const float* rgb_gt, const float* grad4, const float* pts4, const float* weights,
+                         const float* motion, const float* w_sum_global, int64_t N, int64_t P, float w_rgb, float w_eik,
+                         float w_flow, float* losses, float* coef, float* ws, cope_stream_t s);
+int cope_step_losses_bwd(const float* color, const float* rgb_gt, const float* grad4, const float* pts4, const float* weights,
+                         const float* motion, int64_t N, int64_t P, const float* coef, const float* g, float* d_color,
+                         float* d_grad4, float* d_pts4, float* d_motion, cope_stream_t s);
+/* wp [N x 4] = sum_s weights[n,s] * (pts4[n,s].xyz, 1): the per-sample part of the flow-RGB loss (train.py:488-489).
+ * Backward: d_weights [N x S] and d_pts4 [P x 4] OVERWRITTEN (either may be NULL). */
+int cope_weighted_points_fwd(const float* weights, const float* pts4, int64_t N, int S, float* wp, cope_stream_t s);
+int cope_weighted_points_bwd(const float* weights, const float* pts4, const float* d_wp, int64_t N, int S, float* d_weights,
+                             float* d_pts4, cope_stream_t s);
+/* Flow-RGB loss (train.py:486-517 + warp_pixel :235-244): for each of the T reference frames, m = w2c_t[:3,:] wp,
+ * q = KS_t m, pixel flow = ((q.xy / q.z) - norm_pix) * (W/2, H/2), source = pix + flow, bilinear border-clamped sample of
+ * ref_imgs [T x 3 x H x W] (grid_sample, align_corners=True), loss = sum_t (sum_valid |warped - rgb_gt| / (#valid + 1e-10)) / 3.
+ * flow_pred [T x N x 2] may be NULL; ws >= 2T + 1 floats, zeroed by the callee and read again by the backward.
+ * Backward: g [1] device (NULL = 1); d_wp [N x 4] OVERWRITTEN; d_w2c [T x 16] ACCUMULATED (may be NULL). */
+int cope_flow_rgb_fwd(const float* wp, const float* w2c, const float* KS, const float* norm_pix, const float* pix,
+                      const float* ref_imgs, const float* rgb_gt, int64_t N, int T, int H, int W, float* flow_pred, float* loss,
+                      float* ws, cope_stream_t s);
+int cope_flow_rgb_bwd(const float* wp, const float* w2c, const float* KS, const float* norm_pix, const float* pix,
+                      const float* ref_imgs, const float* rgb_gt, int64_t N, int T, int H, int W, const float* ws, const float* g,
+                      float* d_wp, float* d_w2c, cope_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

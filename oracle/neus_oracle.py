@@ -25,6 +25,7 @@ __all__ = [
     "train_step", "render_image", "DEFAULT_CFG",
     "MOTION_CFG", "init_motion_params", "motion_forward", "euler_xyz_to_matrix", "consecutive_relative_pose",
     "relative_camera_pose", "w2c_mappings",
+    "warp_pixel", "flow_forward_prediction", "flow_rgb_loss", "sdf_consistency_loss", "stage1_losses",
 ]
 
 # configs/default.yaml:103-156 (no scene config overrides any of these shapes)
@@ -589,3 +590,84 @@ def w2c_mappings(rel):
     for r in rel:
         w2c.append(r @ w2c[-1])
     return torch.stack(w2c)
+
+
+# --------------------------------------------------------------------------- stage-1 auxiliary losses
+def warp_pixel(src_frame, uv):
+    """train.py:235-244 (normalize_pix=True): bilinear, border-clamped sample of src_frame [1,3,H,W] at pixel coordinates
+    uv [N,2] (x, y) -> [N,3]."""
+    _, _, h, w = src_frame.shape
+    gx = uv[:, 0] / ((w - 1) / 2) - 1
+    gy = uv[:, 1] / ((h - 1) / 2) - 1
+    grid = torch.stack([gx, gy], dim=-1).view(1, -1, 1, 2)
+    return F.grid_sample(src_frame, grid, mode="bilinear", padding_mode="border", align_corners=True)[0, :, :, 0].T
+
+
+def flow_forward_prediction(pts, weights, n_rays, w2c_t, ref_camera_mat, scale_mat, norm_pix, img_hw):
+    """train.py:487-494 for one reference frame: rigid map of the sampled points, render-weight average per ray, projection
+    with scale_mat[:3,:3] @ ref_camera_mat[:3,:3], flow in pixels relative to the ray's own normalised pixel."""
+    h, w = img_hw
+    pts_map = (w2c_t[:3, :3] @ pts.T + w2c_t[:3, 3:]).T
+    wpm = torch.sum(weights.view(n_rays, -1, 1) * pts_map.view(n_rays, -1, 3), dim=1)
+    pm = (scale_mat[0, :3, :3] @ ref_camera_mat[:3, :3] @ wpm.T).T
+    pm = pm[:, :2] / pm[:, 2:]
+    d = pm - norm_pix
+    return torch.stack([d[:, 0] * (w / 2), d[:, 1] * (h / 2)], dim=-1)
+
+
+def flow_rgb_loss(flow_list, pix, ref_imgs, rgb_gt):
+    """train.py:506-517: warp every reference frame to the sampled pixels, masked L1 against the target colours, summed
+    over the frames and divided by 3 (a constant in the reference, whatever the number of valid frames)."""
+    total = 0.0
+    for t, flow in enumerate(flow_list):
+        ref = ref_imgs[t].unsqueeze(0).float()
+        corr = pix + flow
+        with torch.no_grad():
+            lim = torch.tensor([ref.shape[3], ref.shape[2]]).float()
+            mask = ((corr >= 0) & (corr < lim)).all(dim=1, keepdim=True)
+        warped = warp_pixel(ref, corr)
+        total = total + torch.sum(torch.abs(warped - rgb_gt) * mask) / (torch.sum(mask) + 1e-10)
+    return total / 3.0
+
+
+def sdf_consistency_loss(sdf_params, pts, sdf, cw2, world_time_step, **kw):
+    """train.py:502-505: the SDF at the world time step, queried at the sampled points mapped by cw2, against the rendered one."""
+    pw = (cw2[:3, :3] @ pts.T + cw2[:3, 3:]).T
+    x = torch.cat([pw, torch.ones_like(pw[:, :1]) * world_time_step], dim=1)
+    return torch.mean(torch.abs(sdf_value(sdf_params, x, **kw) - sdf))
+
+
+def stage1_losses(sdf_params, motion_params, out, rgb_gt, query_time_step, image_idx, ref_image_idx_list, nb_valid,
+                  total_nb_images, nb_sample_timestep, ref_camera_mats, scale_mat, norm_pix, pix, img_hw, ref_imgs,
+                  world_cam_idx, world_time_step, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True,
+                  sdf_kw=None, motion_kw=None):
+    """train.py:467-517 (the `not query_in_canonical_space` branch): SDF-flow loss, flow-RGB loss over the valid reference
+    frames and SDF-consistency loss.  `out` holds sampled_points, normals, sdf_flows, weights, sdf as NeuSRenderer returns them.
+    Returns dict(sdf_loss, flow_rgb_loss, sdf_consistency_loss, flow_fw_pred)."""
+    sdf_kw, motion_kw = sdf_kw or {}, motion_kw or {}
+    pts = out["sampled_points"].reshape(-1, 3)
+    weights = out["weights"].reshape(-1)
+    n_rays = rgb_gt.shape[0]
+    ang, vel = motion_forward(motion_params, torch.as_tensor([float(query_time_step)]).view(-1, 1), **motion_kw)
+    res = dict(sdf_loss=sdf_flow_loss(out, ang, vel), flow_rgb_loss=torch.zeros(()), sdf_consistency_loss=torch.zeros(()),
+               flow_fw_pred=[])
+    if (use_flow_rgb or use_consistency) and int(ref_image_idx_list[0]) > int(image_idx):
+        _, c2c = relative_camera_pose(motion_params, int(image_idx), int(ref_image_idx_list[nb_valid - 1]), total_nb_images,
+                                      nb_sample_timestep, **motion_kw)
+        sel = [int(r) - int(image_idx) for r in ref_image_idx_list[:nb_valid]]
+        w2c = w2c_mappings(c2c)[sel]
+        flows = [flow_forward_prediction(pts, weights, n_rays, w2c[t], ref_camera_mats[t], scale_mat, norm_pix, img_hw)
+                 for t in range(len(w2c))]
+        res["flow_fw_pred"] = flows
+        if use_consistency and int(image_idx) != world_cam_idx:
+            with torch.set_grad_enabled(consistency_pose_grad):
+                lo, hi = min(world_cam_idx, int(image_idx)), max(world_cam_idx, int(image_idx))
+                _, rel = relative_camera_pose(motion_params, lo, hi, total_nb_images, nb_sample_timestep, **motion_kw)
+                c2c_w = w2c_mappings(rel)[-1]
+                cw2 = torch.inverse(c2c_w) if world_cam_idx <= int(image_idx) else c2c_w
+                pw = (cw2[:3, :3] @ pts.T + cw2[:3, 3:]).T
+            x = torch.cat([pw, torch.ones_like(pw[:, :1]) * world_time_step], dim=1)
+            res["sdf_consistency_loss"] = torch.mean(torch.abs(sdf_value(sdf_params, x, **sdf_kw) - out["sdf"]))
+        if use_flow_rgb:
+            res["flow_rgb_loss"] = flow_rgb_loss(flows[:nb_valid], pix, ref_imgs, rgb_gt)
+    return res

@@ -401,6 +401,94 @@ def main():
     mo.update({f"param.{k}": v for k, v in mp.items()})
     G["motion_small"] = npd(mo)
 
+    # ---------------------------------------------------------------- stage-1 auxiliary losses (train.py:467-517)
+    # The reference's own source lines are executed here (train.py cannot be imported: tensorboardX, datasets ...): lines
+    # 235-244 (warp_pixel) and 467-517 (SDF-flow, flow-RGB, SDF-consistency) are read from the mounted file, dedented and run
+    # against a stand-in `self` that carries the IMPORTED reference networks.  Nothing of them is written into this repo.
+    import textwrap
+    src = open(os.path.join(REF, "train.py")).read().split("\n")
+    ns = {"torch": torch, "np": np}
+    exec(textwrap.dedent("\n".join(src[234:244])), ns)                     # def warp_pixel(self, src_frame, uv, normalize_pix=True)
+    block = textwrap.dedent("\n".join(src[466:517]))
+    exec("def stage1_block(self, render_out, sdf, query_time_step, image_idx, ref_image_idx_list, nb_valid_next_time_step,\n"
+         "                 ref_camera_mat_list, scale_mat, normalized_sampled_pixel, sampled_pixel, img, rgb_pred, rgb_gt,\n"
+         "                 ref_image_list):\n"
+         "    flow_rgb_loss = torch.tensor(0.0).float()\n"
+         "    sdf_consistency_loss = torch.tensor(0.0).float()\n"
+         + textwrap.indent(block, "    ") +
+         "\n    return sdf_loss, flow_rgb_loss, sdf_consistency_loss, (flow_fw_pred_list if 'flow_fw_pred_list' in dir() else [])\n", ns)
+    torch.manual_seed(41)
+    s_sdf = R.fields.SDFNetwork(**{**SMALL_SDF, "skip_in": [4]})
+    s_mot = R.fields.MotionNetwork(**mcfg)
+    with torch.no_grad():
+        for k in ("lin4.weight_g", "lin4.bias"):
+            s_mot.state_dict()[k].mul_(4.0).add_(0.2)
+        for q in s_sdf.parameters():
+            q.add_(0.05 * torch.randn_like(q))
+    n1, S1, H1, W1, T1 = 24, 8, 20, 30, 3
+    fake = types.SimpleNamespace(
+        query_in_canonical_space=False, motion_network=s_mot, sdf_network=s_sdf, device="cpu", total_nb_images=6,
+        nb_sample_timestep=3, world_cam_idx=0, world_time_step=-1.0,
+        cfg={"training": {"flow_rgb_weight": [0.0, 1.0], "sdf_consistency_weight": [0.1, 0.1],
+                          "sdf_consistency_enable_pose_grad": True}})
+    fake.warp_pixel = types.MethodType(ns["warp_pixel"], fake)
+    leaf = lambda *sh, sc=1.0: (sc * torch.randn(*sh)).requires_grad_(True)
+    pts_l = leaf(n1, S1, 3, sc=0.4)
+    with torch.no_grad():
+        pts_l[..., 2] -= 2.0                                              # in front of the cameras (K has -1 on z)
+    nrm_l, flw_l, sdf_l = leaf(n1, S1, 3), leaf(n1, S1, 1, sc=0.3), leaf(n1 * S1, 1, sc=0.2)
+    wts_l = torch.softmax(torch.randn(n1, S1), dim=1).mul(0.9).requires_grad_(True)
+    rgbp_l = torch.rand(n1, 3)
+    rgb_gt1 = torch.rand(n1, 3)
+    image_idx = torch.tensor(1)
+    ref_idx = torch.tensor([2, 3, 5])
+    nb_valid = 2
+    Kr = torch.stack([O.camera_matrix(0.8 * W1 * (1 + 0.05 * k), 0.8 * W1, W1, H1) for k in range(T1)]).unsqueeze(1)[:, 0]
+    Sc1 = torch.eye(4).unsqueeze(0)
+    sp = torch.stack([torch.randint(0, W1, (n1,)), torch.randint(0, H1, (n1,))], dim=-1).float()
+    nsp = torch.stack([2 * sp[:, 0] / (W1 - 1) - 1, 2 * sp[:, 1] / (H1 - 1) - 1], dim=-1)
+    img1 = torch.rand(1, 3, H1, W1)
+    refs = torch.rand(T1, 3, H1, W1)
+    qts = torch.tensor([-0.6])
+    ro1 = {"sampled_points": pts_l, "normals": nrm_l, "sdf_flows": flw_l, "weights": wts_l}
+    sl_r, fl_r, cl_r, fw_r = ns["stage1_block"](fake, ro1, sdf_l, qts, image_idx, ref_idx, nb_valid, Kr, Sc1, nsp, sp, img1,
+                                               rgbp_l, rgb_gt1, refs)
+    wsl = (0.7, 1.3, 0.9)
+    (wsl[0] * sl_r + wsl[1] * fl_r + wsl[2] * cl_r).backward()
+    leaves = dict(pts=pts_l, normals=nrm_l, sdf_flows=flw_l, sdf=sdf_l, weights=wts_l)
+    g_ref = {k: v.grad.clone() for k, v in leaves.items()}
+    g_ref.update({f"motion.{k}": v.grad.clone() for k, v in s_mot.named_parameters()})
+    g_ref.update({f"sdfnet.{k}": v.grad.clone() for k, v in s_sdf.named_parameters()})
+    # oracle restatement on the same inputs
+    mp1 = {k: v.detach().clone().requires_grad_(True) for k, v in s_mot.state_dict().items()}
+    sp1 = {k: v.detach().clone().requires_grad_(True) for k, v in s_sdf.state_dict().items()}
+    lv = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+    oo = O.stage1_losses(sp1, mp1, {"sampled_points": lv["pts"], "normals": lv["normals"], "sdf_flows": lv["sdf_flows"],
+                                    "weights": lv["weights"], "sdf": lv["sdf"]}, rgb_gt1, float(qts), 1, [2, 3, 5], nb_valid,
+                         6, 3, Kr, Sc1, nsp, sp, (H1, W1), refs, 0, -1.0)
+    close(oo["sdf_loss"], sl_r, 1e-6, "stage1 sdf_loss"); close(oo["flow_rgb_loss"], fl_r, 1e-6, "stage1 flow_rgb")
+    close(oo["sdf_consistency_loss"], cl_r, 1e-6, "stage1 consistency")
+    for a, b in zip(oo["flow_fw_pred"], fw_r):
+        close(a, b, 1e-5, "stage1 flow_fw_pred")
+    (wsl[0] * oo["sdf_loss"] + wsl[1] * oo["flow_rgb_loss"] + wsl[2] * oo["sdf_consistency_loss"]).backward()
+    for k in leaves:
+        close(lv[k].grad, g_ref[k], 2e-5, f"stage1 grad {k}")
+    for k, v in mp1.items():
+        if f"motion.{k}" in g_ref:
+            close(v.grad, g_ref[f"motion.{k}"], 5e-5, f"stage1 motion grad {k}")
+    for k, v in sp1.items():
+        if f"sdfnet.{k}" in g_ref:
+            close(v.grad, g_ref[f"sdfnet.{k}"], 5e-5, f"stage1 sdf-net grad {k}")
+    s1 = dict(n=n1, S=S1, H=H1, W=W1, image_idx=1, ref_idx=ref_idx, nb_valid=nb_valid, total_nb_images=6, nb_sample_timestep=3,
+              world_cam_idx=0, world_time_step=-1.0, query_time_step=qts, Kr=Kr, scale=Sc1, pix=sp, norm_pix=nsp, refs=refs,
+              rgb_gt=rgb_gt1, loss_weights=torch.tensor(wsl), sdf_loss=sl_r, flow_rgb_loss=fl_r, sdf_consistency_loss=cl_r,
+              flow_fw_pred=torch.stack(fw_r))
+    s1.update({f"in.{k}": v.detach() for k, v in leaves.items()})
+    s1.update({f"grad.{k}": v for k, v in g_ref.items()})
+    s1.update({f"motion.{k}": v.detach() for k, v in s_mot.state_dict().items()})
+    s1.update({f"sdfnet.{k}": v.detach() for k, v in s_sdf.state_dict().items()})
+    G["stage1_small"] = npd(s1)
+
     only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     for name, d in G.items():
         if only and name not in only:

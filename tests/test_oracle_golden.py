@@ -178,3 +178,38 @@ def test_motion_network_and_pose_integration():
     (w2c * g["wgt"]).sum().backward()
     for k in P:
         assert_close(Pg[k].grad, g[f"grad.{k}"], 2e-5, f"grad {k}")
+
+
+def _stage1_oracle(g, requires_grad=True):
+    """Replays tests/golden/stage1_small.npz (the reference's own train.py:467-517 lines, executed by make_golden.py)."""
+    mk = (lambda v: v.clone().requires_grad_(True)) if requires_grad else (lambda v: v.clone())
+    mp = {k: mk(v) for k, v in unflatten(g, "motion.").items()}
+    sp = {k: mk(v) for k, v in unflatten(g, "sdfnet.").items()}
+    lv = {k: mk(v) for k, v in unflatten(g, "in.").items()}
+    small = dict(multires=6, skip_in=(4,), scale=1.0)
+    out = {"sampled_points": lv["pts"], "normals": lv["normals"], "sdf_flows": lv["sdf_flows"], "weights": lv["weights"],
+           "sdf": lv["sdf"]}
+    res = O.stage1_losses(sp, mp, out, g["rgb_gt"], float(g["query_time_step"]), int(g["image_idx"]),
+                          [int(v) for v in g["ref_idx"]], int(g["nb_valid"]), int(g["total_nb_images"]),
+                          int(g["nb_sample_timestep"]), g["Kr"], g["scale"], g["norm_pix"], g["pix"], (int(g["H"]), int(g["W"])),
+                          g["refs"], int(g["world_cam_idx"]), float(g["world_time_step"]), sdf_kw=small)
+    return res, mp, sp, lv
+
+
+def test_stage1_auxiliary_losses():
+    g = load_golden("stage1_small")
+    res, mp, sp, lv = _stage1_oracle(g)
+    for k in ("sdf_loss", "flow_rgb_loss", "sdf_consistency_loss"):
+        assert_close(res[k], g[k], 1e-6, k)
+    assert_close(torch.stack(res["flow_fw_pred"]), g["flow_fw_pred"], 1e-5, "flow_fw_pred")
+    w = g["loss_weights"]
+    (w[0] * res["sdf_loss"] + w[1] * res["flow_rgb_loss"] + w[2] * res["sdf_consistency_loss"]).backward()
+    for k, v in lv.items():
+        assert_close(v.grad, g[f"grad.{k}"], 2e-5, f"grad {k}")
+    n = 0
+    for tag, params in (("motion", mp), ("sdfnet", sp)):
+        for k, v in params.items():
+            if f"grad.{tag}.{k}" in g:
+                assert_close(v.grad, g[f"grad.{tag}.{k}"], 5e-5, f"grad {tag}.{k}")
+                n += 1
+    assert n == 15 + 27
