@@ -142,7 +142,23 @@ def main():
                 g_grad.copy_(g_grad0)
                 L.call("cope_render_mlp_bwd", sn.desc, flat, cn.desc, cflat, x, dirs_pp, S, cn.multires_view, P, sdf_saved, col_saved,
                        g_sdf, g_grad, g_rgb, dWs, dWc, dx, ddirs, ws, C.PREC_BF16, st)
+        # loss reductions (cope_step_losses_*: rgb L1 + eikonal + SDF-flow; cope_weighted_points_fwd: flow-RGB's per-sample part)
+        gt, mot6 = torch.rand(N, 3, device=dev), torch.randn(6, device=dev)
+        l_out, l_coef, l_ws, l_g = f(4), f(4), f(8), torch.ones(1, device=dev)
+        dl_color, dl_grad, dl_pts, dl_mot, wpts = f(N, 3), f(P, 4), f(P, 4), torch.zeros(6, device=dev), f(N, 4)
+
+        def loss_fwd():
+            L.call("cope_step_losses_fwd", color, gt, grad, x, weights, mot6, None, N, P, 0.33333, 0.1, 0.1, l_out, l_coef, l_ws, st)
+
+        def loss_bwd():
+            L.call("cope_step_losses_bwd", color, gt, grad, x, weights, mot6, N, P, l_coef, l_g, dl_color, dl_grad, dl_pts, dl_mot, st)
+
+        def wpts_fwd():
+            L.call("cope_weighted_points_fwd", weights, x, N, S, wpts, st)
         rows = [
+            ("step_losses_fwd", loss_fwd, P * 36 + N * 24, "hbm"),               # grad4 16 + pts4 16 + w 4 per sample in
+            ("step_losses_bwd", loss_bwd, P * 68 + N * 36, "hbm"),               # + d_grad4 16 + d_pts4 16 out
+            ("weighted_points_fwd", wpts_fwd, P * 20 + N * 16, "hbm"),
             ("composite_fwd", comp_fwd, N * (S * 36 + 44), "hbm"),                # z,dists,sdf 12 + grad 16 + rgb 12 in; w 4 out
             ("composite_bwd", comp_bwd, N * (S * 84 + 60), "hbm"),                # 40 in + d_w 4 + d_grad rw 32 + d_sdf 4 + d_rgb 12 - z
             ("upsample", ups, N * ((S - 16) * 8 + 64), "hbm"),

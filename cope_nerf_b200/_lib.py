@@ -87,6 +87,7 @@ _SIGS = {
     "cope_weighted_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),
     "cope_flow_rgb_fwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f]),
     "cope_flow_rgb_bwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f, _f]),
+    "cope_sample_pixels": (_i, [_f, C.c_uint64, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }
 EXPORTS = tuple(_SIGS)

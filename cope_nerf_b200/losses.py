@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["step_losses", "weighted_points", "flow_rgb_loss", "sdf_consistency_loss", "projection_matrices", "rigid_inverse",
+__all__ = ["step_losses", "packed_outputs", "weighted_points", "flow_rgb_loss", "sdf_consistency_loss", "projection_matrices", "rigid_inverse",
            "stage1_losses"]
 
 
@@ -62,11 +62,24 @@ class _StepLossFn(torch.autograd.Function):
         return d_color, None, d_grad4, d_pts4, None, d_motion, None, None, None, None
 
 
+def packed_outputs(out):
+    """(grad4 [P,4], pts4 [P,4]) of a renderer output: the packed tensors a `RenderOutputs` carries, or — for a plain dict
+    with the reference's keys — the concatenation of normals | sdf_flows and sampled_points | 0."""
+    g4, p4 = getattr(out, "grad4", None), getattr(out, "pts4", None)
+    if g4 is None:
+        g4 = torch.cat([out["normals"].reshape(-1, 3), out["sdf_flows"].reshape(-1, 1)], dim=1)
+    if p4 is None:
+        p = out["sampled_points"].reshape(-1, 3)
+        p4 = torch.cat([p, torch.zeros_like(p[:, :1])], dim=1)
+    return g4, p4
+
+
 def step_losses(out, rgb_gt, rgb_weight=1.0, eikonal_weight=0.1, sdf_weight=0.0, motion=None, w_sum_global=None):
     """total, parts = losses of model/training.py:508 (rgb L1), train.py:526 (eikonal) and train.py:467-477 (SDF-flow, when
     `motion` = (angular velocity | velocity) [6] is given) from a `NeuSRenderer.forward` output dict.
     parts = [total, rgb, eikonal, sdf_flow] (no gradient)."""
-    return _StepLossFn.apply(out["color_fine"], rgb_gt, out["_grad4"], out["_pts4"], out["weights"], motion, w_sum_global,
+    grad4, pts4 = packed_outputs(out)
+    return _StepLossFn.apply(out["color_fine"], rgb_gt, grad4, pts4, out["weights"], motion, w_sum_global,
                              rgb_weight, eikonal_weight, sdf_weight)
 
 
@@ -187,14 +200,14 @@ def stage1_losses(out, rgb_gt, motion_network, sdf_network, query_time_step, ima
                 _, rel = motion_network.compute_relative_camera_pose(lo, hi, total_nb_images, nb_sample_timestep)
                 c2c_w = motion_network.compute_w2c_mappings(rel)[-1]
                 cw2 = rigid_inverse(c2c_w) if world_cam_idx <= image_idx else c2c_w
-            res["sdf_consistency_loss"] = sdf_consistency_loss(sdf_network, out["_pts4"][:, :3], out["sdf"], cw2,
+            res["sdf_consistency_loss"] = sdf_consistency_loss(sdf_network, packed_outputs(out)[1][:, :3], out["sdf"], cw2,
                                                                world_time_step)
         if use_flow_rgb:
             _, c2c = motion_network.compute_relative_camera_pose(image_idx, refs[nb_valid - 1], total_nb_images,
                                                                  nb_sample_timestep)
             sel = torch.as_tensor([r - image_idx for r in refs[:nb_valid]], device=dev)
             w2c = motion_network.compute_w2c_mappings(c2c)[sel]
-            wp = weighted_points(out["weights"], out["_pts4"])
+            wp = weighted_points(out["weights"], packed_outputs(out)[1])
             KS = projection_matrices(scale_mat, ref_camera_mats[:nb_valid])
             res["flow_rgb_loss"], res["flow_fw_pred"] = flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs[:nb_valid], rgb_gt,
                                                                       return_flow=True)

@@ -251,12 +251,21 @@ def _render_core_infer(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d
     return color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z, grad, pts
 
 
-class _LazyOutputs(dict):
+class RenderOutputs(dict):
+    """The reference's 15-key output dict (model/neus_renderer.py:567-584) plus, as ATTRIBUTES, the packed tensors the keys
+    are views of: grad4 [P,4] = (normals | sdf_flows), pts4 [P,4] = (sampled_points | t).  The loss / image-reduction kernels
+    read the packed form."""
+    grad4 = None
+    pts4 = None
+
+
+class _LazyOutputs(RenderOutputs):
     """Output dict of the fused training path: the per-key views / fills of `NeuSRenderer.forward` are only built when a
     key is read (logging), so the timed step launches none of them."""
 
     def __init__(self, n, color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, parts):
         super().__init__()
+        self.grad4, self.pts4 = grad4, pts4
         nrm = lambda: _unpack_views(grad4, pts4, n)
         self._make = {
             'sdf': lambda: sdf, 'color_fine': lambda: color, 'depth_pred': lambda: depth, 'weighted_z_vals': lambda: wz,
@@ -265,7 +274,7 @@ class _LazyOutputs(dict):
             'sampled_points': lambda: nrm()[2], 'weights': lambda: weights,
             'inside_sphere': lambda: torch.ones_like(weights), 'weight_inside': lambda: wsum.reshape(n),
             'weight_outside': lambda: torch.zeros(n, dtype=torch.float32, device=weights.device),
-            '_grad4': lambda: grad4, '_pts4': lambda: pts4, 'loss': lambda: parts[0], 'loss_rgb': lambda: parts[1],
+            'loss': lambda: parts[0], 'loss_rgb': lambda: parts[1],
             'loss_eikonal': lambda: parts[2], 'loss_sdf': lambda: parts[3],
         }
 
@@ -406,21 +415,17 @@ class NeuSRenderer(nn.Module):
         sdf_flat = self.sdf_network.flat_weights()
         col_flat = self.color_network.flat_weights()
         z, n_coarse = self.sample_z(rays_o, rays_d, time_step, near, far, eval, sdf_flat, it)
-        extra = {}
         if not torch.is_grad_enabled():
             # inference (torch.no_grad(): render_eval / render_visdata, model/training.py:210-283): nothing kept for backward
             (color, depth, normals, flows, weights, sdf, points, wz, cdf, wsum, wmax, inv_s, dists, mid_z, grad4, pts4) = \
                 _render_core_infer(self, sdf_flat.detach(), col_flat.detach(), self.deviation_network.variance.detach(), rays_o,
                                    rays_d, ray_d_norm, time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
-            extra = {'_grad4': grad4, '_pts4': pts4}      # packed (x,y,z,t) views for cope_eval_reduce
         else:
             (color, depth, grad4, weights, sdf, pts4, wz, cdf, wsum, wmax, inv_s, dists, mid_z) = \
                 _RenderCoreFn.apply(self, sdf_flat, col_flat, self.deviation_network.variance, rays_o, rays_d, ray_d_norm,
                                     time_step, z, near, far, n_coarse, cos_anneal_ratio, eval)
             normals, flows, points = _unpack_views(grad4, pts4, n)
-            extra = {'_grad4': grad4, '_pts4': pts4}      # the packed tensors behind normals / sdf_flows / sampled_points
-        return {
-            **extra,
+        out = RenderOutputs({
             'sdf': sdf,
             'color_fine': color,
             'depth_pred': depth,
@@ -436,4 +441,6 @@ class NeuSRenderer(nn.Module):
             'inside_sphere': torch.ones_like(weights),
             'weight_inside': wsum.reshape(n).detach(),
             'weight_outside': torch.zeros(n, dtype=torch.float32, device=weights.device),
-        }
+        })
+        out.grad4, out.pts4 = grad4, pts4
+        return out

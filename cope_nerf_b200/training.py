@@ -7,7 +7,7 @@ import torch
 
 from .common import get_world_cameraOrigin_cameraRay, pixels_from_indices
 
-__all__ = ["near_far_from_sphere", "get_cos_anneal_ratio", "get_patch_indices", "sample_rays", "eikonal_loss",
+__all__ = ["near_far_from_sphere", "get_cos_anneal_ratio", "get_patch_indices", "process_data", "sample_rays", "eikonal_loss",
            "rgb_l1_loss", "sdf_flow_loss", "neus_losses", "render_train_step", "build_networks", "DEFAULT_CFG"]
 
 # configs/default.yaml:103-156
@@ -57,6 +57,30 @@ def get_patch_indices(h, w, patch_size, n_points):
     off = torch.arange(patch_size).repeat(patch_size, 1)
     off = (off + off.t() * w).flatten()
     return ((rows * w + cols).unsqueeze(1) + off.view(-1)).flatten()
+
+
+def process_data(img, camera_mat, world_mat, scale_mat, n_points, patch_size=1, corners=None, seed=0):
+    """process_data (model/training.py:439-471) on the device, one launch for the pixel part: patch corners -> flat pixel
+    ids, integer + normalised pixel coordinates, target colours (cope_sample_pixels), then the rays (cope_raygen_fwd).
+    img [1,3,h,w] or [3,h,w] on the device.  `corners` = int64 top-left corner ids (e.g. the reference's CPU stream,
+    `torch.randperm((h-ps+1)*(w-ps+1))[:n_points // ps**2]`: identical pixels); None draws distinct corners on the device
+    from `seed` (no randperm over ~10^6 elements, no h*w pixel grid).
+    Returns (sampled_pixel [N,2], normalized_sampled_pixel [N,2], rays_o, rays_d, rays_d_norm, rgb_gt [N,3], ray_idx [N])."""
+    from . import _lib as L
+    img3 = img.reshape(3, img.shape[-2], img.shape[-1]).contiguous().float()
+    h, w = img3.shape[-2:]
+    dev = img3.device
+    n_patches = min(n_points // (patch_size ** 2), (h - patch_size + 1) * (w - patch_size + 1))
+    n = n_patches * patch_size ** 2
+    if corners is not None:
+        corners = corners[:n_patches].to(dev, torch.int64).contiguous()
+    ray_idx = torch.empty(n, dtype=torch.int64, device=dev)
+    pix, npix = torch.empty(n, 2, dtype=torch.float32, device=dev), torch.empty(n, 2, dtype=torch.float32, device=dev)
+    rgb_gt = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    L.call("cope_sample_pixels", L.ptr(corners), int(seed) & (2 ** 64 - 1), h, w, patch_size, n_patches, L.ptr(img3),
+           L.ptr(ray_idx), L.ptr(pix), L.ptr(npix), L.ptr(rgb_gt), L.stream())
+    o, d, dn = get_world_cameraOrigin_cameraRay(npix.unsqueeze(0), camera_mat, world_mat, scale_mat)
+    return pix, npix, o, d, dn, rgb_gt, ray_idx
 
 
 def sample_rays(ray_idx, h, w, camera_mat, world_mat, scale_mat):
@@ -143,7 +167,7 @@ def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, de
             near, far = near_far_from_sphere(o, d, depth_range)
             ro = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=True)
             S = ro['weights'].shape[1]
-            L.call("cope_eval_reduce", L.ptr(ro['weights']), L.ptr(ro['_grad4']), L.ptr(ro['_pts4']), L.ptr(wm), n, S,
+            L.call("cope_eval_reduce", L.ptr(ro['weights']), L.ptr(ro.grad4), L.ptr(ro.pts4), L.ptr(wm), n, S,
                    L.ptr(out['normal'][c0:c0 + n]), L.ptr(out['depth_highest_weight'][c0:c0 + n]), L.stream())
             out['rgb'][c0:c0 + n] = ro['color_fine']
             out['depth_pred'][c0:c0 + n] = ro['depth_pred']

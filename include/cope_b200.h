@@ -280,6 +280,15 @@ int cope_flow_rgb_bwd(const float* wp, const float* w2c, const float* KS, const 
                       const float* ref_imgs, const float* rgb_gt, int64_t N, int T, int H, int W, const float* ws, const float* g,
                       float* d_wp, float* d_w2c, cope_stream_t s);
 
+/* ---- training-pixel selection (process_data, model/training.py:413-471; arange_pixels, model/common.py:12-39) ----------
+ * n_patches patch_size x patch_size patches of an h x w frame -> N = n_patches * patch_size^2 rays, row-major inside each patch:
+ * ray_idx [N] int64 flat pixel ids, pix [N x 2] (col, row) as floats, norm_pix [N x 2] = 2 * (col, row) / (w-1, h-1) - 1,
+ * rgb_gt [N x 3] gathered from img [3 x h x w] (any output may be NULL).  corners [n_patches] int64 = top-left corner ids
+ * in the (h-ps+1) x (w-ps+1) grid (the reference's randperm prefix); corners == NULL draws distinct corners on the device from
+ * a keyed permutation of that grid (seed). */
+int cope_sample_pixels(const int64_t* corners, uint64_t seed, int h, int w, int patch_size, int n_patches, const float* img,
+                       int64_t* ray_idx, float* pix, float* norm_pix, float* rgb_gt, cope_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,14 @@ def _rand_out(n, s, seed, with_grad=True):
                 weights=mk(torch.softmax(torch.randn(n, s), dim=1) * 0.8), rgb_gt=torch.rand(n, 3))
 
 
+def _as_outputs(d):
+    """a RenderOutputs (15-key dict + packed attributes) from the test's tensors"""
+    from cope_nerf_b200.renderer import RenderOutputs
+    out = RenderOutputs({k: v for k, v in d.items() if not k.startswith("_")})
+    out.grad4, out.pts4 = d["_grad4"], d["_pts4"]
+    return out
+
+
 def _oracle_view(o):
     n = o["color_fine"].shape[0]
     return {"color_fine": o["color_fine"], "normals": o["_grad4"][:, :3].reshape(n, -1, 3),
@@ -46,7 +54,7 @@ def test_step_losses_vs_oracle(n, s, with_motion):
     l_flow = O.sdf_flow_loss(ov, mot_r[:3], mot_r[3:]) if with_motion else torch.zeros(())
     tot_r = w[0] * l_rgb + w[1] * l_eik + w[2] * l_flow
     (tot_r * 1.7).backward()
-    tot, parts = CL.step_losses(dev, dev["rgb_gt"], w[0], w[1], w[2], motion=mot_d)
+    tot, parts = CL.step_losses(_as_outputs(dev), dev["rgb_gt"], w[0], w[1], w[2], motion=mot_d)
     (tot * 1.7).backward()
     assert rel_err(tot, tot_r) < 1e-5 and rel_err(parts[0], tot_r) < 1e-5
     assert rel_err(parts[1], l_rgb) < 1e-5 and rel_err(parts[2], l_eik) < 1e-5
@@ -65,7 +73,7 @@ def test_step_losses_global_normaliser():
     dev = {k: v.to(DEV) for k, v in ref.items()}
     mot = torch.randn(6)
     wsum = torch.tensor([37.5], device=DEV)
-    _, parts = CL.step_losses(dev, dev["rgb_gt"], 0.0, 0.0, 1.0, motion=mot.to(DEV), w_sum_global=wsum)
+    _, parts = CL.step_losses(_as_outputs(dev), dev["rgb_gt"], 0.0, 0.0, 1.0, motion=mot.to(DEV), w_sum_global=wsum)
     local = O.sdf_flow_loss(_oracle_view(ref), mot[:3], mot[3:]) * (ref["weights"].sum() + 1e-10) / (37.5 + 1e-10)
     assert rel_err(parts[3], local) < 1e-5
 
@@ -122,9 +130,8 @@ def test_stage1_losses_golden():
     g, mot, sdf = _stage1_fixture()
     n, S = int(g["n"]), int(g["S"])
     lv = {k: cu(v).requires_grad_(True) for k, v in unflatten(g, "in.").items()}
-    grad4 = torch.cat([lv["normals"].reshape(-1, 3), lv["sdf_flows"].reshape(-1, 1)], dim=1)
-    pts4 = torch.cat([lv["pts"].reshape(-1, 3), torch.zeros(n * S, 1, device=DEV)], dim=1)
-    out = {"color_fine": torch.zeros(n, 3, device=DEV), "_grad4": grad4, "_pts4": pts4, "weights": lv["weights"], "sdf": lv["sdf"]}
+    out = {"color_fine": torch.zeros(n, 3, device=DEV), "normals": lv["normals"], "sdf_flows": lv["sdf_flows"],
+           "sampled_points": lv["pts"], "weights": lv["weights"], "sdf": lv["sdf"]}      # a plain reference-shaped dict
     res = CL.stage1_losses(out, cu(g["rgb_gt"]), mot, sdf, float(g["query_time_step"]), int(g["image_idx"]),
                            [int(v) for v in g["ref_idx"]], int(g["nb_valid"]), int(g["total_nb_images"]),
                            int(g["nb_sample_timestep"]), cu(g["Kr"]), cu(g["scale"]), cu(g["norm_pix"]), cu(g["pix"]), cu(g["refs"]),
@@ -230,3 +237,45 @@ def test_fused_step_with_sdf_flow_term(small_params):
         for k, p in net.named_parameters():
             assert rel_err(p.grad, Pg[tag][k].grad) < 1e-3, (tag, k)
     assert rel_err(pose.r.grad, po["r"].grad) < 2e-3 and rel_err(pose.t.grad, po["t"].grad) < 2e-3
+
+
+def test_process_data_on_device():
+    """cope_sample_pixels against the reference's process_data arithmetic (model/training.py:413-471): with the reference's
+    own CPU randperm prefix as corners the pixel ids / coordinates / colours are bit-exact; with device-drawn corners the
+    patches are distinct, in range and row-major."""
+    h, w, ps, n = 60, 80, 4, 256
+    torch.manual_seed(12)
+    img = torch.rand(1, 3, h, w)
+    K = O.camera_matrix(0.8 * w, 0.8 * w, w, h).unsqueeze(0)
+    torch.manual_seed(99)
+    idx_ref = O.patch_indices(h, w, ps, n)
+    torch.manual_seed(99)
+    corners = torch.randperm((h - ps + 1) * (w - ps + 1))[:n // ps ** 2]
+    loc, sc = O.pixel_grid(h, w)
+    world = torch.eye(4, device=DEV)
+    pix, npix, o, d, dn, rgb, idx = C.training.process_data(cu(img), cu(K), world, torch.eye(4, device=DEV).unsqueeze(0), n, ps,
+                                                          corners=corners)
+    assert torch.equal(idx.cpu(), idx_ref)
+    assert torch.equal(npix.cpu(), sc[0, idx_ref]) and torch.equal(pix.cpu(), loc[0, idx_ref].float())
+    assert torch.equal(rgb.cpu(), img.view(3, h * w).t()[idx_ref])
+    ro, rd, rn = O.ray_generation(sc[:, idx_ref], K, torch.eye(4), torch.eye(4).unsqueeze(0))
+    assert_close(d, rd, 1e-5); assert_close(o, ro, 1e-6)
+    for hh, ww, pp, nn in ((717, 1275, 4, 1024), (9, 7, 3, 45), (5, 5, 1, 25), (4, 4, 4, 16)):
+        im = torch.rand(3, hh, ww, device=DEV)
+        seen = set()
+        for seed in (0, 1, 12345678901234):
+            pix, npix, *_, rgb, idx = C.training.process_data(im, cu(O.camera_matrix(ww, ww, ww, hh).unsqueeze(0)), world,
+                                                              torch.eye(4, device=DEV).unsqueeze(0), nn, pp, seed=seed)
+            k = idx.shape[0] // pp ** 2
+            assert k == min(nn // pp ** 2, (hh - pp + 1) * (ww - pp + 1))
+            pt = idx.view(k, pp, pp).cpu()
+            corner = pt[:, 0, 0]
+            assert corner.unique().numel() == k, "corners must be distinct"
+            r0, c0 = corner // ww, corner % ww
+            assert (r0 <= hh - pp).all() and (c0 <= ww - pp).all()
+            off = torch.arange(pp).view(1, pp, 1) * ww + torch.arange(pp).view(1, 1, pp)
+            assert torch.equal(pt, corner.view(-1, 1, 1) + off)
+            assert torch.equal(rgb, im.view(3, -1).t()[idx])
+            seen.add(tuple(corner.tolist()))
+        if (hh - pp + 1) * (ww - pp + 1) > 1 and k < (hh - pp + 1) * (ww - pp + 1):
+            assert len(seen) > 1, "different seeds must give different patches"
