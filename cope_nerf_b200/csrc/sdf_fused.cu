@@ -35,6 +35,9 @@ template <int MODE> struct Cfg;
 template <> struct Cfg<FZ_FWD> { static constexpr int kW = 3, kAux = 2, kStg = 1, kBias = (COPE_MAX_LIN * 256 + 64) * 4; };
 template <> struct Cfg<FZ_TAN> { static constexpr int kW = 2, kAux = 5, kStg = 1, kBias = 0; };
 template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 2, kAux = 6, kStg = 0, kBias = 0; };
+// value-path adjoint (no zb2 tiles to stream): latency-bound on the weight ring, so the freed auxiliary slots go to it
+template <> struct Cfg<FZ_ADJ1> { static constexpr int kW = 3, kAux = 3, kStg = 0, kBias = 0; };
+constexpr bool is_adj(int mode) { return mode == FZ_ADJ || mode == FZ_ADJ1; }
 template <int MODE> using Lay = ChainLay<4, Cfg<MODE>::kW, Cfg<MODE>::kAux, Cfg<MODE>::kStg, Cfg<MODE>::kBias>;
 
 constexpr float kC2 = -kSoftplusBeta * 1.4426950408889634f;   // exp(-100 h) = 2^(kC2 h)
@@ -161,10 +164,10 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
           st(400 + jb);
         }
         // the last A-write of the tile has no MMA consumer: keep the panel parities in step
-        if (MODE == FZ_TAN || (MODE == FZ_ADJ && !a.want_e)) {
+        if (MODE == FZ_TAN || (is_adj(MODE) && !a.want_e)) {
           for (int j = 0; j < 4; ++j) { mbar_wait_park(B.a_ready + j, (aph >> j) & 1); aph ^= 1u << j; }
         }
-        if (MODE == FZ_ADJ) umma_commit(B.tile_done);
+        if (is_adj(MODE)) umma_commit(B.tile_done);
       }
     }
   } else if (warp == kStore) {
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
       const bool ok = m < a.P;
       const int64_t mm = ok ? m : 0;
       float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f}, gv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (MODE != FZ_ADJ && ok) {
+      if (!is_adj(MODE) && ok) {
         const float4 t = *reinterpret_cast<const float4*>(a.x + mm * 4);
         xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
         if (MODE == FZ_TAN) {
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
         }
       }
 
-      if (MODE == FZ_ADJ) {
+      if (is_adj(MODE)) {
         const float dsdf = (ok && a.d_sdf) ? a.d_sdf[m * a.d_sdf_ld] : 0.0f;
         for (int l = top; l >= 1; --l) {
           const int s = top - l;
@@ -603,7 +606,7 @@ int launch_sdf_fused(int mode, const FzArgs& a, const FzMaps& maps, cudaStream_t
   switch (mode) {
     case FZ_FWD: rc = launch_t<FZ_FWD>(b, maps, s); break;
     case FZ_TAN: rc = launch_t<FZ_TAN>(b, maps, s); break;
-    case FZ_ADJ: rc = launch_t<FZ_ADJ>(b, maps, s); break;
+    case FZ_ADJ: rc = b.has_d ? launch_t<FZ_ADJ>(b, maps, s) : launch_t<FZ_ADJ1>(b, maps, s); break;
     default: COPE_REQUIRE(false, "sdf_fused: unknown mode %d", mode);
   }
   if (timeline && rc == 0) {

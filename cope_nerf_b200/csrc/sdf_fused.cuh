@@ -12,6 +12,7 @@ enum FzMode : int {
   FZ_FWD = 0,   // PE -> value pass (stores H_1..H_top) -> sdf / feature -> reverse sweep (stores delta_l) -> ge0 / ge1
   FZ_TAN = 1,   // tangent pass of the double backward: T_{l+1}, zb2_l
   FZ_ADJ = 2,   // adjoint pass: zb_l (optionally with the second-order term zb2_l), eb0 / eb1
+  FZ_ADJ1 = 3,  // the same pass launched without zb2 (has_d == 0): picked by launch_sdf_fused, deeper weight ring
 };
 
 constexpr int kFzMaxJobs = 20;
