@@ -9,6 +9,8 @@
 //   * tcgen05.mma M128 x N256 x K16 into two alternating TMEM accumulators; the MMA of layer l+1 starts on K-panel j
 //     as soon as the epilogue of layer l has written panel j (per-panel mbarriers), so tensor pipe and epilogue overlap
 //   * the skip layer's [h | PE]/sqrt2 input takes its PE part from a shared-memory stash written with layer 0's input
+#include <stdlib.h>
+
 #include "mlp_shape.cuh"
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
@@ -30,6 +32,7 @@ struct ChainArgs {
   uint32_t w_off[COPE_MAX_LIN];      // element offset of the packed forward weights of layer l (top: 16-row sdf block)
   int Np[COPE_MAX_LIN], Kp[COPE_MAX_LIN], n_out[COPE_MAX_LIN];
   int64_t b_off[COPE_MAX_LIN];
+  long long* dbg;                    // optional clock64 timeline of CTA 0 (COPE_Q2_TIMELINE=<file>; profiling only)
 };
 
 __device__ __forceinline__ float ch_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -250,6 +253,241 @@ __global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query_kernel(const __
   if (warp == kChMma) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two tiles in flight per CTA (launches with more tiles than SMs).  In the kernel above the tensor pipe idles while the 16
+// epilogue warps work through a layer (4 panels x ~1.1 k cycles against 2 k cycles of MMAs, plus the serial hand-over at
+// both ends).  Here every CTA owns TWO 128-row tiles with one 256-column TMEM accumulator each: the epilogue warps
+// alternate between the tiles, and while they are busy with tile A's layer the MMAs of tile B's layer run, so the step is
+// paced by the epilogue alone.  Job order of every role: (A, l), (B, l), (A, l+1), ...  The PE stash of the skip layer is
+// recomputed from x instead of kept in shared memory (2 x 64 KB of activation panels + the weight ring fill it).
+struct Q2Stamp {     // region `role` of the timeline buffer holds (tag << 48 | clock) entries, entry 0 = count
+  long long* p; int n;
+  __device__ __forceinline__ void init(long long* base, int role) { p = (base && blockIdx.x == 0) ? base + role * 4096 : nullptr; n = 1; }
+  __device__ __forceinline__ void operator()(int tag) {
+    if (p && n < 4096) { p[n++] = ((long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFll); p[0] = n; }
+  }
+};
+constexpr int kQ2WRing = 3;   // 2 x 64 KB activation panels + 3 x 32 KB weight chunks: biases are read from global memory
+
+__global__ void __launch_bounds__(kChThreads, 1) sdf_chain_query2_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                   // 2 tiles x 4 panels, 128 KB
+  uint8_t* sW = smem + 8 * kPanelBytes;                 // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kQ2WRing * kWChunkBytes);
+  uint64_t* w_full = bars;                  // [kQ2WRing]
+  uint64_t* w_empty = bars + kQ2WRing;      // [kQ2WRing]
+  uint64_t* in_ready = bars + 2 * kQ2WRing; // [2] tile slot t: the whole input tile of its next layer is written
+  uint64_t* acc_full = in_ready + 2;        // [2] tile slot t: its accumulator holds the layer's result
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kQ2WRing; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(in_ready + t, kChEpiWarps); mbar_init(acc_full + t, 1); }
+    fence_barrier_init();
+  }
+  if (warp == kChMma) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntiles = (int)((a.P + 127) / 128);
+  const int top = a.n_lin - 1;
+  const int G = gridDim.x;
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + G - 1) / G : 0;
+
+  if (warp == kChProd) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; i += 2) {
+        const int nt = min(2, my_tiles - i);
+        for (int l = 0; l <= top; ++l) {
+          const int nkc = a.Kp[l] >> 6;
+          const uint32_t cbytes = (uint32_t)a.Np[l] * 128;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + a.w_off[l]);
+          for (int t = 0; t < nt; ++t)
+            for (int c = 0; c < nkc; ++c) {
+              ch_wait_park(w_empty + stage, phase ^ 1);
+              mbar_arrive_expect_tx(w_full + stage, cbytes);
+              bulk_g2s(sW + stage * kWChunkBytes, src + (size_t)c * cbytes, cbytes, w_full + stage);
+              if (++stage == kQ2WRing) { stage = 0; phase ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == kChMma) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, inph = 0;     // inph: bit t = parity to wait for on in_ready[t]
+      Q2Stamp st; st.init(a.dbg, 0);
+      for (int i = 0; i < my_tiles; i += 2) {
+        const int nt = min(2, my_tiles - i);
+        for (int l = 0; l <= top; ++l) {
+          const int nkc = a.Kp[l] >> 6;
+          const uint32_t idesc = idesc_bf16(128, a.Np[l], 0, 0);
+          const uint32_t b_lbo = (uint32_t)a.Np[l] * 16;
+          const uint64_t bdesc0 = smem_desc(smem_u32(sW), b_lbo, 128);
+          const uint32_t b_kstep = (2 * b_lbo) >> 4;
+          for (int t = 0; t < nt; ++t) {
+            const uint32_t d_tmem = tmem_base + t * 256;
+            const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA + t * 4 * kPanelBytes), 16, 1024);
+            mbar_wait(in_ready + t, (inph >> t) & 1);
+            inph ^= 1u << t;
+            st(1000 + l * 10 + t);
+            for (int c = 0; c < nkc; ++c) {
+              mbar_wait(w_full + stage, phase);
+              tc_fence_after();
+              const uint64_t ad = adesc0 + (uint64_t)(c * (kPanelBytes >> 4));
+              const uint64_t bd = bdesc0 + (uint64_t)(stage * (kWChunkBytes >> 4));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_bf16(d_tmem, ad + ks * 2, bd + ks * b_kstep, idesc, (c | ks) != 0);
+              umma_commit(w_empty + stage);
+              if (++stage == kQ2WRing) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full + t);
+            st(2000 + l * 10 + t);
+          }
+        }
+      }
+    }
+  } else if (warp < kChEpiWarps) {
+    // ------------------------------------------------------------------ PE + epilogue warps
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;
+    uint32_t accp = 0;
+    Q2Stamp st; st.init((warp == 0 && lane == 0) ? a.dbg : nullptr, 1);
+    for (int i = 0; i < my_tiles; i += 2) {
+      const int nt = min(2, my_tiles - i);
+      float xv[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};   // this row's input point (d_in <= 4), per tile slot
+      int64_t mrow[2] = {0, 0};
+      // ---- layer-0 input of both tiles: [x_hi | sin/cos | x_lo | 0] into panel 0
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t >= nt) break;
+        const int tile = blockIdx.x + (i + t) * G;
+        const int64_t m = (int64_t)tile * 128 + r;
+        mrow[t] = m;
+        const bool ok = m < a.P;
+        bf16* row0 = reinterpret_cast<bf16*>(sA + t * 4 * kPanelBytes);
+        auto put = [&](int k, float v) { row0[(a_off(r, k & ~7) >> 1) + (k & 7)] = __float2bfloat16(v); };
+        if (part == 0)
+          for (int k = a.pe_w + a.d_in; k < 64; ++k) put(k, 0.0f);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) xv[t][dd] = (ok && dd < a.d_in) ? a.x[m * a.d_in + dd] : 0.0f;
+        for (int dd = part; dd < a.d_in; dd += 4) {       // d_in <= 4: at most one iteration, dd == part
+          const float v = part == 0 ? xv[t][0] : part == 1 ? xv[t][1] : part == 2 ? xv[t][2] : xv[t][3];
+          put(dd, v);
+          put(a.pe_w + dd, v - __bfloat162float(__float2bfloat16(v)));
+          float sn, cs;
+          sincosf(v, &sn, &cs);
+          for (int k = 0; k < a.L; ++k) {
+            put(a.d_in * (1 + 2 * k) + dd, sn); put(a.d_in * (2 + 2 * k) + dd, cs);
+            const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;
+            sn = s2; cs = c2;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_ready + t);
+      }
+      // ---- layers, alternating between the two tiles
+      for (int l = 0; l <= top; ++l) {
+        const float* bias = a.Wflat + a.b_off[l];        // global (L2-resident): only columns < n_out are read
+        const bool to_skip = (l + 1 == a.skip);
+        const float alpha = to_skip ? kInvSqrt2 : 1.0f;
+        const int n_out = a.n_out[l];
+        const int npan = l < top ? (a.Kp[l + 1] >> 6) : 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t >= nt) break;
+          mbar_wait(acc_full + t, (accp >> t) & 1);
+          accp ^= 1u << t;
+          tc_fence_after();
+          st(3000 + l * 10 + t);
+          const uint32_t taddr = tmem_base + t * 256 + ((uint32_t)(q * 32) << 16);
+          uint8_t* sAt = sA + t * 4 * kPanelBytes;
+          if (l == top) {
+            if (part == 0) {
+              float v[16];
+              tmem_ld16(taddr, v);
+              if (mrow[t] < a.P) a.sdf_out[mrow[t]] = v[0] + __ldg(bias);
+            }
+            tc_fence_before();
+            continue;
+          }
+          if (to_skip) {
+            // PE part of the skip concat [h | PE] / sqrt2: this thread's input dimension (d_in == 4 == slabs per panel), same
+            // angle doubling as the layer-0 input; the raw coordinates at its head belong to the straddling slab below
+            const float xd = part == 0 ? xv[t][0] : part == 1 ? xv[t][1] : part == 2 ? xv[t][2] : xv[t][3];
+            bf16* rowp = reinterpret_cast<bf16*>(sAt);
+            auto put = [&](int kk, float val) { rowp[(a_off(r, kk & ~7) >> 1) + (kk & 7)] = __float2bfloat16(val); };
+            float sn, cs;
+            sincosf(xd, &sn, &cs);
+            for (int f = 0; f < a.L; ++f) {
+              put(n_out + a.d_in * (1 + 2 * f) + part, sn * kInvSqrt2);
+              put(n_out + a.d_in * (2 + 2 * f) + part, cs * kInvSqrt2);
+              const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;
+              sn = s2; cs = c2;
+            }
+            if (part == 0)
+              for (int kk = n_out + a.pe_w; kk < npan * 64; ++kk) put(kk, 0.0f);
+          }
+          for (int j = 0; j < npan; ++j) {
+            const int n0 = j * 64 + part * 16;
+            if (n0 >= n_out) {                          // skip layer: PE columns, written above
+              st(5000 + l * 10 + j);
+              continue;
+            }
+            const bool full = n0 + 16 <= n_out;
+            // issued ahead of the TMEM load: the L2 latency hides behind it.  In the straddling slab the loads run past the
+            // layer's last bias into the next layer's weights (same flat buffer): those columns are overwritten below
+            float bz[16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(bz + 4 * k) = __ldg(reinterpret_cast<const float4*>(bias + n0) + k);
+            float v[16];
+            tmem_ld16(taddr + n0, v);
+            if (to_skip) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] = kInvSqrt2 * ch_softplus(v[k] + bz[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] = ch_softplus(v[k] + bz[k]);
+            }
+            if (!full) {
+              // the slab that straddles the end of the real outputs (launch condition: it ends with the d_in raw coordinates
+              // that head the PE): [.. softplus .. | x, y, z, t] / sqrt2
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int e = n0 + k - n_out;
+                const float xs = e == 0 ? xv[t][0] : e == 1 ? xv[t][1] : e == 2 ? xv[t][2] : xv[t][3];
+                if (e >= 0) v[k] = (to_skip && e < a.d_in) ? xs * kInvSqrt2 : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8)
+              *reinterpret_cast<uint4*>(sAt + a_off(r, n0 + g8 * 8)) =
+                  make_uint4(pack_bf16(v[g8 * 8], v[g8 * 8 + 1]), pack_bf16(v[g8 * 8 + 2], v[g8 * 8 + 3]),
+                             pack_bf16(v[g8 * 8 + 4], v[g8 * 8 + 5]), pack_bf16(v[g8 * 8 + 6], v[g8 * 8 + 7]));
+            st(5000 + l * 10 + j);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(in_ready + t);
+          st(4000 + l * 10 + t);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kChMma) tmem_dealloc(tmem_base, 512);
+}
+
 // host side: eligible when every hidden width is 256 (the reference architecture); otherwise the caller falls back to
 // the layer-by-layer path
 bool sdf_chain_supported(const MlpShape& m) {
@@ -281,6 +519,38 @@ int launch_sdf_chain_query(const MlpShape& m, const float* Wflat, const bf16* wp
     attr_set = true;
   }
   const int ntiles = (int)((P + 127) / 128);
+  // more tiles than SMs: two tiles in flight per CTA (COPE_CHAIN_PAIR=0 keeps the one-tile kernel for A/B measurements)
+  static const bool pair_ok = !(getenv("COPE_CHAIN_PAIR") && atoi(getenv("COPE_CHAIN_PAIR")) == 0);
+  bool bias_aligned = true;
+  for (int l = 0; l + 1 < m.n_lin; ++l) bias_aligned = bias_aligned && (m.b_off[l] % 4 == 0) && ((uintptr_t)Wflat % 16 == 0);
+  // ... and the slab that straddles the skip layer's real outputs must end with the d_in raw coordinates of the PE
+  const int skw2 = m.skip > 0 ? m.in[m.skip] - m.pe_w : 0;
+  const bool skip_ok = m.skip > 1 && m.d_in == 4 && (skw2 + m.d_in) % 16 == 0 && skw2 + m.pe_w == 256;
+  if (ntiles > 148 && pair_ok && skip_ok && bias_aligned) {
+    static bool attr2_set = false;
+    const size_t smem2 = 8 * kPanelBytes + kQ2WRing * kWChunkBytes + 256;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(sdf_chain_query2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      COPE_REQUIRE(e == cudaSuccess, "sdf_chain: cannot raise dynamic shared memory to %zu: %s", smem2, cudaGetErrorString(e));
+      attr2_set = true;
+    }
+    static long long* tl = nullptr;
+    const char* tl_file = getenv("COPE_Q2_TIMELINE");
+    if (tl_file) {
+      if (!tl) cudaMalloc(&tl, 2 * 4096 * sizeof(long long));
+      cudaMemsetAsync(tl, 0, 2 * 4096 * sizeof(long long), s);
+      a.dbg = tl;
+    }
+    sdf_chain_query2_kernel<<<148, kChThreads, smem2, s>>>(a);
+    COPE_CHECK_LAUNCH("sdf_chain_query2");
+    if (tl_file) {      // profiling aid: the only place this path synchronises
+      static long long host[2 * 4096];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(tl_file, "wb")) { fwrite(host, 1, sizeof(host), f); fclose(f); }
+    }
+    return 0;
+  }
   sdf_chain_query_kernel<<<std::min(ntiles, 148), kChThreads, smem, s>>>(a);
   COPE_CHECK_LAUNCH("sdf_chain_query");
   return 0;

@@ -124,7 +124,8 @@ def test_fused_query_chain_matches_layered_path(monkeypatch):
     P = full_params(perturb=0.02)
     r = bf16_renderer(P, C.training.DEFAULT_CFG)
     torch.manual_seed(9)
-    for n in (1, 100, 128, 5000, 16384 + 77):
+    # > 148 tiles of 128 points: the two-tiles-in-flight kernel (one CTA with a pair, pairs + singles, 3-4 tiles per CTA)
+    for n in (1, 100, 128, 5000, 16384 + 77, 148 * 128 + 1, 40000, 65536 + 5):
         x = torch.cat([torch.randn(n, 3) * 0.7, torch.full((n, 1), 0.3)], -1)
         flat = r.sdf_network.flat_weights().detach()
         fused = r.sdf_network.query_flat(flat, cu(x))
