@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
       else sBias[i] = n < (l + 1 == a.skip ? a.skw : 256) ? a.Wflat[a.b_off[l] + n] : 0.0f;
     }
     if (threadIdx.x == 0) sBias[a.n_lin * 256] = a.Wflat[a.b_off[a.n_lin - 1]];   // sdf bias (row 0)
+    if (a.n_lin + 2 <= COPE_MAX_LIN)      // row 0 of the last layer (d sdf / d H_top), read by the top of the reverse sweep
+      for (int i = threadIdx.x; i < 256; i += kThreads) sBias[(a.n_lin + 1) * 256 + i] = a.Wflat[a.w_top_off + i];
   }
   if (warp == kMma) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -395,13 +397,14 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
         E.begin_event();
         {
           const float hc = kC2 * (top == a.skip ? 1.41421356237309505f : 1.0f);
+          const float* w0s = (a.n_lin + 2 <= COPE_MAX_LIN) ? sBias + (a.n_lin + 1) * 256 : w0;   // shared-memory copy
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             const int n0 = j * 64 + part * 16;
             const Pk16 hp = read16(sA + j * kPanel, r, part);
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __ldg(w0 + n0 + i) * (1.0f - ex2(pk_get(hp, i) * hc));
+            for (int i = 0; i < 16; ++i) v[i] = w0s[n0 + i] * (1.0f - ex2(pk_get(hp, i) * hc));
             write16(sA + j * kPanel, r, part, v);
             E.panel_done(j);
           }
