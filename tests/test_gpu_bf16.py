@@ -6,6 +6,7 @@ import torch
 
 import cope_nerf_b200 as C
 import oracle as O
+from cope_nerf_b200 import _lib as L
 from conftest import assert_close, cos_sim, load_golden, rel_err
 from test_gpu_parity import DEV, SMALL_CFG, cu, full_params, renderer_from, _run_step
 
@@ -273,3 +274,48 @@ def test_bf16_eval_image_render_full_size():
     near, far = C.training.near_far_from_sphere(o, d, (0.01, 5.0))
     out = r16(o, d, dn, t0, near, far, cos_anneal_ratio=1.0, it=1, eval=True)
     assert_close(a["rgb"], out["color_fine"].detach(), 2e-3, "rgb infer vs autograd forward")
+
+
+def _render_mlp_fwd_bwd(r, x, dirs, S, seed):
+    """cope_render_mlp_fwd + cope_render_mlp_bwd through the C ABI on P points; returns outputs and parameter gradients."""
+    sn, cn = r.sdf_network, r.color_network
+    P = x.shape[0]
+    f = lambda *s: torch.empty(*s, device=DEV)
+    flat, cflat = sn.flat_weights().detach(), cn.flat_weights().detach()
+    o_sdf, o_grad, o_rgb = f(P, 1), f(P, 4), f(P, 3)
+    sdf_saved = f(L.query("cope_sdf_saved_floats", sn.desc, P, 1, C.PREC_BF16))
+    col_saved = f(L.query("cope_color_saved_floats", cn.desc, P, C.PREC_BF16))
+    ws = f(L.query("cope_render_mlp_ws_floats", sn.desc, cn.desc, P, C.PREC_BF16))
+    st = L.stream()
+    L.call("cope_render_mlp_fwd", sn.desc, flat, cn.desc, cflat, x, dirs, S, cn.multires_view, P, o_sdf, o_grad, o_rgb, sdf_saved,
+           col_saved, ws, C.PREC_BF16, st)
+    torch.manual_seed(seed)
+    g_sdf, g_grad, g_rgb = (torch.randn(P, 1, device=DEV) * 1e-3, torch.randn(P, 4, device=DEV) * 1e-3,
+                            torch.randn(P, 3, device=DEV) * 1e-3)
+    dWs, dWc, dx, dd = torch.zeros_like(flat), torch.zeros_like(cflat), torch.zeros(P, 4, device=DEV), f(P, 3)
+    L.call("cope_render_mlp_bwd", sn.desc, flat, cn.desc, cflat, x, dirs, S, cn.multires_view, P, sdf_saved, col_saved, g_sdf, g_grad,
+           g_rgb, dWs, dWc, dx, dd, ws, C.PREC_BF16, st)
+    torch.cuda.synchronize()
+    return dict(sdf=o_sdf, grad=o_grad, rgb=o_rgb, dWs=dWs, dWc=dWc, dx=dx)
+
+
+def test_fwd_pair_kernel_matches_one_tile_kernel(monkeypatch):
+    """sdf_fwd_pair_kernel (two tiles in flight per CTA; launches with more than 148 tiles) against sdf_fused_kernel<FWD>: same
+    sdf / gradient / colour, and - through the saved H and delta stacks - the same parameter gradients from the backward."""
+    P0 = full_params(perturb=0.02)
+    r = bf16_renderer(P0, C.training.DEFAULT_CFG)
+    for n_rays in (149, 300, 1024):          # 149 tiles (one CTA with a pair), pairs + singles, 6-7 tiles per CTA
+        S = 128
+        torch.manual_seed(n_rays)
+        x = torch.cat([torch.randn(n_rays * S, 3, device=DEV) * 0.6, torch.full((n_rays * S, 1), 0.2, device=DEV)], -1)
+        dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
+        monkeypatch.setenv("COPE_FWD_PAIR", "0")
+        one = _render_mlp_fwd_bwd(r, x, dirs, S, 5)
+        monkeypatch.setenv("COPE_FWD_PAIR", "1")
+        two = _render_mlp_fwd_bwd(r, x, dirs, S, 5)
+        monkeypatch.delenv("COPE_FWD_PAIR")
+        for k in ("sdf", "grad", "rgb"):
+            assert torch.isfinite(two[k]).all()
+            assert rel_err(two[k], one[k]) < 2e-3, (n_rays, k, rel_err(two[k], one[k]))
+        for k in ("dWs", "dWc", "dx"):
+            assert cos_sim(two[k], one[k]) > 0.9999 and rel_err(two[k], one[k]) < 1e-2, (n_rays, k, rel_err(two[k], one[k]))
