@@ -26,19 +26,25 @@ template <> struct CCfg<CZ_FWD> { static constexpr int kP = 5, kW = 3, kAux = 0,
 template <> struct CCfg<CZ_BWD> { static constexpr int kP = 4, kW = 3, kAux = 4, kStg = 0, kBias = 0; };
 template <int MODE> using CLay = ChainLay<CCfg<MODE>::kP, CCfg<MODE>::kW, CCfg<MODE>::kAux, CCfg<MODE>::kStg, CCfg<MODE>::kBias>;
 
-// element e of the 64-column input tail: [x_hi(4) | d, sin/cos(2^k d) (3 + 6 Lv) | normals(4) | x_lo(4) | 0]
+// element e of the 64-column input tail: [x_hi(4) | d, sin/cos(2^k d) (3 + 6 Lv) | normals(4) | x_lo(4) | 0].
+// Select-by-compare instead of x[e] / d[q] / nrm[..]: a run-time index puts the arrays in local memory, and with the shared-memory
+// carve-out at its maximum there is no L1 behind it.  sin / cos through the MUFU (|2^k d| <= 2^(Lv-1): abs. error ~1e-6, against
+// the 4e-3 of the bf16 rounding that follows): the library sinf + cosf made this the longest serial step of a tile, 16 elements x
+// ~160 instructions per thread before the first MMA can start.
+__device__ __forceinline__ float csel3(const float (&v)[3], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : v[2]; }
+__device__ __forceinline__ float csel4(const float (&v)[4], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; }
 __device__ __forceinline__ float tail_elem(const float (&x)[4], const float (&d)[3], const float (&nrm)[4], int Lv, int e) {
   const int pe_w = 3 * (1 + 2 * Lv);
-  if (e < 4) return __bfloat162float(__float2bfloat16(x[e]));
+  if (e < 4) return __bfloat162float(__float2bfloat16(csel4(x, e)));
   if (e < 4 + pe_w) {
     const int q = e - 4;
-    if (q < 3) return d[q];
+    if (q < 3) return csel3(d, q);
     const int blk = (q - 3) / 3, dd = (q - 3) - blk * 3;
-    const float ang = d[dd] * (float)(1 << (blk >> 1));
-    return (blk & 1) ? cosf(ang) : sinf(ang);
+    const float ang = csel3(d, dd) * (float)(1 << (blk >> 1));
+    return (blk & 1) ? __cosf(ang) : __sinf(ang);
   }
-  if (e < 8 + pe_w) return nrm[e - 4 - pe_w];
-  if (e < 12 + pe_w) { const float xv = x[e - 8 - pe_w]; return xv - __bfloat162float(__float2bfloat16(xv)); }
+  if (e < 8 + pe_w) return csel4(nrm, e - 4 - pe_w);
+  if (e < 12 + pe_w) { const float xv = csel4(x, e - 8 - pe_w); return xv - __bfloat162float(__float2bfloat16(xv)); }
   return 0.0f;
 }
 
@@ -250,10 +256,13 @@ __global__ void __launch_bounds__(kThreads, 1) color_fused_kernel(const __grid_c
             float v[16];
             tmem_ld16(taddr, v);
             if (ok) {
-              for (int k = 0; k < a.d_out; ++k) {
-                const float o = __fdividef(1.0f, 1.0f + ex2((v[k] + sBias[top * 256 + k]) * -1.4426950408889634f));
-                a.rgb[m * a.d_out + k] = o;
-                if (a.rgb_saved) a.rgb_saved[m * a.d_out + k] = o;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {              // unrolled with a guard: v[] stays in registers
+                if (k < a.d_out) {
+                  const float o = __fdividef(1.0f, 1.0f + ex2((v[k] + sBias[top * 256 + k]) * -1.4426950408889634f));
+                  a.rgb[m * a.d_out + k] = o;
+                  if (a.rgb_saved) a.rgb_saved[m * a.d_out + k] = o;
+                }
               }
             }
           }
@@ -269,11 +278,15 @@ __global__ void __launch_bounds__(kThreads, 1) color_fused_kernel(const __grid_c
           for (int i = 0; i < 16; ++i) v[i] = 0.0f;
           E.begin_event();
           write16(sA + kPanel, r, part, v);
-          if (part == 0 && ok)
-            for (int k = 0; k < a.d_out; ++k) {
-              const float o = a.rgb_in[m * a.d_out + k];
-              v[k] = a.d_rgb[m * a.d_out + k] * o * (1.0f - o);
+          if (part == 0 && ok) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {                // unrolled with a guard: v[] stays in registers
+              if (k < a.d_out) {
+                const float o = a.rgb_in[m * a.d_out + k];
+                v[k] = a.d_rgb[m * a.d_out + k] * o * (1.0f - o);
+              }
             }
+          }
           write16(sA, r, part, v);
           E.panel_done(0);
           E.panel_done(1);

@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
           gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
         }
       }
-      const float xd = xv[part], gd = gv[part];    // this thread's input dimension (d_in == 4 == slabs per panel)
+      // this thread's input dimension (d_in == 4 == slabs per panel).  Select-by-compare, not xv[part]: a run-time index puts
+      // the array in local memory, and with the shared-memory carve-out at its maximum there is no L1 behind it
+      auto sel4 = [](const float (&v)[4], int i) { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; };
+      const float xd = sel4(xv, part), gd = sel4(gv, part);
 
       if (MODE == FZ_FWD || MODE == FZ_TAN) {
         // ---------------- layer-0 input into panel 0: [x_hi | sin / cos | x_lo | 0]  (TAN: [J_PE g | 0])
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
                     val = alpha * v[i] * fmaf(e100, -0.01f, 1.0f);
                   }
                 } else if (n - n_out < a.d_in) {
-                  val = (MODE == FZ_TAN ? gv[n - n_out] : xv[n - n_out]) * kInvSqrt2;
+                  val = (MODE == FZ_TAN ? sel4(gv, n - n_out) : sel4(xv, n - n_out)) * kInvSqrt2;
                 }
                 v[i] = val;
                 if (MODE == FZ_TAN) z2[MODE == FZ_TAN ? i : 0] = zz;
