@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcope_b200.so")
 MAX_LIN = 12
 PREC_FP32, PREC_BF16 = 0, 1
+WS_HOLDS_PACK = 0x100      # cope_sdf_query: the scratch head still holds this network's packed weights
 ACT_SOFTPLUS100, ACT_LEAKY_RELU = 0, 1
 
 _f = C.c_void_p      # device pointers travel as integers

@@ -403,14 +403,16 @@ static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, c
   return launch_sdf_fused(FZ_FWD, a, maps, s);
 }
 
-int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s) {
+int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s,
+                   bool ws_holds_pack) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   if (P <= 0) return 0;
   bf16* wp = reinterpret_cast<bf16*>(ws);
   bf16* pe = wp + b.w_total;
   bf16* bufs[3] = {pe + P * 64, pe + P * 64 + P * b.LD, pe + P * 64 + 2 * P * b.LD};
-  if (int rc = pack_sdf(m, b, Wflat, wp, true, false, s)) return rc;
+  if (!ws_holds_pack)      // the caller vouches that an earlier query on this stream left the same weights' pack at the head of ws
+    if (int rc = pack_sdf(m, b, Wflat, wp, true, false, s)) return rc;
   if (sdf_chain_supported(m) && !getenv("COPE_NO_CHAIN")) {
     uint32_t offs[COPE_MAX_LIN];
     for (int l = 0; l < m.n_lin; ++l) offs[l] = (uint32_t)b.wf_off[l];

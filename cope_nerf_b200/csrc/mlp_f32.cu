@@ -211,7 +211,8 @@ int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, i
                    int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  if (prec == COPE_PREC_BF16) return sdf_query_bf16(m, Wflat, x, P, sdf_out, ws, as_stream(s_));
+  if ((prec & ~COPE_WS_HOLDS_PACK) == COPE_PREC_BF16)
+    return sdf_query_bf16(m, Wflat, x, P, sdf_out, ws, as_stream(s_), (prec & COPE_WS_HOLDS_PACK) != 0);
   COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_query: unknown precision %d", prec);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);

@@ -46,7 +46,8 @@ inline int make_shape(const cope_mlp_desc* d, MlpShape* s) {
 int64_t sdf_saved_floats_bf16(const MlpShape& m, int64_t P, int with_grad);
 int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P);
 int64_t sdf_query_ws_floats_bf16(const MlpShape& m, int64_t P);
-int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s);
+int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s,
+                   bool ws_holds_pack = false);
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
                  int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, __nv_bfloat16* feat_b16 = nullptr,
                  int feat_b16_ld = 0, bool infer = false);

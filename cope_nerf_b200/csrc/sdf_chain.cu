@@ -520,13 +520,14 @@ int launch_sdf_chain_query(const MlpShape& m, const float* Wflat, const bf16* wp
   }
   const int ntiles = (int)((P + 127) / 128);
   // more tiles than SMs: two tiles in flight per CTA (COPE_CHAIN_PAIR=0 keeps the one-tile kernel for A/B measurements)
-  static const bool pair_ok = !(getenv("COPE_CHAIN_PAIR") && atoi(getenv("COPE_CHAIN_PAIR")) == 0);
+  static const int pair_mode = getenv("COPE_CHAIN_PAIR") ? atoi(getenv("COPE_CHAIN_PAIR")) : 1;   // 0: never, 1: > 148 tiles, 2: always
+  const bool pair_ok = pair_mode != 0;
   bool bias_aligned = true;
   for (int l = 0; l + 1 < m.n_lin; ++l) bias_aligned = bias_aligned && (m.b_off[l] % 4 == 0) && ((uintptr_t)Wflat % 16 == 0);
   // ... and the slab that straddles the skip layer's real outputs must end with the d_in raw coordinates of the PE
   const int skw2 = m.skip > 0 ? m.in[m.skip] - m.pe_w : 0;
   const bool skip_ok = m.skip > 1 && m.d_in == 4 && (skw2 + m.d_in) % 16 == 0 && skw2 + m.pe_w == 256;
-  if (ntiles > 148 && pair_ok && skip_ok && bias_aligned) {
+  if ((ntiles > 148 || pair_mode == 2) && pair_ok && skip_ok && bias_aligned) {
     static bool attr2_set = false;
     const size_t smem2 = 8 * kPanelBytes + kQ2WRing * kWChunkBytes + 256;
     if (!attr2_set) {
@@ -541,7 +542,7 @@ int launch_sdf_chain_query(const MlpShape& m, const float* Wflat, const bf16* wp
       cudaMemsetAsync(tl, 0, 2 * 4096 * sizeof(long long), s);
       a.dbg = tl;
     }
-    sdf_chain_query2_kernel<<<148, kChThreads, smem2, s>>>(a);
+    sdf_chain_query2_kernel<<<std::min(ntiles, 148), kChThreads, smem2, s>>>(a);
     COPE_CHECK_LAUNCH("sdf_chain_query2");
     if (tl_file) {      // profiling aid: the only place this path synchronises
       static long long host[2 * 4096];

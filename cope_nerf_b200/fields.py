@@ -204,14 +204,21 @@ class SDFNetwork(_MlpBase):
             raise NotImplementedError("scale != 1 is not wired into the fused kernels (reference default is 1.0)")
         return _SdfFn.apply(self, flat, x, want_grad, self.precision)
 
-    def query_flat(self, flat, x):
-        """sdf only, no autograd state (cope_sdf_query)."""
+    def query_flat(self, flat, x, pack_token=None):
+        """sdf only, no autograd state (cope_sdf_query).  `pack_token`: a mutable list shared by consecutive queries with the SAME
+        `flat` on the same stream (the four sampling queries of one forward): from the second call on, the packed bf16 weights that
+        the first call left at the head of the scratch buffer are reused instead of re-packed."""
         P = x.shape[0]
         x = x.contiguous().float()
         out = torch.empty(P, 1, dtype=torch.float32, device=x.device)
         ws = L.scratch(L.query("cope_sdf_query_ws_floats", self.desc, P, self.precision), x.device)
-        L.call("cope_sdf_query", self.desc, L.ptr(flat), L.ptr(x), P, L.ptr(out), L.ptr(ws), self.precision,
-               L.stream())
+        prec = self.precision
+        if pack_token is not None and prec == L.PREC_BF16:
+            key = (ws.data_ptr(), flat.data_ptr(), flat._version, L.stream())
+            if pack_token and pack_token[0] == key:
+                prec |= L.WS_HOLDS_PACK
+            pack_token[:] = [key]
+        L.call("cope_sdf_query", self.desc, L.ptr(flat), L.ptr(x), P, L.ptr(out), L.ptr(ws), prec, L.stream())
         return out
 
     # -- reference API ------------------------------------------------------------------------------------

@@ -351,7 +351,7 @@ class NeuSRenderer(nn.Module):
                L.stream())
         return z_out, sdf_out
 
-    def cat_z_vals(self, rays_o, rays_d, time_step, z_vals, new_z_vals, sdf, last=False, sdf_flat=None):
+    def cat_z_vals(self, rays_o, rays_d, time_step, z_vals, new_z_vals, sdf, last=False, sdf_flat=None, pack_token=None):
         """model/neus_renderer.py:282-298 (sorted merge instead of a full sort)."""
         if last:
             return self.merge_z(z_vals, new_z_vals)[0], sdf
@@ -360,7 +360,7 @@ class NeuSRenderer(nn.Module):
         tstep = time_step.reshape(-1)[:1].contiguous().float()
         near = far = tstep   # unused when use_mid = 0
         pts = self._points(rays_o.contiguous(), rays_d.contiguous(), new_z_vals, tstep, near, far)
-        new_sdf = self.sdf_network.query_flat(flat, pts).reshape(n, k)
+        new_sdf = self.sdf_network.query_flat(flat, pts, pack_token).reshape(n, k)
         return self.merge_z(z_vals, new_z_vals, sdf.reshape(z_vals.shape), new_sdf)
 
     def sample_z(self, rays_o, rays_d, time_step, near, far, eval, sdf_flat, it=0):
@@ -381,12 +381,13 @@ class NeuSRenderer(nn.Module):
             z = self.coarse_z(near_c, far_c, n_samples, t_rand)
             if use_imp:
                 flat = sdf_flat.detach()
-                sdf = self.sdf_network.query_flat(flat, self._points(ro, rd, z, tstep, near_c, far_c)).reshape(n, n_samples)
+                token = []          # the four queries below share one weight pack (cope_sdf_query, COPE_WS_HOLDS_PACK)
+                sdf = self.sdf_network.query_flat(flat, self._points(ro, rd, z, tstep, near_c, far_c), token).reshape(n, n_samples)
                 k = self.n_importance // self.up_sample_steps
                 for i in range(self.up_sample_steps):
                     new_z = self.up_sample(ro, rd, z, sdf, k, 64 * 2 ** i)
                     z, sdf = self.cat_z_vals(ro, rd, tstep, z, new_z, sdf, last=(i + 1 == self.up_sample_steps),
-                                             sdf_flat=flat)
+                                             sdf_flat=flat, pack_token=token)
         return z, n_samples
 
     def forward_losses(self, rays_o, rays_d, ray_d_norm, time_step, near, far, rgb_gt, cos_anneal_ratio=0.0, it=-1,

@@ -32,6 +32,9 @@ typedef void* cope_stream_t;
 /* precision of the MLP paths */
 #define COPE_PREC_FP32 0 /* fp32 SIMT GEMMs: strict-parity mode (<= 1e-3 rel vs the reference)          */
 #define COPE_PREC_BF16 1 /* bf16 tcgen05 tensor-core path, fp32 accumulate (cos-sim > 0.999 contract)    */
+/* OR-ed into `prec` of cope_sdf_query: the head of `ws` still holds the packed bf16 weights that an earlier cope_sdf_query left there
+ * on the same stream for the same Wflat contents (the four sampling queries of one NeuSRenderer.forward): skip the re-pack launch */
+#define COPE_WS_HOLDS_PACK 0x100
 
 /* Shape of a weight-normalised MLP (SDFNetwork / RenderingNetwork, model/neus_fields.py:205-374).
  * Flat parameter layout (floats): for l in 0..n_lin-1: W_l [dims_out[l] x dims_in[l]] row-major, then
