@@ -239,7 +239,7 @@ def main():
         opt.step()
         return loss
 
-    # The step has ~330 short launches: replay them as ONE CUDA graph (static input buffers), keep the NCCL
+    # The step has ~70 short launches around the chain kernels: replay them as ONE CUDA graph (static input buffers), keep the NCCL
     # all-reduce and the fused Adam eager.  --no-graph times the eager launch path instead.
     graph, static, static_loss, graph_note = None, None, None, "eager launches"
     if not args.no_graph:
