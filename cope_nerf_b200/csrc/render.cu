@@ -133,6 +133,7 @@ __global__ void sample_cdf_kernel(const float* __restrict__ cdf, const float* __
 
 // ------------------------------------------------------------------------------------ up_sample
 // neus_renderer.py:178-224 + sample_pdf :39-70.  Lane owns sections [lane*C, lane*C+C).
+template <int MAXC>      // sections per lane the loops are unrolled for: 4 (S <= 129) or 8 (S <= kMaxS)
 __global__ void upsample_kernel(const float* __restrict__ z, const float* __restrict__ sdf, int64_t N, int S, int K,
                                 float inv_s, float* __restrict__ new_z, float* __restrict__ cdf_out,
                                 int64_t* __restrict__ inds_out) {
@@ -146,25 +147,35 @@ __global__ void upsample_kernel(const float* __restrict__ z, const float* __rest
   const float* F = s_f[w];
   const int M = S - 1;                      // sections
   const int C = (M + 31) / 32;
-  constexpr int MAXC = (kMaxS + 31) / 32;
   float alpha[MAXC], wgt[MAXC];
-  auto raw_cos = [&](int j) { return __fdiv_rn(__fsub_rn(F[j + 1], F[j]), __fadd_rn(__fsub_rn(Z[j + 1], Z[j]), 1e-5f)); };
+  // The kernel is instruction-bound (one warp turns ~1 KB of a ray into 16 samples), so the per-section arithmetic uses the
+  // fast division / exp intrinsics: |error| of alpha ~3e-7, of the CDF ~1e-6 (tests: 2e-6), far below what moves a sample by
+  // more than the 2e-5 the parity test allows.  The inverse-CDF step (invert_cdf) keeps the IEEE operations: it is the part
+  // that is bit-exact against torch.searchsorted when fed the reference's CDF.  raw_cos(j-1) is carried from the previous
+  // section of the lane instead of being recomputed.
+  auto raw_cos = [&](int j) { return __fdividef(F[j + 1] - F[j], (Z[j + 1] - Z[j]) + 1e-5f); };
+  auto fast_sigmoid = [](float x) { return __fdividef(1.0f, 1.0f + __expf(fminf(-x, 80.0f))); };
   float prod = 1.0f;
+  float pv = 0.0f;
+  {
+    const int j0 = lane * C;
+    if (j0 > 0 && j0 < M) pv = raw_cos(j0 - 1);
+  }
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     int j = lane * C + c;
     alpha[c] = 0.0f;
     if (c < C && j < M) {
-      float cs = raw_cos(j);
-      float pv = j > 0 ? raw_cos(j - 1) : 0.0f;
-      cs = fminf(fmaxf(fminf(pv, cs), -1e3f), 0.0f);
-      float mid = __fmul_rn(__fadd_rn(F[j], F[j + 1]), 0.5f);
-      float dist = __fsub_rn(Z[j + 1], Z[j]);
-      float half = __fmul_rn(__fmul_rn(cs, dist), 0.5f);
-      float pc = sigmoidf_(__fmul_rn(__fsub_rn(mid, half), inv_s));
-      float nc = sigmoidf_(__fmul_rn(__fadd_rn(mid, half), inv_s));
-      alpha[c] = __fdiv_rn(__fadd_rn(__fsub_rn(pc, nc), 1e-5f), __fadd_rn(pc, 1e-5f));
-      prod *= __fadd_rn(__fsub_rn(1.0f, alpha[c]), 1e-7f);
+      const float raw = raw_cos(j);
+      const float cs = fminf(fmaxf(fminf(pv, raw), -1e3f), 0.0f);
+      pv = raw;
+      const float mid = (F[j] + F[j + 1]) * 0.5f;
+      const float dist = Z[j + 1] - Z[j];
+      const float half = cs * dist * 0.5f;
+      const float pc = fast_sigmoid((mid - half) * inv_s);
+      const float nc = fast_sigmoid((mid + half) * inv_s);
+      alpha[c] = __fdividef(pc - nc + 1e-5f, pc + 1e-5f);
+      prod *= 1.0f - alpha[c] + 1e-7f;
     }
   }
   // exclusive product scan of the per-lane products
@@ -182,18 +193,19 @@ __global__ void upsample_kernel(const float* __restrict__ z, const float* __rest
     int j = lane * C + c;
     wgt[c] = 0.0f;
     if (c < C && j < M) {
-      wgt[c] = __fadd_rn(__fmul_rn(alpha[c], T), 1e-5f);      // weights + 1e-5 (:42)
-      T *= __fadd_rn(__fsub_rn(1.0f, alpha[c]), 1e-7f);
+      wgt[c] = alpha[c] * T + 1e-5f;                          // weights + 1e-5 (:42)
+      T *= 1.0f - alpha[c] + 1e-7f;
       lsum += wgt[c];
     }
   }
   float total = warp_sum(lsum);
   // inclusive sum scan of pdf
   float lp = 0.0f;
+  const float inv_total = __frcp_rn(total);
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     int j = lane * C + c;
-    if (c < C && j < M) { wgt[c] = __fdiv_rn(wgt[c], total); lp += wgt[c]; }
+    if (c < C && j < M) { wgt[c] *= inv_total; lp += wgt[c]; }
   }
   float isum = lp;
 #pragma unroll
@@ -472,7 +484,10 @@ int cope_upsample(const float* z, const float* sdf, int64_t N, int S, int K, flo
                   int64_t* inds_out, cope_stream_t s) {
   COPE_REQUIRE(S >= 2 && S <= kMaxS, "upsample: S=%d outside [2,%d]", S, kMaxS);
   if (N <= 0) return 0;
-  upsample_kernel<<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, sdf, N, S, K, inv_s, new_z, cdf_out, inds_out);
+  if (S - 1 <= 128)
+    upsample_kernel<4><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, sdf, N, S, K, inv_s, new_z, cdf_out, inds_out);
+  else
+    upsample_kernel<8><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, sdf, N, S, K, inv_s, new_z, cdf_out, inds_out);
   COPE_CHECK_LAUNCH("upsample");
   return 0;
 }
