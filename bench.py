@@ -34,7 +34,7 @@ H, W = 717, 1275
 DEPTH_RANGE = (0.01, 5.0)
 METRIC = "train rays/s fwd+bwd+eikonal (NeuS 64+64 samples)"
 # dram__bytes_read + dram__bytes_write of the chain / wgrad kernels of one 1024-ray step (profiles/r01_fused_kernels_ncu_full.csv)
-MLP_DRAM_GB_PER_STEP = 9.87
+MLP_DRAM_GB_PER_STEP = 9.76   # ncu --set full, profiles/r01_end_kernels_ncu_full.csv (1024 rays)
 MLP_CALLS = {"cope_sdf_query", "cope_sdf_fwd", "cope_sdf_bwd", "cope_color_fwd", "cope_color_bwd", "cope_render_mlp_fwd",
              "cope_render_mlp_bwd"}
 
@@ -361,7 +361,7 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "SDF+colour MLP kernels (cope_sdf_query, cope_render_mlp_fwd/bwd = sdf_chain_query / sdf_fused<FWD,TAN,ADJ> / color_fused / tc_wgrad)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-                         "traffic": MLP_DRAM_GB_PER_STEP, "traffic_unit": "GB of DRAM traffic per step of the MLP kernel group at 1024 rays (ncu --set full, profiles/r01_fused_kernels_ncu_full.csv)", "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                         "traffic": MLP_DRAM_GB_PER_STEP, "traffic_unit": "GB of DRAM traffic per step of the MLP kernel group at 1024 rays (ncu --set full, profiles/r01_end_kernels_ncu_full.csv)", "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                          "measured": "CUDA events around the MLP entry points, same K batches launched eagerly after the timed region",
                          "mlp_ms_per_step": mlp_ms_step, "mlp_share_of_step": min(1.0, mlp_ms_step / ms_per_step) if ms_per_step else None,
                          "algorithmic_flop_per_ray": FLOP_PER_TRAIN_RAY},
