@@ -141,7 +141,21 @@ __global__ void upsample_kernel(const float* __restrict__ z, const float* __rest
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + w;
   if (n >= N) return;
-  for (int j = lane; j < S; j += 32) { s_z[w][j] = z[n * S + j]; s_f[w][j] = sdf[n * S + j]; }
+  {
+    // all loads of the row in flight together (S <= 32 * (MAXC + 1); the last pass covers S - 1 = 32 * MAXC)
+    float zr[MAXC + 1], fr[MAXC + 1];
+#pragma unroll
+    for (int c = 0; c <= MAXC; ++c) {
+      const int j = lane + 32 * c;
+      zr[c] = j < S ? z[n * S + j] : 0.0f;
+      fr[c] = j < S ? sdf[n * S + j] : 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c <= MAXC; ++c) {
+      const int j = lane + 32 * c;
+      if (j < S) { s_z[w][j] = zr[c]; s_f[w][j] = fr[c]; }
+    }
+  }
   __syncwarp();
   const float* Z = s_z[w];
   const float* F = s_f[w];
@@ -230,6 +244,10 @@ __global__ void upsample_kernel(const float* __restrict__ z, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------ merge (cat_z_vals)
+// One warp per ray.  Every global load of the ray (old depths and sdf, new depths and sdf) is issued before anything is used:
+// with the loads inside the rank loops a warp paid ~10 dependent HBM latencies per ray and the kernel ran at 37 % of the copy
+// bandwidth with every SM full of waiting warps.  MAXC = old samples per lane (4: S <= 128, 8: S <= kMaxS); K <= 64.
+template <int MAXC>
 __global__ void merge_z_kernel(const float* __restrict__ z, const float* __restrict__ nz, const float* __restrict__ sdf,
                                const float* __restrict__ nsdf, int64_t N, int S, int K, float* __restrict__ z_out,
                                float* __restrict__ sdf_out) {
@@ -237,25 +255,50 @@ __global__ void merge_z_kernel(const float* __restrict__ z, const float* __restr
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + w;
   if (n >= N) return;
-  for (int j = lane; j < S; j += 32) s_z[w][j] = z[n * S + j];
-  for (int k = lane; k < K; k += 32) s_n[w][k] = nz[n * K + k];
+  float zv[MAXC], sv[MAXC], nv[2], nsv[2];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = lane + 32 * c;
+    zv[c] = j < S ? z[n * S + j] : 0.0f;
+    sv[c] = (sdf_out && j < S) ? sdf[n * S + j] : 0.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int k = lane + 32 * c;
+    nv[c] = k < K ? nz[n * K + k] : 0.0f;
+    nsv[c] = (sdf_out && k < K) ? nsdf[n * K + k] : 0.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (lane + 32 * c < S) s_z[w][lane + 32 * c] = zv[c];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    if (lane + 32 * c < K) s_n[w][lane + 32 * c] = nv[c];
   __syncwarp();
   const int T = S + K;
-  for (int j = lane; j < S; j += 32) {         // old element: ties go before new ones
-    float v = s_z[w][j];
-    int r = j;
-    for (int k = 0; k < K; ++k) r += s_n[w][k] < v;
-    z_out[n * T + r] = v;
-    if (sdf_out) sdf_out[n * T + r] = sdf[n * S + j];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {             // old element: ties go before new ones
+    const int j = lane + 32 * c;
+    if (j < S) {
+      const float v = zv[c];
+      int r = j;
+      for (int k = 0; k < K; ++k) r += s_n[w][k] < v;
+      z_out[n * T + r] = v;
+      if (sdf_out) sdf_out[n * T + r] = sv[c];
+    }
   }
-  for (int k = lane; k < K; k += 32) {
-    float v = s_n[w][k];
-    int lo = 0, hi = S;                        // # old <= v
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (s_z[w][mid] <= v) lo = mid + 1; else hi = mid; }
-    int r = lo;
-    for (int q = 0; q < K; ++q) { float u = s_n[w][q]; r += (u < v) || (u == v && q < k); }
-    z_out[n * T + r] = v;
-    if (sdf_out) sdf_out[n * T + r] = nsdf[n * K + k];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int k = lane + 32 * c;
+    if (k < K) {
+      const float v = nv[c];
+      int lo = 0, hi = S;                      // # old <= v
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (s_z[w][mid] <= v) lo = mid + 1; else hi = mid; }
+      int r = lo;
+      for (int q = 0; q < K; ++q) { float u = s_n[w][q]; r += (u < v) || (u == v && q < k); }
+      z_out[n * T + r] = v;
+      if (sdf_out) sdf_out[n * T + r] = nsv[c];
+    }
   }
 }
 
@@ -496,8 +539,12 @@ int cope_merge_z(const float* z, const float* new_z, const float* sdf, const flo
                  float* z_out, float* sdf_out, cope_stream_t s) {
   COPE_REQUIRE(S >= 1 && S <= kMaxS && K >= 1 && K <= 64, "merge_z: S=%d K=%d out of range", S, K);
   if (N <= 0) return 0;
-  merge_z_kernel<<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, new_z, sdf, new_sdf, N, S, K, z_out,
-                                                                         sdf ? sdf_out : nullptr);
+  if (S <= 128)
+    merge_z_kernel<4><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, new_z, sdf, new_sdf, N, S, K, z_out,
+                                                                              sdf ? sdf_out : nullptr);
+  else
+    merge_z_kernel<8><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(z, new_z, sdf, new_sdf, N, S, K, z_out,
+                                                                              sdf ? sdf_out : nullptr);
   COPE_CHECK_LAUNCH("merge_z");
   return 0;
 }
