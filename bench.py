@@ -196,8 +196,8 @@ def main():
     from cope_nerf_b200 import _lib as L
     from cope_nerf_b200.dist import FlatGradBucket, init_from_env
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # NCCL prints its version banner on stdout: keep stdout to the
-        os.environ["NCCL_DEBUG"] = "WARN"                         # one JSON line of the contract
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):   # NCCL prints its version banner on stdout (env or nccl.conf):
+        os.environ["NCCL_DEBUG"] = "WARN"                             # keep stdout to the one JSON line of the contract
     rank, world, local = init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
