@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (BASELINE.json configs[2]): --rays is the TOTAL batch, split over the ranks in 16-ray blocks")
     ap.add_argument("--precision", default=os.environ.get("COPE_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="ray sample of the CPU baseline step (BASELINE.json configs[0]: 512 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -206,6 +208,11 @@ def main():
     if prec is None:
         prec = getattr(C, "DEFAULT_PRECISION", C.PREC_FP32)
     n = args.rays
+    if args.strong and world > 1:
+        from cope_nerf_b200.dist import shard_range
+        lo, hi = shard_range(args.rays, rank, world)      # this rank's slice of the total batch (multiples of one 4x4 patch)
+        n = hi - lo
+    total_rays = args.rays if (args.strong and world > 1) else n * world
 
     torch.manual_seed(678)
     rnd = C.training.build_networks(device=dev, precision=prec)
@@ -314,7 +321,7 @@ def main():
     ms_total, launches = timed_region(step, resident)
     clk = clocks.stop()
     ms_per_step = ms_total / args.steps
-    value = n * world * args.steps / (ms_total * 1e-3)
+    value = total_rays * args.steps / (ms_total * 1e-3)
     if graph is not None:       # kernels inside a replayed graph do not pass through the library's launch counter
         l0 = lib.cope_launch_count()
         step_eager(resident[0])
@@ -339,7 +346,7 @@ def main():
         return step(b).item()        # pinned host -> static device buffers -> graph replay -> loss read-back
 
     ms_e2e, _ = timed_region(step_e2e, pinned)
-    e2e = n * world * args.steps / (ms_e2e * 1e-3)
+    e2e = total_rays * args.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
 
     if rank == 0:
@@ -349,7 +356,8 @@ def main():
         peak = pk["bf16_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32" if prec == C.PREC_FP32 else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(n), "rays_per_gpu": n, "parallelism": f"dp{world} (rays sharded, one flat-grad allreduce)",
                        "precision": "fp32 SIMT (strict parity)" if prec == C.PREC_FP32 else "bf16 tcgen05, fp32 accumulate",

@@ -436,3 +436,33 @@ def test_motion_network_full_size_vs_oracle():
     (w2c * cu(wgt)).sum().backward(); (w2co * wgt).sum().backward()
     for k, p in m.named_parameters():
         assert rel_err(p.grad, Pg[k].grad) < 1e-3, (k, rel_err(p.grad, Pg[k].grad))
+
+
+def test_tanks_config_step_vs_oracle():
+    """BASELINE.json configs[2] constants (configs/Tanks/Ballroom.yaml:10,41,43): 540 x 960 frames, depth range [0.01, 10],
+    variance init 0.2 - one full training step of the full-size networks against the CPU oracle."""
+    P = full_params(perturb=0.01)
+    P["variance"] = O.init_variance_params(init_val=0.2)
+    cfg = dict(C.training.DEFAULT_CFG, neus_variance_network=dict(init_val=0.2))
+    r = renderer_from(P, cfg)
+    torch.manual_seed(33)
+    n = 32
+    g = dict(pix=(torch.rand(1, n, 2) * 2 - 1) * 0.8, rgb_gt=torch.rand(n, 3), t=torch.tensor([-0.4]), t_rand=torch.rand(n, 64))
+    r0, t0 = torch.randn(1, 3) * 0.05, torch.randn(1, 3) * 0.05
+    Kc = O.camera_matrix(0.8 * 960, 0.8 * 960, 960, 540).unsqueeze(0)
+    Pg = {t: {k: v.clone().requires_grad_(True) for k, v in P[t].items()} for t in P}
+    po = dict(r=r0.clone().requires_grad_(True), t=t0.clone().requires_grad_(True), init_c2w=torch.eye(4).unsqueeze(0))
+    lo, aux = O.train_step(Pg, po, g["pix"], Kc, torch.eye(4).unsqueeze(0), g["rgb_gt"], g["t"], [0.01, 10.0], cos_anneal=0.5,
+                           t_rand=g["t_rand"])
+    lo.backward()
+    pose = C.PoseRetriever(1).to(DEV)
+    with torch.no_grad():
+        pose.r.copy_(r0); pose.t.copy_(t0)
+    loss, out = _run_step(r, pose, g, cu(Kc), depth_range=(0.01, 10.0))
+    assert rel_err(loss, lo) < 1e-4
+    assert_close(out["color_fine"], aux["out"]["color_fine"], 1e-3, "rgb")
+    assert rel_err(out["depth_pred"], aux["out"]["depth_pred"]) < 1e-3
+    for tag, net in (("sdf", r.sdf_network), ("color", r.color_network), ("variance", r.deviation_network)):
+        for k, p in net.named_parameters():
+            assert rel_err(p.grad, Pg[tag][k].grad) < 1e-3, (tag, k, rel_err(p.grad, Pg[tag][k].grad))
+    assert rel_err(pose.r.grad, po["r"].grad) < 2e-3 and rel_err(pose.t.grad, po["t"].grad) < 2e-3
