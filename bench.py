@@ -200,8 +200,21 @@ def main():
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):   # NCCL prints its version banner on stdout (env or nccl.conf):
         os.environ["NCCL_DEBUG"] = "WARN"                             # keep stdout to the one JSON line of the contract
-    rank, world, local = init_from_env("nccl")
-    torch.cuda.set_device(local)
+    # NCCL prints its version banner on the C-level stdout when the communicator is created: point fd 1 at stderr until the first
+    # collective has run, so that stdout carries exactly the one JSON line of the contract
+    sys.stdout.flush()
+    fd1 = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local = init_from_env("nccl")
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(fd1, 1)
+        os.close(fd1)
     dev = torch.device("cuda", local)
     lib = C.load_library()
     prec = {"fp32": C.PREC_FP32, "bf16": C.PREC_BF16}.get(args.precision)

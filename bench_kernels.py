@@ -42,13 +42,26 @@ def eval_image(rnd, pk, dev, h, w, chunk):
     world[:3, 3] = torch.tensor([0.02, -0.03, 0.05], device=dev)
     S = torch.eye(4, device=dev)[None]
     t0 = torch.zeros(1, device=dev)
-    fn = lambda: C.training.render_image(rnd, world, K, S, h, w, t0, (0.01, 5.0), chunk=chunk)
+    # multi-GPU (torchrun): contiguous pixel ranges, one per rank; device time = max over ranks
+    import torch.distributed as dist
+    nrank = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    first, last = rank * (h * w) // nrank, (rank + 1) * (h * w) // nrank
+    fn = lambda: C.training.render_image(rnd, world, K, S, h, w, t0, (0.01, 5.0), chunk=chunk, rays=(first, last - first))
+    if nrank > 1:
+        dist.barrier()
     t = timeit(fn, iters=3, warm=1)
+    if nrank > 1:
+        tt = torch.tensor([t], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = tt.item()
+        if rank != 0:
+            return
     rays = h * w
     flop = rays * 440_983_552          # 112 F_sdfq + 128 (2 F_sdf + F_col) per evaluation ray
-    print(json.dumps({"kernel": "eval_image_render", "height": h, "width": w, "rays": rays, "chunk": chunk, "ms": t * 1e3,
+    print(json.dumps({"kernel": "eval_image_render", "n_gpus": nrank, "height": h, "width": w, "rays": rays, "chunk": chunk, "ms": t * 1e3,
                       "rays_per_s": rays / t, "achieved": flop / t / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                      "frac": flop / t / 1e12 / pk["bf16_sustained"], "bound": "tensor", "peak_source": pk["src"],
+                      "frac": flop / t / 1e12 / (pk["bf16_sustained"] * nrank), "bound": "tensor", "peak_source": pk["src"],
                       "note": "pose -> rays -> 64+64 hierarchical sampling -> SDF value + gradient -> colour -> compositing -> "
                               "normal / arg-max-depth maps; every result stays on the device"}))
 
@@ -79,13 +92,21 @@ def main():
     ap.add_argument("--rays", type=int, nargs="*", default=[4096, 16384, 65536, 262144])
     ap.add_argument("--eval-image", type=int, nargs=2, default=[484, 648], metavar=("H", "W"))
     ap.add_argument("--eval-chunk", type=int, default=16384)
+    ap.add_argument("--eval-only", action="store_true", help="only the evaluation-image row (the one that runs under torchrun)")
     args = ap.parse_args()
-    dev = torch.device("cuda")
+    from cope_nerf_b200.dist import init_from_env
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    rank, nrank, local = init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     pk = peaks()
     torch.manual_seed(678)
     rnd = C.training.build_networks(device=dev, precision=C.PREC_BF16)
     if args.eval_image[0] > 0:
         eval_image(rnd, pk, dev, args.eval_image[0], args.eval_image[1], args.eval_chunk)
+        if args.eval_only or nrank > 1:
+            return
         motion_chain(dev, 100, 10)
     S = 128
     for N in args.rays:
