@@ -66,6 +66,46 @@ def eval_image(rnd, pk, dev, h, w, chunk):
                               "normal / arg-max-depth maps; every result stays on the device"}))
 
 
+def stage1_losses_row(rnd, dev, n_rays=1024, S=128, T=3, h=717, w=1275):
+    """the stage-1 auxiliary losses of train.py:467-517 at the training shapes (1024 rays x 128 samples, three
+    717 x 1275 reference frames, 100-frame sequence), forward + backward through losses.stage1_losses: (a) the fused kernels alone
+    (SDF-flow + flow-RGB incl. the MotionNetwork pose chain), (b) with the SDF-consistency re-query (131 072-point SDF forward +
+    backward)."""
+    from cope_nerf_b200 import losses as CL
+    from cope_nerf_b200.motion import MotionNetwork
+    from cope_nerf_b200.renderer import RenderOutputs
+    torch.manual_seed(11)
+    mot = MotionNetwork(d_out=6, d_in=1, d_hidden=256, n_layers=4, skip_in=[2], multires=6, bias=0.5, scale=1.0, geometric_init=False,
+                        weight_norm=True).to(dev)
+    P = n_rays * S
+    pts4 = torch.cat([torch.randn(P, 3, device=dev) * 0.4 - torch.tensor([0, 0, 2.0], device=dev), torch.zeros(P, 1, device=dev)], -1)
+    out = RenderOutputs({"color_fine": torch.rand(n_rays, 3, device=dev),
+                         "weights": (torch.softmax(torch.randn(n_rays, S, device=dev), -1) * 0.9).requires_grad_(True),
+                         "sdf": (torch.randn(P, 1, device=dev) * 0.2).requires_grad_(True)})
+    out.grad4, out.pts4 = torch.randn(P, 4, device=dev).requires_grad_(True), pts4.requires_grad_(True)
+    f = 0.8 * w
+    K = torch.tensor([[2 * f / w, 0, 0, 0], [0, -2 * f / h, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)
+    Kr, Sc = K[None].repeat(T, 1, 1), torch.eye(4, device=dev)[None]
+    pix = torch.stack([torch.randint(0, w, (n_rays,), device=dev), torch.randint(0, h, (n_rays,), device=dev)], -1).float()
+    npix = torch.stack([2 * pix[:, 0] / (w - 1) - 1, 2 * pix[:, 1] / (h - 1) - 1], -1)
+    refs, gt = torch.rand(T, 3, h, w, device=dev), torch.rand(n_rays, 3, device=dev)
+
+    def run(consistency):
+        for t in (out["weights"], out["sdf"], out.grad4, out.pts4):
+            t.grad = None
+        mot.zero_grad(); rnd.sdf_network.zero_grad()
+        res = CL.stage1_losses(out, gt, mot, rnd.sdf_network, -0.3, 40, [41, 42, 43], T, 100, 10, Kr, Sc, npix, pix, refs, 39, -0.2,
+                               use_consistency=consistency)
+        (res["sdf_loss"] + res["flow_rgb_loss"] + res["sdf_consistency_loss"]).backward()
+    for name, cons in (("stage1_sdfflow_flowrgb_fwd_bwd", False), ("stage1_all_fwd_bwd", True)):
+        t = timeit(lambda: run(cons), iters=10, warm=2)
+        print(json.dumps({"kernel": name, "rays": n_rays, "samples": S, "ref_frames": T, "ms": t * 1e3,
+                          "note": "losses.stage1_losses forward + backward: MotionNetwork pose chain (3 + 1 relative poses x 10 sub-steps), "
+                                  "cope_step_losses / cope_weighted_points / cope_flow_rgb" +
+                                  (", SDF-consistency re-query of 131072 points (cope_sdf_fwd / cope_sdf_bwd, bf16 layer-by-layer path)"
+                                   if cons else "")}))
+
+
 def motion_chain(dev, n_img, n_sub):
     """relative poses of all n_img - 1 consecutive frame pairs (n_sub sub-steps each) chained into
     world -> camera maps, forward + backward to the MotionNetwork parameters.  (The CPU port of the reference's Python
@@ -108,6 +148,7 @@ def main():
         if args.eval_only or nrank > 1:
             return
         motion_chain(dev, 100, 10)
+        stage1_losses_row(rnd, dev)
     S = 128
     for N in args.rays:
         P = N * S
