@@ -624,6 +624,61 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
     return 0;
   }
 
+  if (!dgrad && have_dy && fused_enabled(m, b, "adj") && fused_enabled(m, b, "val")) {
+    // ---- value-only backward (SDFNetwork.forward / .sdf with gradients, e.g. the SDF-consistency loss of train.py:504): ONE
+    // fused adjoint sweep (stores every zb_l, and eb0 / eb1 when dx is wanted), then all weight gradients in one launch
+    if (d_feat) {
+      cvt_f32_bf16_kernel<<<g1(P * (r64(featW) / 8)), 256, 0, s>>>(d_feat, d_feat_ld, dyb, LD, P, featW, r64(featW), 1.0f);
+      COPE_CHECK_LAUNCH("cvt_dfeat");
+    } else if (!d_feat_in_ws) {
+      cudaMemsetAsync(dyb, 0, sizeof(bf16) * P * LD, s);
+    }
+    FzMaps maps{};
+    if (int rc = make_tmap3(sv.H, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.H)) return rc;
+    maps.D = maps.H; maps.Z2 = maps.H;
+    if (int rc = make_tmap3(dyb, LDu, Pu, 1, LDu, Pu * LDu, &maps.in0)) return rc;
+    if (int rc = make_tmap3(ZBall, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.out)) return rc;
+    FzArgs a{};
+    fz_common(m, b, Wflat, wp, x, P, &a);
+    a.d_sdf = d_sdf; a.d_sdf_ld = d_sdf_ld; a.eb0 = eb0; a.eb1 = eb1;
+    a.has_d = 0; a.store_out = 1; a.want_e = dx != nullptr;
+    fz_job(&a, b.wt_off[top], r16(m.in[top]), r64(featW), 0, 2, 1);
+    for (int l = top - 1; l >= 1; --l) {
+      const int st = top - l;
+      fz_job(&a, b.wt_off[l], r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
+    }
+    if (a.want_e) fz_job(&a, b.wt_off[0], 64, r64(m.out[0]), top & 1, 1, (top & 1) + 1);
+    if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, s)) return rc;
+    TcWgradArgs wg[COPE_MAX_LIN];
+    int nw = 0;
+    if (d_feat || d_feat_in_ws) {
+      TcWgradArgs w{};
+      w.P = P; w.Mp = r128(featW); w.Np = r16(m.in[top]); w.m_valid = featW; w.n_valid = m.in[top];
+      w.X[0] = dyb; w.ldx[0] = LD; w.Y[0] = sv.h(top); w.ldy[0] = LD; w.n_pairs = 1;
+      w.dW = dWflat + m.w_off[top] + m.in[top]; w.ldw = m.in[top]; w.part = part; w.db = dWflat + m.b_off[top] + 1;
+      wg[nw++] = w;
+    }
+    if (d_sdf) {
+      if (int rc = wcolsum(sv.h(top), LD, d_sdf, d_sdf_ld, P, m.in[top], dWflat + m.w_off[top], s)) return rc;
+      sum_strided_kernel<<<(unsigned)std::min<int64_t>(296, ceil_div(P, 256)), 256, 0, s>>>(d_sdf, d_sdf_ld, P, dWflat + m.b_off[top]);
+      COPE_CHECK_LAUNCH("colsum_dsdf");
+    }
+    for (int l = top - 1; l >= 0; --l) {
+      TcWgradArgs w{};
+      w.P = P; w.Mp = r128(m.out[l]); w.Np = l == 0 ? 64 : r16(m.in[l]); w.m_valid = m.out[l];
+      w.n_valid = l == 0 ? m.pe_w : m.in[l];
+      w.X[0] = ZBall + (int64_t)l * P * LD; w.ldx[0] = LD; w.Y[0] = sv.in(l); w.ldy[0] = sv.ld_in(l); w.n_pairs = 1;
+      w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part; w.db = dWflat + m.b_off[l];
+      wg[nw++] = w;
+    }
+    if (int rc = launch_tc_wgrad_batch(wg, nw, s)) return rc;
+    if (dx) {
+      pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, eb0, 64, b.skip > 0 ? eb1 : nullptr, 64, dx, m.d_in, dx_accumulate);
+      COPE_CHECK_LAUNCH("pe_vjp");
+    }
+    return 0;
+  }
+
   if (dgrad && !fused_tan) {
     if (int rc = sdf_tangent_layered(m, b, sv, wp, x, P, dgrad, T, t0, ZB2, dWflat, s)) return rc;
   }

@@ -153,6 +153,38 @@ class _SdfFn(torch.autograd.Function):
         return None, dflat, dx, None, None
 
 
+class _SdfValueFn(torch.autograd.Function):
+    """sdf = SDFNetwork.sdf(x) with gradients on the tensor-core path (the SDF-consistency re-query, train.py:504): the forward
+    is the fused value + sweep chain (its analytic gradient is computed and dropped: still 3x faster than nine separate GEMM
+    launches with an fp32 [P,257] output), the backward one fused adjoint sweep + one batched weight-gradient launch."""
+
+    @staticmethod
+    def forward(ctx, net, flat, x):
+        P, dev = x.shape[0], x.device
+        x = x.contiguous().float()
+        sdf = torch.empty(P, 1, dtype=torch.float32, device=dev)
+        grad = torch.empty(P, net.desc.d_in, dtype=torch.float32, device=dev)
+        saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, 1, L.PREC_BF16), dtype=torch.float32, device=dev)
+        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, L.PREC_BF16), dev)
+        L.call("cope_sdf_fwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(sdf), 1, None, 0, L.ptr(grad), L.ptr(saved), L.ptr(ws),
+               L.PREC_BF16, L.stream())
+        ctx.net = net
+        ctx.save_for_backward(flat, x, saved)
+        return sdf
+
+    @staticmethod
+    def backward(ctx, d_sdf):
+        flat, x, saved = ctx.saved_tensors
+        net = ctx.net
+        P, dev = x.shape[0], x.device
+        dflat = torch.zeros_like(flat)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, L.PREC_BF16), dev)
+        L.call("cope_sdf_bwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(saved), L.ptr(d_sdf.contiguous()), 1, None, 0, None,
+               L.ptr(dflat), L.ptr(dx), 0, L.ptr(ws), L.PREC_BF16, L.stream())
+        return None, dflat, dx
+
+
 class SDFNetwork(_MlpBase):
     """model/neus_fields.py:205-303."""
 
@@ -228,6 +260,8 @@ class SDFNetwork(_MlpBase):
     def sdf(self, x):
         if not torch.is_grad_enabled() or not (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self.query_flat(self.flat_weights().detach(), x)
+        if self.precision == L.PREC_BF16 and self.scale == 1 and x.shape[0] > 0:
+            return _SdfValueFn.apply(self, self.flat_weights(), x)
         return self.forward(x)[:, :1]
 
     def sdf_hidden_appearance(self, x):

@@ -319,3 +319,55 @@ def test_fwd_pair_kernel_matches_one_tile_kernel(monkeypatch):
             assert rel_err(two[k], one[k]) < 2e-3, (n_rays, k, rel_err(two[k], one[k]))
         for k in ("dWs", "dWc", "dx"):
             assert cos_sim(two[k], one[k]) > 0.9999 and rel_err(two[k], one[k]) < 1e-2, (n_rays, k, rel_err(two[k], one[k]))
+
+
+@pytest.mark.parametrize("n", [3000, 128 * 150 + 5])
+def test_bf16_value_only_backward_fused_vs_layered_and_oracle(monkeypatch, n):
+    """SDFNetwork.forward / .sdf with gradients (the SDF-consistency re-query, train.py:504): the backward runs as one fused
+    adjoint sweep + one batched weight-gradient launch; against the layer-by-layer path (COPE_NO_FUSED=val) and the oracle."""
+    P = full_params(perturb=0.02)
+    torch.manual_seed(13)
+    x = torch.cat([torch.randn(n, 3) * 0.6, torch.full((n, 1), 0.1)], -1)
+    tgt = torch.randn(n, 1) * 0.1
+    wy = torch.randn(n, 257) * 0.05
+    res = {}
+    for mode, env in (("fused", None), ("layered", "val")):
+        if env:
+            monkeypatch.setenv("COPE_NO_FUSED", env)
+        r = bf16_renderer(P, C.training.DEFAULT_CFG)
+        xc = cu(x).requires_grad_(True)
+        y = r.sdf_network.forward(xc)
+        (torch.mean(torch.abs(y[:, :1] - cu(tgt))) + (y * cu(wy)).mean()).backward()
+        res[mode] = dict(y=y.detach(), dx=xc.grad, **{k: p.grad for k, p in r.sdf_network.named_parameters()})
+        r2 = bf16_renderer(P, C.training.DEFAULT_CFG)          # .sdf(): only column 0 carries a gradient
+        xs = cu(x).requires_grad_(True)
+        torch.mean(torch.abs(r2.sdf_network.sdf(xs) - cu(tgt))).backward()
+        res[mode + "_sdf"] = dict(dx=xs.grad, **{k: p.grad for k, p in r2.sdf_network.named_parameters()})
+        if env:
+            monkeypatch.delenv("COPE_NO_FUSED")
+    for tag in ("", "_sdf"):
+        for k, v in res["fused" + tag].items():
+            ref = res["layered" + tag][k]
+            if ref.abs().max() == 0:
+                assert v.abs().max() == 0, (tag, k)
+            else:
+                assert cos_sim(v, ref) > 0.9995, (tag, k, cos_sim(v, ref))
+    if n <= 4096:
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P["sdf"].items()}
+        xo = x.clone().requires_grad_(True)
+        yo = O.sdf_forward(Pg, xo)
+        (torch.mean(torch.abs(yo[:, :1] - tgt)) + (yo * wy).mean()).backward()
+        assert cos_sim(res["fused"]["y"], yo) > COS
+        assert cos_sim(res["fused"]["dx"], xo.grad) > 0.99
+        check_grads(res_named(res["fused"]), {k: v.grad for k, v in Pg.items()}, "sdf value-only", bias_cos=0.98, cos=0.99)
+        Ps = {k: v.clone().requires_grad_(True) for k, v in P["sdf"].items()}      # .sdf(): fused value + sweep forward, fused backward
+        xs = x.clone().requires_grad_(True)
+        torch.mean(torch.abs(O.sdf_value(Ps, xs) - tgt)).backward()
+        assert cos_sim(res["fused_sdf"]["dx"], xs.grad) > 0.99
+        check_grads(res_named(res["fused_sdf"]), {k: v.grad for k, v in Ps.items()}, "sdf()", bias_cos=0.98, cos=0.99)
+
+
+def res_named(d):
+    class _P:
+        def __init__(self, g): self.grad = g
+    return [(k, _P(v)) for k, v in d.items() if k.startswith("lin")]
