@@ -194,19 +194,27 @@ def stage1_losses(out, rgb_gt, motion_network, sdf_network, query_time_step, ima
     res = dict(sdf_loss=step_losses(out, rgb_gt, 0.0, 0.0, 1.0, motion=motion)[0], flow_rgb_loss=zero,
                sdf_consistency_loss=zero, flow_fw_pred=None)
     if (use_flow_rgb or use_consistency) and refs[0] > image_idx:
-        if use_consistency and image_idx != world_cam_idx:
-            with torch.set_grad_enabled(consistency_pose_grad and torch.is_grad_enabled()):
-                lo, hi = min(world_cam_idx, image_idx), max(world_cam_idx, image_idx)
-                _, rel = motion_network.compute_relative_camera_pose(lo, hi, total_nb_images, nb_sample_timestep)
-                c2c_w = motion_network.compute_w2c_mappings(rel)[-1]
-                cw2 = rigid_inverse(c2c_w) if world_cam_idx <= image_idx else c2c_w
+        need_cons = use_consistency and image_idx != world_cam_idx
+        # ONE MotionNetwork call + ONE integration launch for every consecutive frame pair that either term needs (the reference
+        # walks the pairs of the reference frames and of the world map in two separate Python loops, train.py:480-483, 498-501)
+        first = min(world_cam_idx, image_idx) if need_cons else image_idx
+        last = refs[nb_valid - 1] if use_flow_rgb else image_idx
+        if need_cons:
+            last = max(last, world_cam_idx, image_idx)
+        _, rel_all = motion_network._relative_poses(first, last, total_nb_images, nb_sample_timestep)
+        if need_cons:
+            lo, hi = min(world_cam_idx, image_idx), max(world_cam_idx, image_idx)
+            rel_w = rel_all[lo - first:hi - first]
+            if not (consistency_pose_grad and torch.is_grad_enabled()):
+                rel_w = rel_w.detach()
+            c2c_w = motion_network.compute_w2c_mappings(rel_w)[-1]
+            cw2 = rigid_inverse(c2c_w) if world_cam_idx <= image_idx else c2c_w
             res["sdf_consistency_loss"] = sdf_consistency_loss(sdf_network, packed_outputs(out)[1][:, :3], out["sdf"], cw2,
                                                                world_time_step)
         if use_flow_rgb:
-            _, c2c = motion_network.compute_relative_camera_pose(image_idx, refs[nb_valid - 1], total_nb_images,
-                                                                 nb_sample_timestep)
+            rel_f = rel_all[image_idx - first:refs[nb_valid - 1] - first]
             sel = torch.as_tensor([r - image_idx for r in refs[:nb_valid]], device=dev)
-            w2c = motion_network.compute_w2c_mappings(c2c)[sel]
+            w2c = motion_network.compute_w2c_mappings(rel_f)[sel]
             wp = weighted_points(out["weights"], packed_outputs(out)[1])
             KS = projection_matrices(scale_mat, ref_camera_mats[:nb_valid])
             res["flow_rgb_loss"], res["flow_fw_pred"] = flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs[:nb_valid], rgb_gt,
