@@ -22,7 +22,7 @@ using namespace chain;
 namespace {
 
 template <int MODE> struct CCfg;
-template <> struct CCfg<CZ_FWD> { static constexpr int kP = 5, kW = 3, kAux = 0, kStg = 0, kBias = COPE_MAX_LIN * 256 * 4; };
+template <> struct CCfg<CZ_FWD> { static constexpr int kP = 5, kW = 4, kAux = 0, kStg = 0, kBias = COPE_MAX_LIN * 256 * 4; };
 template <> struct CCfg<CZ_BWD> { static constexpr int kP = 4, kW = 3, kAux = 4, kStg = 0, kBias = 0; };
 template <int MODE> using CLay = ChainLay<CCfg<MODE>::kP, CCfg<MODE>::kW, CCfg<MODE>::kAux, CCfg<MODE>::kStg, CCfg<MODE>::kBias>;
 
