@@ -35,9 +35,10 @@ template <int MODE> struct Cfg;
 // FWD: measured kW = 2 / kAux = 4 (deeper H-reload prefetch for the reverse sweep, shallower weight ring): 535 instead of 498 us
 template <> struct Cfg<FZ_FWD> { static constexpr int kW = 3, kAux = 2, kStg = 1, kBias = (COPE_MAX_LIN * 256 + 64) * 4; };
 template <> struct Cfg<FZ_TAN> { static constexpr int kW = 2, kAux = 5, kStg = 1, kBias = 0; };
-template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 2, kAux = 6, kStg = 0, kBias = 0; };
-// value-path adjoint (no zb2 tiles to stream): latency-bound on the weight ring, so the freed auxiliary slots go to it
-template <> struct Cfg<FZ_ADJ1> { static constexpr int kW = 3, kAux = 3, kStg = 0, kBias = 0; };
+// ADJ (H + zb2 tiles streamed): measured kW / kAux = 2 / 6: 344 us, 3 / 4: 317 us, 4 / 2: 401 us.  TAN (H + delta): 2 / 5: 351 us, 3 / 3: 415 us
+template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 3, kAux = 4, kStg = 0, kBias = 0; };
+// value-path adjoint (no zb2 tiles to stream): the freed auxiliary slots go to the weight ring (2 / 6: 292 us, 3 / 3: 284 us, 4 / 2: 278 us)
+template <> struct Cfg<FZ_ADJ1> { static constexpr int kW = 4, kAux = 2, kStg = 0, kBias = 0; };
 constexpr bool is_adj(int mode) { return mode == FZ_ADJ || mode == FZ_ADJ1; }
 template <int MODE> using Lay = ChainLay<4, Cfg<MODE>::kW, Cfg<MODE>::kAux, Cfg<MODE>::kStg, Cfg<MODE>::kBias>;
 
