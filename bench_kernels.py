@@ -172,7 +172,7 @@ def main():
 
         def comp_bwd():
             L.call("cope_composite_bwd", sdf, grad, rgb, z, dists, rays_d, dn, var, 0.5, 0, N, S, d_color, d_depth, d_w,
-                   d_sdf, d_grad, d_rgb, d_var, d_rd, st)
+                   None, d_sdf, d_grad, d_rgb, d_var, d_rd, st)
         new_z = f(N, 16)
 
         def ups():

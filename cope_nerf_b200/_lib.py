@@ -73,7 +73,7 @@ _SIGS = {
     "cope_upsample": (_i, [_f, _f, _l, _i, _i, _fl, _f, _f, _f, _f]),
     "cope_merge_z": (_i, [_f, _f, _f, _f, _l, _i, _i, _f, _f, _f]),
     "cope_composite_fwd": (_i, [_f] * 8 + [_fl, _i, _l, _i] + [_f] * 8 + [_f]),
-    "cope_composite_bwd": (_i, [_f] * 8 + [_fl, _i, _l, _i] + [_f] * 8 + [_f]),
+    "cope_composite_bwd": (_i, [_f] * 8 + [_fl, _i, _l, _i] + [_f] * 9 + [_f]),
     "cope_pose_fwd": (_i, [_f, _f, _f, _f, _f]),
     "cope_pose_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f]),
     "cope_raygen_fwd": (_i, [_f, _f, _f, _f, _l, _f, _f, _f, _f]),
@@ -88,6 +88,8 @@ _SIGS = {
     "cope_weighted_points_bwd": (_i, [_f, _f, _f, _l, _i, _f, _f, _f]),
     "cope_flow_rgb_fwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f]),
     "cope_flow_rgb_bwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f, _f]),
+    "cope_patch_smooth_fwd": (_i, [_f, _f, _l, _i, _fl, _fl, _fl, _f, _f, _f]),
+    "cope_patch_smooth_bwd": (_i, [_f, _f, _l, _i, _fl, _fl, _fl, _f, _f, _f]),
     "cope_sample_pixels": (_i, [_f, C.c_uint64, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }
@@ -158,16 +160,26 @@ def query(name, *args):
     return n
 
 
-_scratch = {}
+_scratch = {}      # (device index, stream handle) -> [buffer, replayed_by_a_graph]
+_retired = []      # buffers a captured CUDA graph still writes into: kept alive for the life of the process
 
 
 def scratch(n_floats, device):
-    """Grow-only per-device fp32 scratch (stream-ordered reuse on the current stream)."""
+    """Grow-only fp32 scratch, ONE PER (device, stream): kernels on one stream reuse it in stream order, and two streams of
+    one device (e.g. the per-GPU threads of a DataParallel-style caller, or a CUDA-graph capture stream next to eager work)
+    never share it.  A buffer that was handed out while its stream was being captured is replayed into by that graph for as
+    long as the graph lives, so it is never freed: when a later, larger request outgrows it, it is retired (kept
+    referenced) and a new one is allocated, instead of being released under the graph."""
     if not torch.cuda.is_available():
         raise CopeError("cope_nerf_b200 kernels need a CUDA device (sm_100a); there is no CPU fallback")
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < n_floats:
-        buf = torch.empty(int(n_floats * 1.25) + 1024, dtype=torch.float32, device=device)
-        _scratch[key] = buf
-    return buf
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    ent = _scratch.get(key)
+    if ent is None or ent[0].numel() < n_floats:
+        if ent is not None and ent[1]:
+            _retired.append(ent[0])
+        ent = [torch.empty(int(n_floats * 1.25) + 1024, dtype=torch.float32, device=device), False]
+        _scratch[key] = ent
+    if torch.cuda.is_current_stream_capturing():
+        ent[1] = True
+    return ent[0]

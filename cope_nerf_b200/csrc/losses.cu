@@ -332,6 +332,96 @@ __global__ void __launch_bounds__(kLossThreads) flow_rgb_bwd_kernel(const FlowRg
   if (n < a.N && d_wp) d_wp[n] = dwp;
 }
 
+
+// ------------------------------------------------------------------------------------------------ depth-patch smoothness
+// model/losses.py:7-38 on ps x ps patches of depth_pred (train.py:519-525): four neighbour differences per patch
+//   D1 (r,c)-(r,c+1)   D2 (r,c)-(r+1,c)   D3 (r,c)-(r+1,c+1)   D4 (r+1,c)-(r,c+1)
+// smooth = mean_k mean|D_k|, edge = mean_k mean(w_k |D_k|) with the bilateral weight w_k = exp(-sum_c |rgb diff_k| / gamma).
+// One thread per patch.  ws: [0..3] sum |D_k|, [4..7] sum w_k |D_k|, [8] block counter.
+constexpr int kMaxPatch = 8;
+struct PatchArgs {
+  const float* depth;      // [n x ps x ps]
+  const float* rgb;        // [n x ps x ps x 3] (null: no edge-aware term)
+  int64_t n; int ps; float inv_gamma, w_edge, w_smooth;
+};
+__device__ __forceinline__ void patch_pair(int k, int r, int c, int ps, int* i0, int* i1) {
+  // element indices (inside the patch) of the minuend / subtrahend of difference k at position (r, c)
+  switch (k) {
+    case 0: *i0 = r * ps + c; *i1 = r * ps + c + 1; break;
+    case 1: *i0 = r * ps + c; *i1 = (r + 1) * ps + c; break;
+    case 2: *i0 = r * ps + c; *i1 = (r + 1) * ps + c + 1; break;
+    default: *i0 = (r + 1) * ps + c; *i1 = r * ps + c + 1; break;
+  }
+}
+__device__ __forceinline__ float bilateral(const float* rgb, int i0, int i1, float inv_gamma) {
+  const float d = fabsf(rgb[i0 * 3] - rgb[i1 * 3]) + fabsf(rgb[i0 * 3 + 1] - rgb[i1 * 3 + 1]) + fabsf(rgb[i0 * 3 + 2] - rgb[i1 * 3 + 2]);
+  return __expf(-d * inv_gamma);
+}
+__global__ void __launch_bounds__(kLossThreads) patch_smooth_fwd_kernel(const PatchArgs a, float* __restrict__ ws,
+                                                                       float* __restrict__ losses) {
+  __shared__ float sh[8 * 8];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int ps = a.ps, pp = ps * ps;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    const float* d = a.depth + n * pp;
+    const float* rgb = a.rgb ? a.rgb + n * pp * 3 : nullptr;
+    for (int k = 0; k < 4; ++k) {
+      const int R = (k == 0) ? ps : ps - 1, Cn = (k == 1) ? ps : ps - 1;
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < Cn; ++c) {
+          int i0, i1;
+          patch_pair(k, r, c, ps, &i0, &i1);
+          const float ad = fabsf(d[i0] - d[i1]);
+          acc[k] += ad;
+          if (rgb) acc[4 + k] += bilateral(rgb, i0, i1, a.inv_gamma) * ad;
+        }
+    }
+  }
+  block_sum<8>(acc, sh);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (acc[k] != 0.0f) atomicAdd(ws + k, acc[k]);
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned*>(ws + 8), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* v = ws;
+    const float c_a = 1.0f / ((float)a.n * (float)(ps * (ps - 1))), c_b = 1.0f / ((float)a.n * (float)((ps - 1) * (ps - 1)));
+    const float smooth = 0.25f * ((v[0] + v[1]) * c_a + (v[2] + v[3]) * c_b);
+    const float edge = 0.25f * ((v[4] + v[5]) * c_a + (v[6] + v[7]) * c_b);
+    losses[0] = a.w_edge * edge + a.w_smooth * smooth;
+    losses[1] = edge; losses[2] = smooth;
+  }
+}
+__global__ void __launch_bounds__(kLossThreads) patch_smooth_bwd_kernel(const PatchArgs a, const float* __restrict__ g_ptr,
+                                                                       float* __restrict__ d_depth) {
+  const float g = g_ptr ? *g_ptr : 1.0f;
+  const int ps = a.ps, pp = ps * ps;
+  const float c_a = 0.25f * g / ((float)a.n * (float)(ps * (ps - 1))), c_b = 0.25f * g / ((float)a.n * (float)((ps - 1) * (ps - 1)));
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    const float* d = a.depth + n * pp;
+    const float* rgb = a.rgb ? a.rgb + n * pp * 3 : nullptr;
+    float* o = d_depth + n * pp;                 // each patch is owned by one thread: plain read-modify-write
+    for (int i = 0; i < pp; ++i) o[i] = 0.0f;
+    for (int k = 0; k < 4; ++k) {
+      const int R = (k == 0) ? ps : ps - 1, Cn = (k == 1) ? ps : ps - 1;
+      const float ck = k < 2 ? c_a : c_b;
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < Cn; ++c) {
+          int i0, i1;
+          patch_pair(k, r, c, ps, &i0, &i1);
+          const float w = a.w_smooth + (rgb ? a.w_edge * bilateral(rgb, i0, i1, a.inv_gamma) : 0.0f);
+          const float t = ck * w * signf_(d[i0] - d[i1]);
+          o[i0] += t; o[i1] -= t;
+        }
+    }
+  }
+}
+
 static inline unsigned loss_grid(int64_t n) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kLossThreads), 148 * 8));
 }
@@ -409,6 +499,28 @@ int cope_flow_rgb_bwd(const float* wp, const float* w2c, const float* KS, const 
   flow_rgb_bwd_kernel<<<(unsigned)ceil_div(N, kLossThreads), kLossThreads, 0, as_stream(s)>>>(a, ws, g, reinterpret_cast<float4*>(d_wp),
                                                                                               d_w2c);
   COPE_CHECK_LAUNCH("flow_rgb_bwd");
+  return 0;
+}
+
+int cope_patch_smooth_fwd(const float* depth, const float* rgb, int64_t n_patches, int ps, float gamma, float w_edge,
+                          float w_smooth, float* losses, float* ws, cope_stream_t s) {
+  COPE_REQUIRE(ps >= 2 && ps <= kMaxPatch, "patch_smooth: patch size %d outside [2, %d]", ps, kMaxPatch);
+  COPE_REQUIRE(gamma > 0.0f, "patch_smooth: gamma must be positive");
+  cudaMemsetAsync(ws, 0, 12 * sizeof(float), as_stream(s));
+  if (n_patches <= 0) { cudaMemsetAsync(losses, 0, 3 * sizeof(float), as_stream(s)); return 0; }
+  PatchArgs a{depth, rgb, n_patches, ps, 1.0f / gamma, w_edge, w_smooth};
+  patch_smooth_fwd_kernel<<<loss_grid(n_patches), kLossThreads, 0, as_stream(s)>>>(a, ws, losses);
+  COPE_CHECK_LAUNCH("patch_smooth_fwd");
+  return 0;
+}
+
+int cope_patch_smooth_bwd(const float* depth, const float* rgb, int64_t n_patches, int ps, float gamma, float w_edge,
+                          float w_smooth, const float* g, float* d_depth, cope_stream_t s) {
+  COPE_REQUIRE(ps >= 2 && ps <= kMaxPatch, "patch_smooth: patch size %d outside [2, %d]", ps, kMaxPatch);
+  if (n_patches <= 0) return 0;
+  PatchArgs a{depth, rgb, n_patches, ps, 1.0f / gamma, w_edge, w_smooth};
+  patch_smooth_bwd_kernel<<<loss_grid(n_patches), kLossThreads, 0, as_stream(s)>>>(a, g, d_depth);
+  COPE_CHECK_LAUNCH("patch_smooth_bwd");
   return 0;
 }
 

@@ -355,6 +355,13 @@ static bool fused_enabled(const MlpShape& m, const SdfB& b, const char* pass) {
   if (e && (strstr(e, pass) || strstr(e, "all") || !strcmp(e, "1"))) return false;
   return b.LD == 256 && sdf_fused_supported(m);
 }
+// true when the inference forward (sdf_fwd_bf16 with infer) runs on the fused chain and therefore never writes the delta
+// stack: only then may the caller size the saved block with with_grad = 0 (the layer-by-layer fallback still stores delta_l)
+bool sdf_infer_compact_bf16(const MlpShape& m) {
+  SdfB b;
+  if (make_sdfb(m, &b)) return false;
+  return fused_enabled(m, b, "fwd");
+}
 static void fz_common(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P, FzArgs* a) {
   a->P = P; a->x = x; a->Wflat = Wflat; a->wp = wp;
   a->n_lin = m.n_lin; a->skip = m.skip; a->skw = b.skw; a->pe_w = m.pe_w; a->d_in = m.d_in; a->L = m.L;

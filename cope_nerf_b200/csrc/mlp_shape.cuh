@@ -45,6 +45,7 @@ inline int make_shape(const cope_mlp_desc* d, MlpShape* s) {
 // bf16 tcgen05 implementations (mlp_bf16.cu); same contracts as the C entry points of include/cope_b200.h
 int64_t sdf_saved_floats_bf16(const MlpShape& m, int64_t P, int with_grad);
 int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P);
+bool sdf_infer_compact_bf16(const MlpShape& m);
 int64_t sdf_query_ws_floats_bf16(const MlpShape& m, int64_t P);
 int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s,
                    bool ws_holds_pack = false);

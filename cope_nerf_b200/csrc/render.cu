@@ -396,8 +396,9 @@ composite_fwd_kernel(const CompositeIn a, float* __restrict__ weights, float* __
 template <int MAXC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(const CompositeIn a, const float* __restrict__ d_color, const float* __restrict__ d_depth,
-                     const float* __restrict__ d_weights, float* __restrict__ d_sdf, float4* __restrict__ d_grad,
-                     float* __restrict__ d_rgb, float* __restrict__ d_variance, float* __restrict__ d_rays_d) {
+                     const float* __restrict__ d_weights, const float4* d_grad_in, float* __restrict__ d_sdf,
+                     float4* d_grad, float* __restrict__ d_rgb, float* __restrict__ d_variance,
+                     float* __restrict__ d_rays_d) {
   int lane = threadIdx.x & 31;
   int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (n >= a.N) return;
@@ -466,7 +467,9 @@ composite_bwd_kernel(const CompositeIn a, const float* __restrict__ d_color, con
       d_sdf[base + j] = dep + den_;
       float dic = (den_ - dep) * dist * 0.5f;
       float dtc = dic * (((-t * 0.5f + 0.5f) > 0.0f ? 0.5f * (1.0f - r) : 0.0f) + ((-t) > 0.0f ? r : 0.0f));
-      float4 og = d_grad[base + j];
+      // write-only unless the caller has upstream gradients of normals / sdf_flows (d_grad_in may alias d_grad: each
+      // element is read and written by the same thread)
+      float4 og = d_grad_in ? d_grad_in[base + j] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       og.x += dtc * dir.x; og.y += dtc * dir.y; og.z += dtc * dir.z;
       d_grad[base + j] = og;
       ddx += dtc * g.x; ddy += dtc * g.y; ddz += dtc * g.z;
@@ -570,18 +573,20 @@ int cope_composite_fwd(const float* sdf, const float* grad, const float* rgb, co
 int cope_composite_bwd(const float* sdf, const float* grad, const float* rgb, const float* z, const float* dists,
                        const float* rays_d, const float* rays_d_norm, const float* variance, float cos_anneal,
                        int eval_mode, int64_t N, int S, const float* d_color, const float* d_depth,
-                       const float* d_weights, float* d_sdf, float* d_grad, float* d_rgb, float* d_variance,
-                       float* d_rays_d, cope_stream_t s) {
+                       const float* d_weights, const float* d_grad_in, float* d_sdf, float* d_grad, float* d_rgb,
+                       float* d_variance, float* d_rays_d, cope_stream_t s) {
   COPE_REQUIRE(S >= 1 && S <= 256, "composite: S=%d outside [1,256]", S);
   if (N <= 0) return 0;
   CompositeIn a{sdf, reinterpret_cast<const float4*>(grad), rgb, z, dists, rays_d, rays_d_norm, variance,
                 cos_anneal, eval_mode, N, S};
   if (S <= 128)
     composite_bwd_kernel<4><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(
-        a, d_color, d_depth, d_weights, d_sdf, reinterpret_cast<float4*>(d_grad), d_rgb, d_variance, d_rays_d);
+        a, d_color, d_depth, d_weights, reinterpret_cast<const float4*>(d_grad_in), d_sdf, reinterpret_cast<float4*>(d_grad),
+        d_rgb, d_variance, d_rays_d);
   else
     composite_bwd_kernel<8><<<grid_rays(N), kWarpsPerBlock * 32, 0, as_stream(s)>>>(
-        a, d_color, d_depth, d_weights, d_sdf, reinterpret_cast<float4*>(d_grad), d_rgb, d_variance, d_rays_d);
+        a, d_color, d_depth, d_weights, reinterpret_cast<const float4*>(d_grad_in), d_sdf, reinterpret_cast<float4*>(d_grad),
+        d_rgb, d_variance, d_rays_d);
   COPE_CHECK_LAUNCH("composite_bwd");
   return 0;
 }

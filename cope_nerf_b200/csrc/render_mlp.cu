@@ -46,9 +46,18 @@ int cope_render_mlp_fwd(const cope_mlp_desc* sd, const float* sdfW, const cope_m
 }
 
 /* ---- inference: same outputs as cope_render_mlp_fwd, nothing kept for a backward pass (full-image rendering, eval.py) */
+// saved-block size of the inference forward: H only (no delta stack) exactly when the bf16 forward runs on the fused chain;
+// the layer-by-layer fallback (COPE_NO_FUSED, or a shape sdf_fused_supported rejects) still writes delta_l behind H
+static int64_t infer_sdf_saved_floats(const cope_mlp_desc* sd, int64_t P, int prec) {
+  MlpShape ms;
+  if (make_shape(sd, &ms)) return -1;
+  const int compact = prec == COPE_PREC_BF16 && sdf_infer_compact_bf16(ms);
+  return cope_sdf_saved_floats(sd, P, compact ? 0 : 1, prec);
+}
+
 int64_t cope_render_mlp_infer_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
   const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
-  const int64_t a = cope_sdf_saved_floats(sd, P, prec == COPE_PREC_BF16 ? 0 : 1, prec), b = cope_color_saved_floats(cd, P, prec);
+  const int64_t a = infer_sdf_saved_floats(sd, P, prec), b = cope_color_saved_floats(cd, P, prec);
   if (w < 0 || a < 0 || b < 0) return -1;
   return w + a + b + 256;
 }
@@ -60,7 +69,7 @@ int cope_render_mlp_infer(const cope_mlp_desc* sd, const float* sdfW, const cope
   if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
   if (P <= 0) return 0;
   const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
-  const int64_t a = cope_sdf_saved_floats(sd, P, prec == COPE_PREC_BF16 ? 0 : 1, prec);
+  const int64_t a = infer_sdf_saved_floats(sd, P, prec);
   COPE_REQUIRE(w >= 0 && a >= 0, "render_mlp_infer: unsupported network shape");
   float* sdf_saved = ws + ((w + 63) / 64) * 64;
   float* col_saved = sdf_saved + ((a + 63) / 64) * 64;

@@ -45,24 +45,52 @@ def shard_range(n_rays, rank, world, align=16):
 
 class FlatGradBucket:
     """All parameter gradients live in ONE flat fp32 buffer (p.grad are views), so the data-parallel exchange is a
-    single all-reduce of ~4 MB (1,003,155 floats for SDF + colour + variance + motion)."""
+    single all-reduce of ~4 MB (1,003,155 floats for SDF + colour + variance + motion).
+
+    Build it ONCE, before the training loop, and clear gradients with `bucket.zero_()` (or
+    `optimizer.zero_grad(set_to_none=False)`) — NOT with the default `optimizer.zero_grad()`: set_to_none=True drops the
+    views, autograd then allocates fresh `.grad` tensors outside the bucket and the all-reduce would exchange a stale
+    buffer.  `allreduce_()` checks this and re-attaches (copying the stray gradients in) rather than exchanging garbage.
+    Gradients that already exist at construction are copied into the bucket, not discarded."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._attach()
+
+    def _views(self):
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            yield p, self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+    def _attach(self):
+        """Point every p.grad at its slice of the flat buffer; a gradient that lives elsewhere is copied in first.
+        Returns the number of parameters that had to be re-attached."""
+        moved = 0
+        for p, view in self._views():
+            g = p.grad
+            if g is not None and g.data_ptr() == view.data_ptr() and g.shape == view.shape:
+                continue
+            with torch.no_grad():
+                if g is not None:
+                    view.copy_(g)
+                else:
+                    view.zero_()
+            p.grad = view
+            moved += 1
+        return moved
+
     def zero_(self):
+        self._attach()
         self.flat.zero_()
 
     def allreduce_(self, average=False):
         """Sum (or mean) over ranks, in place.  Local losses must already carry the 1/world factor of any
         shard-linear term (rgb: sum/N, eikonal: mean over points)."""
+        self._attach()      # no-op when every p.grad is still the bucket's view (the normal case)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             if average:

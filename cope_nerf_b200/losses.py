@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["step_losses", "packed_outputs", "weighted_points", "flow_rgb_loss", "sdf_consistency_loss", "projection_matrices", "rigid_inverse",
-           "stage1_losses"]
+           "stage1_losses", "depth_smoothness_losses", "SmoothnessLoss", "EdgePreservingSmoothnessLoss"]
 
 
 def _f32(*shape, device):
@@ -156,6 +156,69 @@ def flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt, return_flow=Fals
     return (loss, flow) if return_flow else loss
 
 
+# ------------------------------------------------------------------------------------------------ depth-patch smoothness
+class _PatchSmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, rgb, ps, gamma, w_edge, w_smooth):
+        depth = depth.contiguous().float()
+        n = depth.numel() // (ps * ps)
+        if depth.numel() != n * ps * ps:
+            raise L.CopeError(f"depth smoothness: {depth.numel()} depths do not form {ps} x {ps} patches")
+        rgb = rgb.contiguous().float() if rgb is not None else None
+        dev = depth.device
+        losses, ws = _f32(3, device=dev), _f32(12, device=dev)
+        L.call("cope_patch_smooth_fwd", L.ptr(depth), L.ptr(rgb), n, ps, float(gamma), float(w_edge), float(w_smooth),
+               L.ptr(losses), L.ptr(ws), L.stream())
+        ctx.save_for_backward(depth, *([rgb] if rgb is not None else []))
+        ctx.cfg = (n, ps, float(gamma), float(w_edge), float(w_smooth))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _unused=None):
+        if g is None:
+            return (None,) * 6
+        depth = ctx.saved_tensors[0]
+        rgb = ctx.saved_tensors[1] if len(ctx.saved_tensors) > 1 else None
+        n, ps, gamma, w_edge, w_smooth = ctx.cfg
+        d_depth = torch.empty_like(depth)
+        L.call("cope_patch_smooth_bwd", L.ptr(depth), L.ptr(rgb), n, ps, gamma, w_edge, w_smooth, L.ptr(g.reshape(1).float()),
+               L.ptr(d_depth), L.stream())
+        return d_depth, None, None, None, None, None
+
+
+def depth_smoothness_losses(depth_pred, rgb_gt, patch_size, edge_weight=1.0, smooth_weight=0.0, gamma=0.1):
+    """train.py:519-525 in one launch each way: depth_pred [N,1] and rgb_gt [N,3] are viewed as patch_size x patch_size
+    patches (the rays of `process_data` are patch-major).  Returns (edge_weight * edge + smooth_weight * smooth,
+    parts = [total, edge, smooth]) with edge = EdgePreservingSmoothnessLoss(depth, rgb) (model/losses.py:20-38) and
+    smooth = SmoothnessLoss(depth) (model/losses.py:7-18); the reference's 1 / 2**s factor belongs in the weights."""
+    return _PatchSmoothFn.apply(depth_pred, rgb_gt, int(patch_size), gamma, edge_weight, smooth_weight)
+
+
+class SmoothnessLoss(torch.nn.Module):
+    """model/losses.py:7-18 (same constructor and call signature): inputs [n, ps, ps, 1]."""
+
+    def __init__(self, patch_size):
+        super().__init__()
+        self.patch_size = patch_size
+
+    def forward(self, inputs):
+        return _PatchSmoothFn.apply(inputs, None, inputs.shape[1], 0.1, 0.0, 1.0)[0]
+
+
+class EdgePreservingSmoothnessLoss(torch.nn.Module):
+    """model/losses.py:20-38: inputs [n, ps, ps, 1], weights (the target colours) [n, ps, ps, 3]."""
+
+    def __init__(self, patch_size, bilateral_gamma=0.1):
+        super().__init__()
+        self.patch_size = patch_size
+        self.gamma = bilateral_gamma
+
+    def forward(self, inputs, weights):
+        return _PatchSmoothFn.apply(inputs, weights, inputs.shape[1], self.gamma, 1.0, 0.0)[0]
+
+
 # ------------------------------------------------------------------------------------------------ SDF consistency
 def sdf_consistency_loss(sdf_network, pts, sdf, cw2, world_time_step):
     """train.py:496-505: map the sampled points into the world frame with the rigid map cw2 [4,4], query the SDF there at
@@ -178,21 +241,25 @@ def rigid_inverse(m):
 
 def stage1_losses(out, rgb_gt, motion_network, sdf_network, query_time_step, image_idx, ref_image_idx_list, nb_valid,
                   total_nb_images, nb_sample_timestep, ref_camera_mats, scale_mat, norm_pix, pix, ref_imgs, world_cam_idx,
-                  world_time_step, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True):
+                  world_time_step, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True, include_sdf_loss=True):
     """The `not query_in_canonical_space` branch of train.py:467-517 on a NeuSRenderer output dict: SDF-flow loss,
     flow-RGB loss over the valid reference frames and SDF-consistency loss.  Same control flow and argument meaning as the
     reference (image / reference indices, number of valid next time steps, world camera / time step); the per-sample
     arithmetic runs in cope_step_losses_*, cope_weighted_points_*, cope_flow_rgb_* and the SDF kernels.
+    `out` may come from `NeuSRenderer.forward` or from `NeuSRenderer.forward_losses`: both keep weights / sampled_points /
+    sdf differentiable, so the flow-RGB and consistency terms back-propagate into the renderer as in the reference.  With
+    `forward_losses(..., sdf_weight=w, motion=...)` the SDF-flow term is already inside the fused node: pass
+    include_sdf_loss=False so it is not evaluated (and not counted) a second time.
     Returns dict(sdf_loss, flow_rgb_loss, sdf_consistency_loss, flow_fw_pred [T,N,2] or None)."""
     dev = rgb_gt.device
     image_idx = int(image_idx)
     refs = [int(r) for r in ref_image_idx_list]
-    tq = torch.as_tensor([float(query_time_step)], dtype=torch.float32, device=dev).view(-1, 1)
-    ang, vel = motion_network(tq)
-    motion = torch.cat([ang, vel], dim=1)
     zero = torch.zeros((), dtype=torch.float32, device=dev)
-    res = dict(sdf_loss=step_losses(out, rgb_gt, 0.0, 0.0, 1.0, motion=motion)[0], flow_rgb_loss=zero,
-               sdf_consistency_loss=zero, flow_fw_pred=None)
+    res = dict(sdf_loss=zero, flow_rgb_loss=zero, sdf_consistency_loss=zero, flow_fw_pred=None)
+    if include_sdf_loss:
+        tq = torch.as_tensor([float(query_time_step)], dtype=torch.float32, device=dev).view(-1, 1)
+        ang, vel = motion_network(tq)
+        res["sdf_loss"] = step_losses(out, rgb_gt, 0.0, 0.0, 1.0, motion=torch.cat([ang, vel], dim=1))[0]
     if (use_flow_rgb or use_consistency) and refs[0] > image_idx:
         need_cons = use_consistency and image_idx != world_cam_idx
         # ONE MotionNetwork call + ONE integration launch for every consecutive frame pair that either term needs (the reference

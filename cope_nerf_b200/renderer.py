@@ -81,29 +81,31 @@ def _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm
     return (color, depth, grad, weights, sdf, pts, wz, cdf, wsum, wmax, inv_s, dists, mid_z), saved
 
 
-def _core_backward(rnd, cfg, saved, need_rays, need_var, d_color, d_depth, d_grad, d_weights, d_sdf_up, d_pts):
+def _core_backward(rnd, cfg, saved, need_rays, need_var, d_color, d_depth, d_grad_in, d_weights, d_sdf_up, d_pts):
     """render_core backward: compositing -> colour net -> SDF net (first + second order) -> rays.
-    d_grad [P,4] / d_pts [P,4] are buffers OWNED by the caller's backward (accumulated into here), or None."""
+    Upstream gradients (each may be None): d_color [N,3], d_depth [N,1], d_grad_in [P,4] (normals | sdf_flows, read only),
+    d_weights [N,S], d_sdf_up [P,1]; d_pts [P,4] is a buffer OWNED by the caller's backward (accumulated into here)."""
     (sdf_flat, col_flat, variance, rays_d, rays_d_norm, z, dists, mid_z, pts, sdf, grad, rgb, sdf_saved, col_saved) = saved
     sdf_net, col_net = rnd.sdf_network, rnd.color_network
     N, S, n_coarse, cos_anneal, eval_mode = cfg
     P, dev, s = N * S, z.device, L.stream()
     prec_s = sdf_net.precision
-    if d_grad is None:
-        d_grad = torch.zeros(P, 4, dtype=torch.float32, device=dev)
+    d_grad = _f32(P, 4, device=dev)           # written (not accumulated) by cope_composite_bwd: no zero fill
     d_sdf, d_rgb = _f32(P, 1, device=dev), _f32(P, 3, device=dev)
-    d_var = torch.zeros(1, dtype=torch.float32, device=dev)
     d_rays_d = _f32(N, 3, device=dev)
-    cg = lambda t: L.ptr(t.contiguous()) if t is not None else None
+    # one zero-filled arena for everything the kernels accumulate into: d_variance | dW_colour | dW_sdf (one fill launch)
+    n_c, n_s = col_flat.numel(), sdf_flat.numel()
+    o_s = 64 + (n_c + 63) // 64 * 64           # every block 256-byte aligned (the weight-gradient kernels use 16-byte reductions)
+    arena = torch.zeros(o_s + n_s, dtype=torch.float32, device=dev)
+    d_var, d_col_flat, d_sdf_flat = arena[:1], arena[64:64 + n_c].view_as(col_flat), arena[o_s:].view_as(sdf_flat)
+    cg = lambda t: L.ptr(t.contiguous().float()) if t is not None else None
     L.call("cope_composite_bwd", L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(z), L.ptr(dists), L.ptr(rays_d),
            L.ptr(rays_d_norm), L.ptr(variance), cos_anneal, eval_mode, N, S, cg(d_color),
-           cg(d_depth), cg(d_weights), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb), L.ptr(d_var), L.ptr(d_rays_d), s)
+           cg(d_depth), cg(d_weights), cg(d_grad_in), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb), L.ptr(d_var), L.ptr(d_rays_d), s)
     if d_sdf_up is not None:
-        d_sdf = d_sdf + d_sdf_up.reshape(P, 1)
+        d_sdf.add_(d_sdf_up.reshape(P, 1))
 
     ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
-    d_col_flat = torch.zeros_like(col_flat)
-    d_sdf_flat = torch.zeros_like(sdf_flat)
     d_dirs_pp = None
     if need_rays:
         if d_pts is None:
@@ -142,11 +144,10 @@ class _RenderCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_color, d_depth, d_grad4, d_weights, d_sdf_up, d_pts4, *unused):
         need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
-        # the core accumulates into these: never into autograd's own buffers
-        d_grad = d_grad4.contiguous().clone() if d_grad4 is not None else None
+        # the core accumulates into d_pts: never into autograd's own buffer (d_grad4 is only read)
         d_pts = d_pts4.contiguous().clone() if (d_pts4 is not None and need_rays) else None
         d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d = _core_backward(
-            ctx.rnd, ctx.cfg, ctx.saved_tensors, need_rays, ctx.needs_input_grad[3], d_color, d_depth, d_grad, d_weights,
+            ctx.rnd, ctx.cfg, ctx.saved_tensors, need_rays, ctx.needs_input_grad[3], d_color, d_depth, d_grad4, d_weights,
             d_sdf_up, d_pts)
         return (None, d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d, None, None, None, None, None, None,
                 None, None)
@@ -155,9 +156,14 @@ class _RenderCoreFn(torch.autograd.Function):
 class _RenderStepFn(torch.autograd.Function):
     """render_core AND the step's loss reductions as one autograd node (the fused training path): forward =
     _core_forward + cope_step_losses_fwd, backward = cope_step_losses_bwd + _core_backward.  No per-sample tensor
-    crosses autograd, and the ~60 elementwise launches of the torch loss expressions become two.
+    crosses autograd for the fused terms, and the ~60 elementwise launches of the torch loss expressions become two.
     Losses: rgb L1 (model/training.py:508), eikonal (train.py:526) and, with `motion` = (angular velocity | velocity)
-    [6], the SDF-flow loss (train.py:467-477).  Returns (total, parts[4] = total / rgb / eikonal / sdf-flow, *core outputs)."""
+    [6], the SDF-flow loss (train.py:467-477).  Returns (total, parts[4] = total / rgb / eikonal / sdf-flow, *core outputs).
+
+    The six differentiable core outputs (color, depth, grad4 = normals | sdf_flows, weights, sdf, pts4) stay differentiable:
+    a loss built on them OUTSIDE the node (the flow-RGB term on weights / sampled_points, the SDF-consistency term on sdf, the
+    depth-smoothness terms on depth_pred — train.py:488-525) sends its gradient into the same backward, where it is added to
+    the fused terms' gradients before the one compositing / MLP backward pass."""
 
     @staticmethod
     def forward(ctx, rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far,
@@ -179,11 +185,11 @@ class _RenderStepFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.motion_shape = motion.shape if motion is not None else None
         total = losses[0].clone()                 # a differentiable output must not alias the non-differentiable parts
-        ctx.mark_non_differentiable(losses, *outs)
+        ctx.mark_non_differentiable(losses, *outs[6:])    # wz, cdf, wsum, wmax, inv_s, dists, mid_z
         return (total, losses, *outs)
 
     @staticmethod
-    def backward(ctx, g_total, *unused):
+    def backward(ctx, g_total, _g_parts, d_color_up, d_depth, d_grad4_up, d_weights, d_sdf_up, d_pts4_up, *unused):
         n_saved = 14
         saved = ctx.saved_tensors[:n_saved]
         color, weights, rgb_gt, coef = ctx.saved_tensors[n_saved:n_saved + 4]
@@ -193,16 +199,25 @@ class _RenderStepFn(torch.autograd.Function):
         need_rays = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
         grad4, pts4 = saved[10], saved[8]
         n_in = 19
-        if g_total is None:
+        if all(g is None for g in (g_total, d_color_up, d_depth, d_grad4_up, d_weights, d_sdf_up, d_pts4_up)):
             return (None,) * n_in
-        d_color, d_grad = _f32(N, 3, device=dev), _f32(P, 4, device=dev)
-        d_pts = _f32(P, 4, device=dev) if (need_rays and mot is not None) else None
-        d_motion = torch.zeros(6, dtype=torch.float32, device=dev) if (mot is not None and ctx.needs_input_grad[14]) else None
-        L.call("cope_step_losses_bwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4) if mot is not None else None,
-               L.ptr(weights) if mot is not None else None, L.ptr(mot), N, P, L.ptr(coef),
-               L.ptr(g_total.reshape(1).float()), L.ptr(d_color), L.ptr(d_grad), L.ptr(d_pts), L.ptr(d_motion), L.stream())
+        d_color = d_grad = d_pts = d_motion = None
+        if g_total is not None:
+            d_color, d_grad = _f32(N, 3, device=dev), _f32(P, 4, device=dev)
+            d_pts = _f32(P, 4, device=dev) if (need_rays and mot is not None) else None
+            d_motion = torch.zeros(6, dtype=torch.float32, device=dev) if (mot is not None and ctx.needs_input_grad[14]) else None
+            L.call("cope_step_losses_bwd", L.ptr(color), L.ptr(rgb_gt), L.ptr(grad4), L.ptr(pts4) if mot is not None else None,
+                   L.ptr(weights) if mot is not None else None, L.ptr(mot), N, P, L.ptr(coef),
+                   L.ptr(g_total.reshape(1).float()), L.ptr(d_color), L.ptr(d_grad), L.ptr(d_pts), L.ptr(d_motion), L.stream())
+        # gradients that arrive from losses built outside the node on the differentiable outputs
+        if d_color_up is not None:
+            d_color = d_color_up if d_color is None else d_color.add_(d_color_up)
+        if d_grad4_up is not None:
+            d_grad = d_grad4_up if d_grad is None else d_grad.add_(d_grad4_up)
+        if d_pts4_up is not None and need_rays:
+            d_pts = d_pts4_up.contiguous().clone() if d_pts is None else d_pts.add_(d_pts4_up)
         d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d = _core_backward(
-            ctx.rnd, ctx.cfg, saved, need_rays, ctx.needs_input_grad[3], d_color, None, d_grad, None, None, d_pts)
+            ctx.rnd, ctx.cfg, saved, need_rays, ctx.needs_input_grad[3], d_color, d_depth, d_grad, d_weights, d_sdf_up, d_pts)
         if d_motion is not None:
             d_motion = d_motion.reshape(ctx.motion_shape)
         return (None, d_sdf_flat, d_col_flat, d_variance, d_rays_o, d_rays_d, None, None, None, None, None, None, None,

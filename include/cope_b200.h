@@ -186,16 +186,17 @@ int cope_composite_fwd(const float* sdf, const float* grad, const float* rgb, co
                        const float* variance, float cos_anneal, int eval_mode, int64_t N, int S,
                        float* weights, float* color, float* depth, float* weighted_z, float* cdf, float* wsum,
                        float* wmax, float* inv_s_out, cope_stream_t s);
-/* Upstream: d_color [N x 3], d_depth [N], d_weights [N x S] (any may be NULL = zero).
- * Outputs: d_sdf [P] OVERWRITTEN, d_grad [P x 4] ACCUMULATED (caller pre-fills with the upstream grads of
- * `normals` / `sdf_flows`), d_rgb [P x 3] OVERWRITTEN, d_variance [1] ACCUMULATED,
+/* Upstream: d_color [N x 3], d_depth [N], d_weights [N x S], d_grad_in [P x 4] = upstream gradients of
+ * `normals` / `sdf_flows` (any may be NULL = zero; d_grad_in may alias d_grad).
+ * Outputs: d_sdf [P] OVERWRITTEN, d_grad [P x 4] OVERWRITTEN (= d_grad_in + the true_cos term: no pre-fill, no
+ * read-modify-write when there is no upstream gradient), d_rgb [P x 3] OVERWRITTEN, d_variance [1] ACCUMULATED,
  * d_rays_d [N x 3] OVERWRITTEN (the true_cos term). */
 int cope_composite_bwd(const float* sdf, const float* grad, const float* rgb, const float* z,
                        const float* dists, const float* rays_d, const float* rays_d_norm,
                        const float* variance, float cos_anneal, int eval_mode, int64_t N, int S,
                        const float* d_color, const float* d_depth,
-                       const float* d_weights, float* d_sdf, float* d_grad, float* d_rgb, float* d_variance,
-                       float* d_rays_d, cope_stream_t s);
+                       const float* d_weights, const float* d_grad_in, float* d_sdf, float* d_grad, float* d_rgb,
+                       float* d_variance, float* d_rays_d, cope_stream_t s);
 
 /* ---- pose + ray generation (poses_retriever.py:25-32, common.py:175-215,255-308, training.py:474-487) */
 /* c2w [4x4] = make_c2w(r, t) @ init_c2w   (r, t, init_c2w: device pointers to one camera's entries) */
@@ -282,6 +283,16 @@ int cope_flow_rgb_fwd(const float* wp, const float* w2c, const float* KS, const 
 int cope_flow_rgb_bwd(const float* wp, const float* w2c, const float* KS, const float* norm_pix, const float* pix,
                       const float* ref_imgs, const float* rgb_gt, int64_t N, int T, int H, int W, const float* ws, const float* g,
                       float* d_wp, float* d_w2c, cope_stream_t s);
+
+/* ---- depth-patch smoothness (model/losses.py:7-18 SmoothnessLoss, :20-38 EdgePreservingSmoothnessLoss; called on
+ * depth_pred.view(-1, ps, ps, 1) and rgb_gt.view(-1, ps, ps, 3) at train.py:519-525) ------------------------------------
+ * depth [n_patches x ps x ps], rgb [n_patches x ps x ps x 3] (NULL: no edge-aware term), 2 <= ps <= 8.
+ * losses[3] = { w_edge * edge + w_smooth * smooth, edge, smooth }; ws: 12 floats of scratch.  The backward OVERWRITES
+ * d_depth [n_patches x ps x ps] with g[0] * d losses[0] / d depth (g: device scalar, NULL = 1). */
+int cope_patch_smooth_fwd(const float* depth, const float* rgb, int64_t n_patches, int ps, float gamma, float w_edge,
+                          float w_smooth, float* losses, float* ws, cope_stream_t s);
+int cope_patch_smooth_bwd(const float* depth, const float* rgb, int64_t n_patches, int ps, float gamma, float w_edge,
+                          float w_smooth, const float* g, float* d_depth, cope_stream_t s);
 
 /* ---- training-pixel selection (process_data, model/training.py:413-471; arange_pixels, model/common.py:12-39) ----------
  * n_patches patch_size x patch_size patches of an h x w frame -> N = n_patches * patch_size^2 rays, row-major inside each patch:

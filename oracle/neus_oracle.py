@@ -26,6 +26,7 @@ __all__ = [
     "MOTION_CFG", "init_motion_params", "motion_forward", "euler_xyz_to_matrix", "consecutive_relative_pose",
     "relative_camera_pose", "w2c_mappings",
     "warp_pixel", "flow_forward_prediction", "flow_rgb_loss", "sdf_consistency_loss", "stage1_losses",
+    "smoothness_loss", "edge_smoothness_loss", "stage1_step",
 ]
 
 # configs/default.yaml:103-156 (no scene config overrides any of these shapes)
@@ -671,3 +672,56 @@ def stage1_losses(sdf_params, motion_params, out, rgb_gt, query_time_step, image
         if use_flow_rgb:
             res["flow_rgb_loss"] = flow_rgb_loss(flows[:nb_valid], pix, ref_imgs, rgb_gt)
     return res
+
+
+# --------------------------------------------------------------------------- depth-patch smoothness + the whole stage-1 step
+def smoothness_loss(inputs):
+    """model/losses.py:7-18 (SmoothnessLoss.forward): inputs [n, ps, ps, 1]."""
+    m = lambda x: torch.mean(torch.abs(x))
+    l1 = m(inputs[:, :, :-1] - inputs[:, :, 1:])
+    l2 = m(inputs[:, :-1, :] - inputs[:, 1:, :])
+    l3 = m(inputs[:, :-1, :-1] - inputs[:, 1:, 1:])
+    l4 = m(inputs[:, 1:, :-1] - inputs[:, :-1, 1:])
+    return (l1 + l2 + l3 + l4) / 4
+
+
+def edge_smoothness_loss(inputs, weights, gamma=0.1):
+    """model/losses.py:20-38 (EdgePreservingSmoothnessLoss.forward): inputs [n, ps, ps, 1], weights [n, ps, ps, 3]."""
+    m = lambda x: torch.mean(torch.abs(x))
+    bf = lambda x: torch.exp(-torch.abs(x).sum(-1) / gamma).unsqueeze(-1)
+    w1 = bf(weights[:, :, :-1] - weights[:, :, 1:])
+    w2 = bf(weights[:, :-1, :] - weights[:, 1:, :])
+    w3 = bf(weights[:, :-1, :-1] - weights[:, 1:, 1:])
+    w4 = bf(weights[:, 1:, :-1] - weights[:, :-1, 1:])
+    l1 = m(w1 * (inputs[:, :, :-1] - inputs[:, :, 1:]))
+    l2 = m(w2 * (inputs[:, :-1, :] - inputs[:, 1:, :]))
+    l3 = m(w3 * (inputs[:, :-1, :-1] - inputs[:, 1:, 1:]))
+    l4 = m(w4 * (inputs[:, 1:, :-1] - inputs[:, :-1, 1:]))
+    return (l1 + l2 + l3 + l4) / 4
+
+
+def stage1_step(P, motion_params, rays_o, rays_d, rays_d_norm, near, far, rgb_gt, query_time_step, image_idx,
+                ref_image_idx_list, nb_valid, total_nb_images, nb_sample_timestep, ref_camera_mats, scale_mat, norm_pix, pix,
+                img_hw, ref_imgs, world_cam_idx, world_time_step, weights, patch_size=4, s_level=0, cos_anneal=0.5,
+                t_rand=None, consistency_pose_grad=True, cfg=None, sdf_kw=None, color_kw=None, motion_kw=None):
+    """The reference's stage-1 training iteration from the renderer call to the total loss (train.py:441-531 +
+    model/training.py:490-531): NeuSRenderer.forward, SDF-flow / flow-RGB / SDF-consistency losses on the UN-DETACHED renderer
+    outputs, the two depth-patch smoothness terms on depth_pred, the eikonal term, and compute_loss's weighted sum.
+    `weights` = dict(rgb, eikonal, sdf, flow_rgb, sdf_consistency, edge_aware_smoothness, smoothness).
+    Returns (loss, parts dict, renderer output dict)."""
+    t = torch.as_tensor([float(query_time_step)])
+    out = render(P, rays_o, rays_d, rays_d_norm, t, near, far, cfg=cfg, cos_anneal=cos_anneal, eval_mode=False, t_rand=t_rand)
+    aux = stage1_losses(P["sdf"], motion_params, out, rgb_gt, query_time_step, image_idx, ref_image_idx_list, nb_valid,
+                        total_nb_images, nb_sample_timestep, ref_camera_mats, scale_mat, norm_pix, pix, img_hw, ref_imgs,
+                        world_cam_idx, world_time_step, consistency_pose_grad=consistency_pose_grad, sdf_kw=sdf_kw,
+                        motion_kw=motion_kw)
+    ps = patch_size
+    disp = out["depth_pred"].view(-1, ps, ps, 1)                                  # train.py:520-521
+    edge = 1 / (2 ** s_level) * edge_smoothness_loss(disp, rgb_gt.view(-1, ps, ps, 3))
+    smooth = 1 / (2 ** s_level) * smoothness_loss(disp)
+    parts = dict(rgb=rgb_l1_loss(out["color_fine"], rgb_gt), eikonal=eikonal_loss(out["normals"]), sdf=aux["sdf_loss"],
+                 flow_rgb=aux["flow_rgb_loss"], sdf_consistency=aux["sdf_consistency_loss"], edge_aware_smoothness=edge,
+                 smoothness=smooth)
+    loss = sum(weights[k] * parts[k] for k in parts)                              # model/training.py:525-531
+    parts["flow_fw_pred"] = aux["flow_fw_pred"]
+    return loss, parts, out

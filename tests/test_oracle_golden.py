@@ -213,3 +213,59 @@ def test_stage1_auxiliary_losses():
                 assert_close(v.grad, g[f"grad.{tag}.{k}"], 5e-5, f"grad {tag}.{k}")
                 n += 1
     assert n == 15 + 27
+
+
+def test_stage1_iteration_through_renderer():
+    """tests/golden/stage1_render_small.npz: the imported reference NeuSRenderer + the reference's own train.py:467-526 lines
+    + the imported mdl.Trainer.compute_loss, back-propagated into every SDF / colour / variance / motion / pose parameter
+    through depth_pred, weights, sdf and sampled_points.  Replayed by oracle.stage1_step."""
+    g = load_golden("stage1_render_small")
+    mk = lambda v: v.clone().requires_grad_(True)
+    P = {t: {k: mk(v) for k, v in unflatten(g, f"param.{t}.").items()} for t in ("sdf", "color", "variance")}
+    mp = {k: mk(v) for k, v in unflatten(g, "param.motion.").items()}
+    pose = dict(r=mk(g["r"]), t=mk(g["t"]), init_c2w=g["init_c2w"].clone())
+    o, d, dn = O.ray_generation(g["norm_pix"][None], g["K"], O.pose_forward(pose, 0), torch.eye(4)[None])
+    near, far = O.near_far(o, d, [float(v) for v in g["depth_range"]])
+    w = dict(rgb=float(g["w.rgb_weight"]), eikonal=float(g["w.eikonal_weight"]), sdf=float(g["w.sdf_weight"]),
+             flow_rgb=float(g["w.flow_rgb_weight"]), sdf_consistency=float(g["w.sdf_consistency_weight"]),
+             edge_aware_smoothness=float(g["w.edge_aware_smoothness_weight"]), smoothness=float(g["w.smoothness_weight"]))
+    loss, parts, out = O.stage1_step(P, mp, o, d, dn, near, far, g["rgb_gt"], float(g["query_time_step"]), int(g["image_idx"]),
+                                     [int(v) for v in g["ref_idx"]], int(g["nb_valid"]), int(g["total_nb_images"]),
+                                     int(g["nb_sample_timestep"]), g["Kr"], torch.eye(4)[None], g["norm_pix"], g["pix"],
+                                     (int(g["H"]), int(g["W"])), g["refs"], int(g["world_cam_idx"]), float(g["world_time_step"]),
+                                     w, patch_size=int(g["ps"]), s_level=int(g["s_level"]), cos_anneal=float(g["cos_anneal"]),
+                                     t_rand=g["t_rand"])
+    assert_close(loss, g["loss.loss"], 2e-4, "loss")
+    for a, b in (("rgb", "loss_rgb"), ("eikonal", "loss_eikonal"), ("sdf", "loss_sdf"), ("flow_rgb", "loss_flow_rgb"),
+                 ("sdf_consistency", "sdf_consistency_loss"), ("edge_aware_smoothness", "edge_aware_smoothness_loss"),
+                 ("smoothness", "smoothness_loss")):
+        assert_close(parts[a], g[f"loss.{b}"], 2e-5, a)
+    assert float(g["weight_sum"].max()) > 0.9 and float(g["loss.edge_aware_smoothness_loss"]) > 1e-3   # a non-degenerate scene
+    loss.backward()
+    from conftest import rel_err
+    n = 0
+    for tag, params in (("sdf", P["sdf"]), ("color", P["color"]), ("variance", P["variance"]), ("motion", mp)):
+        for k, v in params.items():
+            assert rel_err(v.grad, g[f"grad.{tag}.{k}"]) < 1e-3, f"{tag}.{k}"
+            n += 1
+    assert n == 27 + 15 + 1 + 15
+    assert rel_err(pose["r"].grad, g["dr"]) < 1e-3 and rel_err(pose["t"].grad, g["dt"]) < 1e-3
+
+
+def test_pretrained_sdf_weights_fixture():
+    """pretrained_sdf/model.pt (train.py:41-43), the reference's only fixture: forward, analytic gradient and the eikonal +
+    value double backward of the oracle against the imported reference's numbers (tests/golden/pretrained_sdf.npz)."""
+    g = load_golden("pretrained_sdf")
+    P = {k: v.clone().requires_grad_(True) for k, v in unflatten(g, "param.").items()}
+    assert len(P) == 27
+    x = g["x"]
+    assert_close(O.sdf_forward(P, x), g["y"], 1e-5, "pretrained fwd")
+    og = O.sdf_gradient(P, x.clone()).squeeze(1)
+    assert_close(og, g["grad"], 1e-5, "pretrained grad")
+    assert abs(float(og[:, :3].norm(dim=-1).mean()) - 1.0) < 0.05          # a trained SDF: |grad| ~ 1 (the plane sdf = y + 1)
+    ((og[:, :3].norm(dim=-1) - 1).pow(2).mean() + (O.sdf_forward(P, x) * g["wy"]).sum() / x.shape[0]).backward()
+    from conftest import rel_err
+    for k, v in P.items():
+        assert abs(float(v.grad.double().norm()) - float(g[f"gnorm.{k}"])) <= 1e-3 * float(g[f"gnorm.{k}"]) + 1e-9, k
+        if f"grad.{k}" in g:
+            assert rel_err(v.grad, g[f"grad.{k}"]) < 1e-3, k
