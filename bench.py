@@ -33,8 +33,6 @@ FLOP_PER_TRAIN_RAY = 1_117_315_072          # 112*F_sdfq + 128*(
 H, W = 717, 1275
 DEPTH_RANGE = (0.01, 5.0)
 METRIC = "train rays/s fwd+bwd+eikonal (NeuS 64+64 samples)"
-# dram__bytes_read + dram__bytes_write of the chain / wgrad kernels of one 1024-ray step (profiles/r01_fused_kernels_ncu_full.csv)
-MLP_DRAM_GB_PER_STEP = 9.76   # ncu --set full, profiles/r01_end_kernels_ncu_full.csv (1024 rays)
 MLP_CALLS = {"cope_sdf_query", "cope_sdf_fwd", "cope_sdf_bwd", "cope_color_fwd", "cope_color_bwd", "cope_render_mlp_fwd",
              "cope_render_mlp_bwd"}
 
@@ -159,7 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.rays), "rays_per_gpu": args.rays},
+        "config": {"workload": workload_name(args.rays), "rays_per_gpu": args.rays, "rays_per_step_timed_here": n},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n} rays x 64+64 samples per step, same nets/losses/Adam, oracle port of the "
                                    f"reference's PyTorch CPU path, torch threads = {cores}"},
@@ -175,6 +173,140 @@ def workload_name(rays):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def eager_cuda_rays_per_s(n_rays, steps, warmup, dev, seed=678):
+    """Informative second baseline: the SAME oracle port of the reference's eager-PyTorch path, run on the
+    B200 (`with torch.device(cuda)`: every factory call of the port lands on the GPU; ATen / cuBLAS fp32 kernels, autograd incl.
+    the double backward, torch.optim.Adam) — what the reference's own code path does on this GPU, since it ships no kernel."""
+    import oracle as O
+    host = synth_inputs(n_rays, steps + warmup, seed)
+    torch.manual_seed(seed)
+    P0 = dict(sdf=O.init_sdf_params(**O.DEFAULT_CFG["sdf"]), color=O.init_color_params(**O.DEFAULT_CFG["color"]),
+              variance=O.init_variance_params(**O.DEFAULT_CFG["variance"]))
+    with torch.device(dev):
+        P = {t: {k: v.to(dev) for k, v in d.items()} for t, d in P0.items()}
+        params = []
+        for t in P.values():
+            for k in t:
+                t[k] = t[k].requires_grad_(True)
+                params.append(t[k])
+        pose = dict(r=(torch.randn(1, 3) * 0.05).requires_grad_(True), t=(torch.randn(1, 3) * 0.05).requires_grad_(True),
+                    init_c2w=torch.eye(4).unsqueeze(0))
+        opt = torch.optim.Adam(params + [pose["r"], pose["t"]], lr=1e-3)
+        batches = [{k: v.to(dev) for k, v in b.items()} for b in host]
+        K, S, t0 = camera().to(dev), torch.eye(4).unsqueeze(0), torch.zeros(1)
+        for i, b in enumerate(batches):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+            opt.zero_grad()
+            loss, _ = O.train_step(P, pose, b["pix"], K, S, b["rgb"], t0, list(DEPTH_RANGE), cos_anneal=0.5, t_rand=b["t_rand"])
+            loss.backward()
+            opt.step()
+        e1 = torch.cuda.Event(enable_timing=True); e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return n_rays / (ms * 1e-3), ms
+
+
+def mlp_traffic_from_profile():
+    """DRAM bytes (read + write) of the MLP kernel group of ONE 1024-ray step, summed from the committed ncu --set full summary
+    of this round (profiles/r02_step_kernels_ncu_full.csv, written by tools/ncu_summary.py from the .ncu-rep).  None when the
+    file is absent: the number is a measurement, never a literal."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_step_kernels_ncu_full.csv")
+    try:
+        tot = 0.0
+        with open(path) as f:
+            for row in csv.DictReader(f):
+                if row.get("mlp_group") == "1":
+                    tot += float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])
+        return (tot / 1e9, os.path.relpath(path, ROOT)) if tot > 0 else (None, None)
+    except Exception:
+        return None, None
+
+
+class Runner:
+    """One configuration of the training step on this rank: networks, optimiser, synthetic batches, and the step as ONE CUDA
+    graph (pose -> rays -> sampling -> render -> loss -> backward -> gradient all-reduce -> fused Adam)."""
+
+    def __init__(self, C, dev, prec, n_rays, world, rank, n_batches, loss_scale, graph_mode):
+        from cope_nerf_b200.dist import FlatGradBucket
+        self.C, self.dev, self.n, self.world = C, dev, n_rays, world
+        torch.manual_seed(678)
+        self.rnd = C.training.build_networks(device=dev, precision=prec)
+        self.pose = C.PoseRetriever(1).to(dev)
+        with torch.no_grad():
+            self.pose.r.copy_(torch.randn(1, 3) * 0.05); self.pose.t.copy_(torch.randn(1, 3) * 0.05)
+        self.bucket = FlatGradBucket(list(self.rnd.parameters()) + [self.pose.r, self.pose.t])
+        self.opt = torch.optim.Adam(self.bucket.params, lr=1e-3, fused=True, capturable=True)
+        self.Kc, self.Sc = camera().to(dev), torch.eye(4, device=dev).unsqueeze(0)
+        self.tstep = torch.zeros(1, device=dev)
+        host = synth_inputs(n_rays, n_batches, seed=678 + 1000 * rank)
+        self.pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+        self.resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+        self.loss_scale = loss_scale
+        self.graph, self.static, self.static_loss, self.tail_eager = None, None, None, False
+        self.note = "eager launches"
+        if graph_mode != "none":
+            self._capture(graph_mode)
+
+    def compute(self, b):
+        """zero grads -> pose -> rays -> sampling -> render -> loss -> backward"""
+        self.bucket.zero_()
+        self.rnd.t_rand_override = b["t_rand"]
+        loss, _, _ = self.C.training.render_train_step(self.rnd, self.pose, 0, b["pix"], self.Kc, self.Sc, b["rgb"], self.tstep,
+                                                       DEPTH_RANGE, cos_anneal_ratio=0.5, it=1, loss_scale=self.loss_scale)
+        return loss
+
+    def exchange_and_update(self):
+        self.bucket.allreduce_()
+        self.opt.step()
+
+    def step_eager(self, b):
+        loss = self.compute(b)
+        self.exchange_and_update()
+        return loss
+
+    def _capture(self, mode):
+        """mode 'full': the whole step incl. the NCCL all-reduce and the (capturable) fused Adam in one graph; on failure, or with
+        mode 'compute', forward + backward only, exchange and optimiser launched eagerly after the replay."""
+        self.static = {k: torch.empty_like(v) for k, v in self.resident[0].items()}
+        for attempt in (("full", "compute") if mode == "full" else ("compute",)):
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for b in self.resident[:3]:
+                        for k in self.static:
+                            self.static[k].copy_(b[k])
+                        self.step_eager(self.static)          # also creates Adam's state before the capture
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self.compute(self.static)
+                    if attempt == "full":
+                        self.exchange_and_update()
+                self.graph, self.static_loss, self.tail_eager = g, loss, attempt != "full"
+                self.note = ("one CUDA graph per step (fwd + bwd + gradient all-reduce + fused Adam)" if attempt == "full" else
+                             "one CUDA graph per step (fwd + bwd), eager all-reduce + fused Adam")
+                return
+            except Exception as e:      # pragma: no cover - depends on the box
+                self.graph = None
+                self.note = f"eager launches (graph capture '{attempt}' failed: {type(e).__name__}: {str(e)[:100]})"
+                torch.cuda.synchronize()
+
+    def step(self, b):
+        if self.graph is None:
+            return self.step_eager(b)
+        for k in self.static:
+            self.static[k].copy_(b[k], non_blocking=True)
+        self.graph.replay()
+        if self.tail_eager:
+            self.exchange_and_update()
+        return self.static_loss
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,16 +319,20 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("COPE_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="ray sample of the CPU baseline step (BASELINE.json configs[0]: 512 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / ray-sweep / eager-CUDA extras of the JSON line")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph-mode", default="full", choices=["full", "compute", "none"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
+    if args.no_graph:
+        args.graph_mode = "none"
 
     import torch.distributed as dist
     import cope_nerf_b200 as C
     from cope_nerf_b200 import _lib as L
-    from cope_nerf_b200.dist import FlatGradBucket, init_from_env
+    from cope_nerf_b200.dist import init_from_env, shard_range
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):   # NCCL prints its version banner on stdout (env or nccl.conf):
         os.environ["NCCL_DEBUG"] = "WARN"                             # keep stdout to the one JSON line of the contract
@@ -222,77 +358,49 @@ def main():
         prec = getattr(C, "DEFAULT_PRECISION", C.PREC_FP32)
     n = args.rays
     if args.strong and world > 1:
-        from cope_nerf_b200.dist import shard_range
         lo, hi = shard_range(args.rays, rank, world)      # this rank's slice of the total batch (multiples of one 4x4 patch)
         n = hi - lo
     total_rays = args.rays if (args.strong and world > 1) else n * world
+    # rgb (sum/N) and eikonal (mean) are shard-linear: scale the local loss by this rank's share of the batch
+    run = Runner(C, dev, prec, n, world, rank, args.steps + args.warmup, n / total_rays, args.graph_mode)
 
-    torch.manual_seed(678)
-    rnd = C.training.build_networks(device=dev, precision=prec)
-    pose = C.PoseRetriever(1).to(dev)
-    with torch.no_grad():
-        pose.r.copy_(torch.randn(1, 3) * 0.05); pose.t.copy_(torch.randn(1, 3) * 0.05)
-    params = list(rnd.parameters()) + [pose.r, pose.t]
-    bucket = FlatGradBucket(params)
-    opt = torch.optim.Adam(bucket.params, lr=1e-3, fused=True)
-    Kc, Sc = camera().to(dev), torch.eye(4, device=dev).unsqueeze(0)
-    tstep = torch.zeros(1, device=dev)
-    n_batches = args.steps + args.warmup
-    host = synth_inputs(n, n_batches, seed=678 + 1000 * rank)
-    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    inv_world = 1.0 / world     # rgb (sum/N) and eikonal (mean) are shard-linear: scale the local loss
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
+    def timed_region(fn, batches, steps, warmup):
+        for b in batches[:warmup]:
+            fn(b)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in batches[warmup:warmup + steps]:
+            fn(b)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- value: device-resident inputs
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_total = timed_region(run.step, run.resident, args.steps, args.warmup)
+    clk = clocks.stop()
+    ms_per_step = ms_total / args.steps
+    value = total_rays * args.steps / (ms_total * 1e-3)
+    # launches of OUR kernels per step: kernels inside a replayed graph do not pass through the library's launch counter, so one
+    # eager step is counted (the graph replays exactly these launches)
+    l0 = lib.cope_launch_count()
+    run.step_eager(run.resident[0])
+    launches = (lib.cope_launch_count() - l0) * args.steps
+
+    # ---- roofline of the MLP kernel group: CUDA events around the cope_sdf_* / cope_color_* calls on the launching
+    # stream, over the same K batches launched eagerly (events cannot be recorded inside a replayed graph)
     mlp_events = []
-
-    def compute(b):
-        """zero grads -> pose -> rays -> sampling -> render -> loss -> backward (everything but the exchange + optimiser)"""
-        bucket.zero_()
-        rnd.t_rand_override = b["t_rand"]
-        loss, _, _ = C.training.render_train_step(rnd, pose, 0, b["pix"], Kc, Sc, b["rgb"], tstep, DEPTH_RANGE,
-                                                  cos_anneal_ratio=0.5, it=1, loss_scale=inv_world)
-        return loss
-
-    def step_eager(b):
-        loss = compute(b)
-        bucket.allreduce_()
-        opt.step()
-        return loss
-
-    # The step has ~70 short launches around the chain kernels: replay them as ONE CUDA graph (static input buffers), keep the NCCL
-    # all-reduce and the fused Adam eager.  --no-graph times the eager launch path instead.
-    graph, static, static_loss, graph_note = None, None, None, "eager launches"
-    if not args.no_graph:
-        try:
-            static = {k: torch.empty_like(v) for k, v in resident[0].items()}
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for b in resident[:2]:
-                    for k in static:
-                        static[k].copy_(b[k])
-                    compute(static)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = compute(static)
-            graph_note = "one CUDA graph per step (fwd+bwd), eager all-reduce + fused Adam"
-        except Exception as e:      # pragma: no cover - depends on the box
-            graph, graph_note = None, f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
-            torch.cuda.synchronize()
-
-    def step(b):
-        if graph is None:
-            return step_eager(b)
-        for k in static:
-            static[k].copy_(b[k], non_blocking=True)
-        graph.replay()
-        bucket.allreduce_()
-        opt.step()
-        return static_loss
-
-    # instrument the MLP entry points with CUDA events on the launching stream (roofline.achieved)
     real_call = L.call
 
     def timed_call(name, *a):
@@ -305,68 +413,61 @@ def main():
         else:
             real_call(name, *a)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed_region(fn, batches):
-        for b in batches[:args.warmup]:
-            fn(b)
-        barrier()
-        mlp_events.clear()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.cope_launch_count()
-        e0.record()
-        for b in batches[args.warmup:]:
-            fn(b)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), lib.cope_launch_count() - l0
-
-    # ---- value: device-resident inputs
-    clocks = ClockSampler(local)
-    clocks.start()
-    ms_total, launches = timed_region(step, resident)
-    clk = clocks.stop()
-    ms_per_step = ms_total / args.steps
-    value = total_rays * args.steps / (ms_total * 1e-3)
-    if graph is not None:       # kernels inside a replayed graph do not pass through the library's launch counter
-        l0 = lib.cope_launch_count()
-        step_eager(resident[0])
-        launches = (lib.cope_launch_count() - l0) * args.steps
-
-    # ---- roofline of the MLP kernel group: CUDA events around the cope_sdf_* / cope_color_* calls on the launching
-    # stream, over the same K batches launched eagerly (events cannot be recorded inside a replayed graph)
     L.call = timed_call
     torch.cuda.synchronize()
-    mlp_events.clear()
-    for b in resident[args.warmup:]:
-        step_eager(b)
+    for b in run.resident[args.warmup:]:
+        run.step_eager(b)
     torch.cuda.synchronize()
     L.call = real_call
     mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events)
 
     # ---- e2e: host inputs every step, loss read back every step
     def step_e2e(b):
-        if graph is None:
+        if run.graph is None:
             dev_b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
-            return step_eager(dev_b).item()
-        return step(b).item()        # pinned host -> static device buffers -> graph replay -> loss read-back
+            return run.step_eager(dev_b).item()
+        return run.step(b).item()        # pinned host -> static device buffers -> graph replay -> loss read-back
 
-    ms_e2e, _ = timed_region(step_e2e, pinned)
+    ms_e2e = timed_region(step_e2e, run.pinned, args.steps, args.warmup)
     e2e = total_rays * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    h2d = sum(v.numel() * v.element_size() for v in run.pinned[0].values())
+    graph_note = run.note
+
+    # ---- extras recorded in the same line (BASELINE.json configs[2] strong split, configs[4] ray sweep): every rank takes part
+    extras = {}
+    if not args.no_extras and not args.strong:
+        del run
+        torch.cuda.empty_cache()
+        if world > 1:
+            lo, hi = shard_range(1024, rank, world)
+            rs = Runner(C, dev, prec, hi - lo, world, rank, 13, (hi - lo) / 1024.0, args.graph_mode)
+            ms = timed_region(rs.step, rs.resident, 10, 3)
+            extras["strong"] = {"rays_total": 1024, "rays_per_gpu": hi - lo, "ms_per_step": ms / 10, "value": 1024 * 10 / (ms * 1e-3),
+                                "unit": "rays/s", "launch": rs.note,
+                                "note": "ONE 1024-ray batch split over the ranks in 16-ray blocks (configs[2]); latency-bound below ~1 wave of 128-point tiles per GPU"}
+            del rs
+            torch.cuda.empty_cache()
+        sweep = []
+        for nr in (4096, 16384, 32768):
+            try:
+                rw = Runner(C, dev, prec, nr, world, rank, 5, 1.0 / world, "none")
+                ms = timed_region(rw.step, rw.resident, 3, 2)
+                sweep.append({"rays_per_gpu": nr, "ms_per_step": ms / 3, "value": nr * world * 3 / (ms * 1e-3),
+                              "mlp_frac_of_sustained_bf16_upper_bound": nr * FLOP_PER_TRAIN_RAY / (ms / 3 * 1e-3) / 1e12 / peaks()["bf16_sustained"]})
+                del rw
+            except Exception as e:      # pragma: no cover - memory of the box
+                sweep.append({"rays_per_gpu": nr, "error": f"{type(e).__name__}: {str(e)[:80]}"})
+            torch.cuda.empty_cache()
+        extras["sweep"] = {"unit": "rays/s (whole job)", "launch": "eager", "points": sweep,
+                           "note": "training steps at 4K-32K rays per GPU x 128 samples (configs[4]; 32K rays/GPU = 256K rays at 8 GPUs); "
+                                   "the fraction counts the WHOLE step against the MLP FLOPs, so it is a lower bound of the MLP group's own"}
 
     if rank == 0:
         pk = peaks()
         mlp_ms_step = mlp_ms / args.steps if args.steps else 0.0
         ach = (n * FLOP_PER_TRAIN_RAY / (mlp_ms_step * 1e-3) / 1e12) if mlp_ms_step > 0 else None
         peak = pk["bf16_sustained"]
+        traffic, traffic_src = mlp_traffic_from_profile()
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -382,17 +483,28 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "SDF+colour MLP kernels (cope_sdf_query, cope_render_mlp_fwd/bwd = sdf_chain_query / sdf_fused<FWD,TAN,ADJ> / color_fused / tc_wgrad)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-                         "traffic": MLP_DRAM_GB_PER_STEP, "traffic_unit": "GB of DRAM traffic per step of the MLP kernel group at 1024 rays (ncu --set full, profiles/r01_end_kernels_ncu_full.csv)", "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                         "traffic": traffic, "traffic_unit": "GB of DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per step of the MLP kernel group at 1024 rays",
+                         "traffic_source": traffic_src,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                          "measured": "CUDA events around the MLP entry points, same K batches launched eagerly after the timed region",
                          "mlp_ms_per_step": mlp_ms_step, "mlp_share_of_step": min(1.0, mlp_ms_step / ms_per_step) if ms_per_step else None,
                          "algorithmic_flop_per_ray": FLOP_PER_TRAIN_RAY},
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            v, spt = cpu_train_rays_per_s(args.cpu_rays, 3, 1)
+            v, spt = cpu_train_rays_per_s(args.cpu_rays, 5, 3)
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_rays} rays x 64+64 samples per step (1 warm-up + 3 timed), same "
+                                    "sample": f"{args.cpu_rays} rays x 64+64 samples per step (3 warm-up + 5 timed), same "
                                               f"nets/losses/Adam, oracle port of the reference's PyTorch CPU path"}
+        if world == 1 and not args.no_extras:
+            try:
+                v, ms = eager_cuda_rays_per_s(1024, 5, 3, dev)
+                line["eager_cuda_baseline"] = {"value": v, "unit": "rays/s", "ms_per_step": ms, "kind": "port on cuda",
+                                               "sample": "1024 rays x 64+64 samples per step (3 warm-up + 5 timed), the oracle port of the reference's "
+                                                         "eager PyTorch path (ATen / cuBLAS fp32, autograd double backward, Adam) on this B200; informative"}
+            except Exception as e:      # pragma: no cover
+                line["eager_cuda_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -19,7 +19,11 @@ from cope_nerf_b200 import _lib as L  # noqa: E402
 from bench import peaks  # noqa: E402
 
 
+ITERS, WARM = None, None     # --iters / --warm: short runs for the ncu pass
+
+
 def timeit(fn, iters=20, warm=3):
+    iters, warm = (ITERS or iters), (WARM if WARM is not None else warm)
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -133,7 +137,14 @@ def main():
     ap.add_argument("--eval-image", type=int, nargs=2, default=[484, 648], metavar=("H", "W"))
     ap.add_argument("--eval-chunk", type=int, default=16384)
     ap.add_argument("--eval-only", action="store_true", help="only the evaluation-image row (the one that runs under torchrun)")
+    ap.add_argument("--hbm-only", action="store_true", help="only the HBM-bound kernels (sampling, compositing, losses): the ncu pass")
+    ap.add_argument("--iters", type=int, default=0)
+    ap.add_argument("--warm", type=int, default=-1)
     args = ap.parse_args()
+    global ITERS, WARM
+    ITERS, WARM = (args.iters or None), (args.warm if args.warm >= 0 else None)
+    if args.hbm_only:
+        args.eval_image = [0, 0]
     from cope_nerf_b200.dist import init_from_env
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
@@ -187,7 +198,7 @@ def main():
         # render-MLP stage through the C ABI (fused chains + batched weight gradients): SDF value + gradient + colour,
         # forward and backward incl. the double backward, 6 F_sdf + 3 F_col FLOP per point
         mlp = None
-        if P <= 16384 * 128:
+        if P <= 16384 * 128 and not args.hbm_only:
             sn, cn = rnd.sdf_network, rnd.color_network
             cflat = cn.flat_weights().detach()
             o_sdf, o_grad, o_rgb = f(P, 1), f(P, 4), f(P, 3)
@@ -222,10 +233,10 @@ def main():
             ("step_losses_bwd", loss_bwd, P * 68 + N * 36, "hbm"),               # + d_grad4 16 + d_pts4 16 out
             ("weighted_points_fwd", wpts_fwd, P * 20 + N * 16, "hbm"),
             ("composite_fwd", comp_fwd, N * (S * 36 + 44), "hbm"),                # z,dists,sdf 12 + grad 16 + rgb 12 in; w 4 out
-            ("composite_bwd", comp_bwd, N * (S * 84 + 60), "hbm"),                # 40 in + d_w 4 + d_grad rw 32 + d_sdf 4 + d_rgb 12 - z
+            ("composite_bwd", comp_bwd, N * (S * 68 + 44), "hbm"),                # re-read 32 + weights/d_weights 8, d_sdf 4 + d_normal 12 + d_rgb 12 out (the kernel's own traffic: 40 in + d_w 4, d_grad4 16 + d_sdf 4 + d_rgb 12 out = 76)
             ("upsample", ups, N * ((S - 16) * 8 + 64), "hbm"),
             ("merge_z", mrg, N * (2 * (112 + 16) * 4 + 2 * S * 4), "hbm"),
-            ("sdf_query_chain", lambda: rnd.sdf_network.query_flat(flat, x), P * 918016, "tensor"),
+            ("sdf_query_chain", None if args.hbm_only else (lambda: rnd.sdf_network.query_flat(flat, x)), P * 918016, "tensor"),
             ("render_mlp_fwd_bwd", mlp, P * (6 * 1049088 + 3 * 543744), "tensor"),
         ]
         for name, fn, work, bound in rows:

@@ -257,3 +257,81 @@ def test_bf16_inference_render_on_layered_fallback(case, monkeypatch, small_para
     for key in ("color_fine", "depth_pred", "normals", "weights", "sdf"):
         assert torch.equal(a[key], a2[key]), key
         assert rel_err(a[key], b[key]) < 1e-5, (key, rel_err(a[key], b[key]))
+
+
+# ------------------------------------------------------------------------------------------------ sampling / compositing kernels
+def test_merge_sorted_new_samples_fast_path():
+    """cope_merge_z with SORTED new depths (what up_sample produces) takes the lower-bound path: bit-identical to a stable
+    sort, including exact ties old-new (old first) and new-new."""
+    r = C.training.build_networks(SMALL_CFG, device=DEV)
+    torch.manual_seed(15)
+    for S, K in ((64, 16), (112, 16), (97, 7), (128, 64), (1, 1), (5, 33)):
+        z = torch.sort(torch.rand(517, S), dim=-1)[0]
+        nz = torch.sort(torch.rand(517, K), dim=-1)[0]
+        nz[:, 0] = z[:, 0]                                      # tie with an old element
+        if K > 2:
+            nz[:, K // 2] = nz[:, K // 2 - 1]                   # tie between two new elements
+            nz[:, -1] = z[:, -1]
+            nz = torch.sort(nz, dim=-1)[0]
+        a, b = torch.randn(517, S), torch.randn(517, K)
+        zo, so = r.merge_z(cu(z), cu(nz), cu(a), cu(b))
+        zs, idx = torch.sort(torch.cat([z, nz], -1), dim=-1, stable=True)
+        assert torch.equal(zo.cpu(), zs), (S, K)
+        assert torch.equal(so.cpu(), torch.gather(torch.cat([a, b], -1), 1, idx)), (S, K)
+
+
+@pytest.mark.parametrize("eval_mode", [0, 1])
+def test_composite_vector_path_matches_scalar_path_and_oracle(eval_mode, monkeypatch):
+    """S = 128 takes composite_fwd128 / composite_bwd128 (16-byte accesses, everything kept in registers); the generic kernels
+    (COPE_COMPOSITE_SCALAR=1) are the A/B reference, and torch autograd on the oracle's compositing lines the checker."""
+    from cope_nerf_b200 import _lib as L
+    torch.manual_seed(31 + eval_mode)
+    N, S = 777, 128
+    P = N * S
+    z = torch.sort(torch.rand(N, S) * 4.9 + 0.01, dim=-1)[0]
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((N, 1), 0.078)], -1)
+    sdf = ((1.5 - z) * 0.7 + 0.02 * torch.randn(N, S)).reshape(P, 1)
+    grad, rgb = torch.randn(P, 4), torch.rand(P, 3)
+    rays_d = torch.nn.functional.normalize(torch.randn(N, 3), dim=-1)
+    dn, var = 1.0 + torch.rand(N, 1), torch.tensor(0.3)
+    d_color, d_depth, d_w, d_gin = torch.randn(N, 3), torch.randn(N, 1), torch.randn(N, S) * 0.1, torch.randn(P, 4) * 0.1
+    dev = {k: cu(v).contiguous() for k, v in dict(z=z, dists=dists, sdf=sdf, grad=grad, rgb=rgb, rays_d=rays_d, dn=dn, var=var,
+                                                  d_color=d_color, d_depth=d_depth, d_w=d_w, d_gin=d_gin).items()}
+    f = lambda *s: torch.empty(*s, device=DEV)
+
+    def run():
+        o = dict(weights=f(N, S), color=f(N, 3), depth=f(N, 1), wz=f(N, 1), cdf=f(N, S), wsum=f(N, 1), wmax=f(N, 1), inv_s=f(1),
+                 d_sdf=f(P, 1), d_grad=f(P, 4), d_rgb=f(P, 3), d_var=torch.zeros(1, device=DEV), d_rd=f(N, 3))
+        L.call("cope_composite_fwd", dev["sdf"], dev["grad"], dev["rgb"], dev["z"], dev["dists"], dev["rays_d"], dev["dn"], dev["var"],
+               0.4, eval_mode, N, S, o["weights"], o["color"], o["depth"], o["wz"], o["cdf"], o["wsum"], o["wmax"], o["inv_s"], L.stream())
+        L.call("cope_composite_bwd", dev["sdf"], dev["grad"], dev["rgb"], dev["z"], dev["dists"], dev["rays_d"], dev["dn"], dev["var"],
+               0.4, eval_mode, N, S, dev["d_color"], dev["d_depth"], dev["d_w"], dev["d_gin"], o["d_sdf"], o["d_grad"], o["d_rgb"],
+               o["d_var"], o["d_rd"], L.stream())
+        torch.cuda.synchronize()
+        return o
+
+    vec = run()
+    monkeypatch.setenv("COPE_COMPOSITE_SCALAR", "1")
+    sca = run()
+    for k in vec:
+        e = rel_err(vec[k], sca[k])
+        assert e < (2e-5 if k == "d_var" else 2e-6), (k, e)
+    # oracle: the compositing lines of render_core (model/neus_renderer.py:360-420) in torch autograd
+    lv = {k: v.clone().requires_grad_(True) for k, v in dict(sdf=sdf, grad=grad, rgb=rgb, var=var).items()}
+    inv_s = torch.exp(lv["var"] * 10.0).clip(1e-3, 1e3)
+    dirs = rays_d[:, None, :].expand(N, S, 3).reshape(-1, 3)
+    true_cos = (dirs * lv["grad"][:, :3]).sum(-1, keepdim=True)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * 0.6 + torch.relu(-true_cos) * 0.4)
+    d = dists.reshape(-1, 1)
+    pc = torch.sigmoid((lv["sdf"] - iter_cos * d * 0.5) * inv_s)
+    nc = torch.sigmoid((lv["sdf"] + iter_cos * d * 0.5) * inv_s)
+    alpha = ((pc - nc + 1e-5) / (pc + 1e-5)).reshape(N, S).clip(0.0, 1.0)
+    w = alpha * torch.cumprod(torch.cat([torch.ones(N, 1), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    color = (lv["rgb"].reshape(N, S, 3) * w[:, :, None]).sum(1)
+    depth = (z * w).sum(1, keepdim=True)
+    if eval_mode:
+        depth = depth / dn
+    ((color * d_color).sum() + (depth * d_depth).sum() + (w * d_w).sum() + (lv["grad"] * d_gin).sum()).backward()
+    assert rel_err(vec["weights"], w) < 1e-4 and rel_err(vec["color"], color) < 1e-4 and rel_err(vec["depth"], depth) < 1e-4
+    assert rel_err(vec["d_sdf"], lv["sdf"].grad) < 1e-3 and rel_err(vec["d_grad"], lv["grad"].grad) < 1e-3
+    assert rel_err(vec["d_rgb"], lv["rgb"].grad) < 1e-4 and rel_err(vec["d_var"], lv["var"].grad.reshape(1)) < 1e-3
