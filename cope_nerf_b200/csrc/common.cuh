@@ -30,18 +30,6 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
   } while (0)
 
 static inline cudaStream_t as_stream(cope_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
-
-// Fork / join of a library-owned side stream (gemm_f32.cu): two INDEPENDENT kernels of one entry point run next to each other
-// on disjoint sets of SMs (an HBM-bound weight-gradient kernel beside a latency-bound chain sweep).  The side stream is created
-// once per device and only ever ordered against the caller's stream with events, so the entry point stays asynchronous,
-// keeps the caller's stream semantics (everything is joined back before it returns) and is capturable into a CUDA graph.
-struct SideFork {
-  cudaStream_t main = nullptr, side = nullptr;
-  bool active = false;
-  int fork(cudaStream_t main_stream);     // side waits for everything queued on main so far; returns 0 / negative
-  int join();                             // main waits for everything queued on side
-};
-int env_int(const char* name, int dflt);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr float kInvSqrt2 = 0.70710678118654752440f;

@@ -2,7 +2,6 @@
 // C[M x N] = epi( op(A) [M x K] * op(B) [K x N] ).  128x128x16 tiles, 256 threads, 8x8 per thread,
 // register-prefetched global loads, split-K with atomics for the weight-gradient (K = points) shape.
 #include <stdarg.h>
-#include <stdlib.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -18,46 +17,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error_str() { return g_err; }
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
-
-// one side stream + two events per device, created on first use (never destroyed: process lifetime)
-namespace {
-constexpr int kMaxDev = 64;
-struct SideState { cudaStream_t side = nullptr; cudaEvent_t fork_ev = nullptr, join_ev = nullptr; };
-SideState g_side[kMaxDev];
-}  // namespace
-int SideFork::fork(cudaStream_t main_stream) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { set_error("side stream: bad device"); return -2; }
-  SideState& st = g_side[dev];
-  if (!st.side) {
-    cudaError_t e = cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.fork_ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.join_ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) { set_error("side stream: %s", cudaGetErrorString(e)); st.side = nullptr; return -2; }
-  }
-  main = main_stream; side = st.side;
-  cudaError_t e = cudaEventRecord(st.fork_ev, main);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(side, st.fork_ev, 0);
-  if (e != cudaSuccess) { set_error("side stream fork: %s", cudaGetErrorString(e)); return -2; }
-  active = true;
-  return 0;
-}
-int SideFork::join() {
-  if (!active) return 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  SideState& st = g_side[dev];
-  cudaError_t e = cudaEventRecord(st.join_ev, side);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, st.join_ev, 0);
-  active = false;
-  if (e != cudaSuccess) { set_error("side stream join: %s", cudaGetErrorString(e)); return -2; }
-  return 0;
-}
 
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
 constexpr int PAD = 4;

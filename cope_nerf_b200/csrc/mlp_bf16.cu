@@ -585,15 +585,6 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
     }
     if (int rc = make_tmap3(dyb, LDu, Pu, 1, LDu, Pu * LDu, &maps.in0)) return rc;
     if (int rc = make_tmap3(ZBall, LDu, Pu, (uint64_t)top, LDu, Pu * LDu, &maps.out)) return rc;
-    // Pass 0 (full adjoint, stores zb_l) feeds the weight gradients; pass 1 (value-path adjoint for dx: render_core detaches the
-    // gradient input, model/neus_renderer.py:356) is independent of them.  The weight-gradient launch is HBM-bound (it streams the
-    // four stored stacks once), the value-path sweep is latency-bound (37 % of the copy bandwidth, 24 % tensor pipe): they run
-    // NEXT TO EACH OTHER on disjoint sets of SMs (side stream forked from / joined to the caller's stream with events) instead of
-    // one after the other.  COPE_BWD_OVERLAP=0 restores the serial order; COPE_BWD_SPLIT_WG = SMs of the weight-gradient launch.
-    const bool overlap = dx && env_int("COPE_BWD_OVERLAP", 1) != 0 && P >= 148 * 128 * 2;
-    const int sm_wg = overlap ? std::max(16, std::min(132, env_int("COPE_BWD_SPLIT_WG", 74))) : 0;
-    const int sm_adj = overlap ? 148 - sm_wg : 0;
-    SideFork fk;
     for (int pass = 0; pass < (dx ? 2 : 1); ++pass) {
       FzArgs a{};
       fz_common(m, b, Wflat, wp, x, P, &a);
@@ -605,21 +596,9 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
         fz_job(&a, b.wt_off[l], r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
       }
       if (a.want_e) fz_job(&a, b.wt_off[0], 64, r64(m.out[0]), top & 1, 1, (top & 1) + 1);
-      cudaStream_t ps = s;
-      if (pass == 1 && overlap) {
-        if (int rc = fk.fork(s)) return rc;          // the side stream waits for pass 0 (and everything before it)
-        ps = fk.side;
-        a.max_ctas = sm_adj;
-      }
-      if (pass == 0 || overlap) {
-        if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, ps)) return rc;
-      }
-      if (pass == 1 && overlap) {
-        pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, ps>>>(x, P, m.d_in, m.L, eb0, 64, b.skip > 0 ? eb1 : nullptr, 64, dx, m.d_in, dx_accumulate);
-        COPE_CHECK_LAUNCH("pe_vjp");
-      }
-      if ((pass == 0 && !overlap) || (pass == 1 && overlap) || (pass == 0 && !dx)) {
-        // ---- weight / bias gradients from the stored adjoints: all layers in ONE launch (caller's stream)
+      if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, s)) return rc;
+      if (pass == 0) {
+        // ---- weight / bias gradients from the stored adjoints: all layers in ONE launch
         TcWgradArgs wg[COPE_MAX_LIN];
         int nw = 0;
         {
@@ -643,15 +622,12 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
           w.dW = dWflat + m.w_off[l]; w.ldw = m.in[l]; w.part = part; w.db = dWflat + m.b_off[l];
           wg[nw++] = w;
         }
-        if (int rc = launch_tc_wgrad_batch(wg, nw, s, sm_wg)) return rc;
-      }
-      if (pass == 1 && !overlap) {
-        if (int rc = launch_sdf_fused(FZ_ADJ, a, maps, s)) return rc;
+        if (int rc = launch_tc_wgrad_batch(wg, nw, s)) return rc;
+      } else {
         pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, eb0, 64, b.skip > 0 ? eb1 : nullptr, 64, dx, m.d_in, dx_accumulate);
         COPE_CHECK_LAUNCH("pe_vjp");
       }
     }
-    if (int rc = fk.join()) return rc;
     return 0;
   }
 

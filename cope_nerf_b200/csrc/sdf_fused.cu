@@ -591,8 +591,7 @@ static int launch_t(const FzArgs& a, const FzMaps& maps, cudaStream_t s) {
     attr_set = true;
   }
   const int ntiles = (int)((a.P + 127) / 128);
-  const int sms = a.max_ctas > 0 ? std::min(a.max_ctas, 148) : 148;
-  sdf_fused_kernel<MODE><<<std::min(ntiles, sms), kThreads, Lay<MODE>::kSmem, s>>>(a, maps);
+  sdf_fused_kernel<MODE><<<std::min(ntiles, 148), kThreads, Lay<MODE>::kSmem, s>>>(a, maps);
   COPE_CHECK_LAUNCH("sdf_fused");
   return 0;
 }

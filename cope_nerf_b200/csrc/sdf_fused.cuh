@@ -48,7 +48,6 @@ struct FzArgs {
   float* eb0; float* eb1;    // [P x 64] fp32 (want_e)
   int has_d, store_out, want_e;
   long long* dbg;            // optional timeline buffer (profiling builds): CTA 0 stamps clock64() per role
-  int max_ctas;              // host only: CTAs (= SMs) the launch may use (0: all), for kernels that run beside another one
 };
 
 // 3-D tensor maps (64 x 128 x 1 boxes, 128B swizzle) over bf16 [layers][P][ld] buffers

@@ -717,9 +717,8 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s) {
 
 // All problems in one launch (L2 reductions into dW / db); CTAs are shared out in proportion to the bytes each problem
 // streams.  COPE_WGRAD_DETERMINISTIC=1 falls back to one launch per problem with the fixed-order reduction.
-int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s, int max_ctas) {
+int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s) {
   if (n <= 0) return 0;
-  const int kSm = std::max(8, std::min(148, max_ctas > 0 ? max_ctas : 148));     // CTAs (= SMs: one CTA per SM) this launch may use
   if (getenv("COPE_WGRAD_DETERMINISTIC") != nullptr || n > kWgMaxProb) {
     for (int i = 0; i < n; ++i)
       if (int rc = launch_tc_wgrad(probs[i], s)) return rc;
@@ -747,10 +746,10 @@ int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s, int m
     int total = 0, nct[kWgMaxProb];
     for (int i = 0; i < m; ++i) {
       const int64_t nchunks = (batch->p[i].P + kWgChunkP - 1) / kWgChunkP;
-      nct[i] = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)((double)kSm * w[i] / wsum)));
+      nct[i] = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)(148.0 * w[i] / wsum)));
       total += nct[i];
     }
-    for (int i = 0; total < kSm && i < 8 * m; ++i) {           // hand the left-over SMs to the heaviest problems
+    for (int i = 0; total < 148 && i < 8 * m; ++i) {           // hand the left-over SMs to the heaviest problems
       const int k = i % m;
       const int64_t nchunks = (batch->p[k].P + kWgChunkP - 1) / kWgChunkP;
       if (w[k] * m >= wsum && nct[k] < nchunks) { ++nct[k]; ++total; }

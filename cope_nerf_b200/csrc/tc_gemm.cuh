@@ -58,7 +58,7 @@ struct TcWgradArgs {
 };
 int64_t tc_wgrad_part_floats();
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t s);
-int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s, int max_ctas = 0);
+int launch_tc_wgrad_batch(const TcWgradArgs* probs, int n, cudaStream_t s);
 
 // packed[(k/8) * Np + n][k%8] = W[sn * ldw + sk] (transposed: W[sk * ldw + sn]) where sn / sk are the source indices
 // that the segment lists map packed row n / packed k to (unmapped -> 0).  Jobs are queued into a PackBatch and
