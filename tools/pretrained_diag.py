@@ -10,7 +10,9 @@ from test_gpu_parity import renderer_from, cu
 
 g, P = _pretrained_params()
 Kc = O.camera_matrix(0.8 * 1275, 0.8 * 1275, 1275, 717).unsqueeze(0)
-for n in (48, 256):
+import os
+print('COPE_NO_FUSED =', os.environ.get('COPE_NO_FUSED'))
+for n in (int(os.environ.get('DIAG_N', '256')),):
     torch.manual_seed(23)
     pix = (torch.rand(1, n, 2) * 2 - 1) * 0.8
     pix[0, :, 1] = pix[0, :, 1].abs()
@@ -35,6 +37,9 @@ for n in (48, 256):
             cs = {k: cos_sim(p.grad, Pg['sdf'][k].grad) for k, p in r.sdf_network.named_parameters() if Pg['sdf'][k].grad.abs().max() > 0}
             res[prec] = cs
             if prec == C.PREC_BF16:
+                oo = aux['out']
+                fe = {k: rel_err(out[k], oo[k]) for k in ('sdf', 'normals', 'sdf_flows', 'weights', 'color_fine', 'depth_pred')}
+                print("   forward rel err:", {k: f"{v:.2e}" for k, v in fe.items()}, "sdf abs mean", f"{float((out['sdf'].cpu() - oo['sdf']).abs().mean()):.2e}")
                 nrm = out['normals'].reshape(-1, 3).norm(dim=-1)
                 on = aux['out']['normals'].reshape(-1, 3).norm(dim=-1)
                 print(f"   |n|-1: oracle mean {float((on - 1).abs().mean()):.4e}  bf16-vs-oracle |n| abs err mean {float((nrm.cpu() - on).abs().mean()):.4e}")
