@@ -60,7 +60,7 @@ _SIGS = {
     "cope_dbg_render_bwd_eb_offset": (_l, [_D, _D, _l]),
     "cope_render_mlp_infer_ws_floats": (_l, [_D, _D, _l, _i]),
     "cope_render_mlp_infer": (_i, [_D, _f, _D, _f, _f, _f, _i, _i, _l, _f, _f, _f, _f, _i, _f]),
-    "cope_eval_reduce": (_i, [_f, _f, _f, _f, _l, _i, _f, _f, _f]),
+    "cope_eval_reduce": (_i, [_f, _f, _f, _f, _l, _i, _f, _f, _f, _f, _f, _fl, _fl, _f, _f]),
     "cope_pose_integrate_fwd": (_i, [_f, _f, _i, _i, _f, _f]),
     "cope_pose_integrate_bwd": (_i, [_f, _f, _i, _i, _f, _f, _f, _f]),
     "cope_pose_chain_fwd": (_i, [_f, _i, _f, _f]),
@@ -90,6 +90,8 @@ _SIGS = {
     "cope_flow_rgb_bwd": (_i, [_f] * 7 + [_l, _i, _i, _i, _f, _f, _f, _f, _f]),
     "cope_patch_smooth_fwd": (_i, [_f, _f, _l, _i, _fl, _fl, _fl, _f, _f, _f]),
     "cope_patch_smooth_bwd": (_i, [_f, _f, _l, _i, _fl, _fl, _fl, _f, _f, _f]),
+    "cope_pose_refine_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
+    "cope_pose_refine_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
     "cope_sample_pixels": (_i, [_f, C.c_uint64, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }

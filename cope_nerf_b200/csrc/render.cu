@@ -788,22 +788,39 @@ int cope_composite_bwd(const float* sdf, const float* grad, const float* rgb, co
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------ evaluation-render reductions
-// model/training.py:236-262: one warp per ray; weighted normal sum + arg-max-weight sample depth in the camera frame
+// model/training.py:236-283: one warp per ray; weighted normal sum + arg-max-weight sample depth in the camera frame + (optional)
+// the predicted forward optical flow.  The reference integrates the scene flow of EVERY sample point over the sub-steps
+// (p <- p + dt (w_t x p + v_t), :269-272) and then takes the weight average (:273-275); each sub-step is affine in p, so the
+// whole integration is one 3 x 4 affine map F and  sum_s w (F [p; 1]) = F [sum_s w p; sum_s w]  - four numbers per ray.
 namespace cope {
+struct FlowMapArgs {
+  const float* F;          // [12] row-major 3 x 4 affine scene-flow map (null: no flow output)
+  const float* KS;         // [9]  scale_mat[:3,:3] @ camera_mat[:3,:3]
+  const float* pix;        // [N x 2] normalised pixel of each ray
+  float sx, sy;            // w / 2, h / 2 (:296-297)
+  float* flow;             // [N x 2] flow in pixels
+};
 __global__ void eval_reduce_kernel(const float* __restrict__ w, const float4* __restrict__ grad, const float4* __restrict__ pts,
-                                   const float* __restrict__ M, int64_t N, int S, float* __restrict__ nrm, float* __restrict__ dhw) {
+                                   const float* __restrict__ M, int64_t N, int S, float* __restrict__ nrm, float* __restrict__ dhw,
+                                   const FlowMapArgs fa) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= N) return;
   float ax = 0.0f, ay = 0.0f, az = 0.0f, best = -1.0f;
+  float px = 0.0f, py = 0.0f, pz = 0.0f, pw = 0.0f;
   int besti = 0;
   for (int s = lane; s < S; s += 32) {
     const float wv = w[n * S + s];
     const float4 g = grad[n * S + s];
     ax = fmaf(wv, g.x, ax); ay = fmaf(wv, g.y, ay); az = fmaf(wv, g.z, az);
+    if (fa.F) {
+      const float4 p = pts[n * S + s];
+      px = fmaf(wv, p.x, px); py = fmaf(wv, p.y, py); pz = fmaf(wv, p.z, pz); pw += wv;
+    }
     if (wv > best) { best = wv; besti = s; }          // first maximum within the lane (torch.max returns the first index)
   }
   ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+  if (fa.F) { px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz); pw = warp_sum(pw); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -816,18 +833,30 @@ __global__ void eval_reduce_kernel(const float* __restrict__ w, const float4* __
     nrm[n * 3 + 2] = M[8] * ax + M[9] * ay + M[10] * az;
     const float4 p = pts[n * S + besti];
     dhw[n] = -(M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
+    if (fa.F) {
+      float m[3], q[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) m[r] = fa.F[r * 4] * px + fa.F[r * 4 + 1] * py + fa.F[r * 4 + 2] * pz + fa.F[r * 4 + 3] * pw;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) q[r] = fa.KS[r * 3] * m[0] + fa.KS[r * 3 + 1] * m[1] + fa.KS[r * 3 + 2] * m[2];
+      fa.flow[n * 2] = (q[0] / q[2] - fa.pix[n * 2]) * fa.sx;
+      fa.flow[n * 2 + 1] = (q[1] / q[2] - fa.pix[n * 2 + 1]) * fa.sy;
+    }
   }
 }
 }  // namespace cope
 
 extern "C" int cope_eval_reduce(const float* weights, const float* grad, const float* pts, const float* world_mat, int64_t N, int S,
-                                float* normal_out, float* depth_hw_out, cope_stream_t s) {
+                                float* normal_out, float* depth_hw_out, const float* flow_affine, const float* KS,
+                                const float* pix_norm, float flow_sx, float flow_sy, float* flow_out, cope_stream_t s) {
   using namespace cope;
   if (N <= 0) return 0;
   COPE_REQUIRE(S > 0 && weights && grad && pts && world_mat && normal_out && depth_hw_out, "eval_reduce: null argument");
+  COPE_REQUIRE(!flow_affine || (KS && pix_norm && flow_out), "eval_reduce: the flow output needs KS, pix_norm and flow_out");
+  FlowMapArgs fa{flow_affine, KS, pix_norm, flow_sx, flow_sy, flow_out};
   eval_reduce_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, as_stream(s)>>>(weights, reinterpret_cast<const float4*>(grad),
                                                                         reinterpret_cast<const float4*>(pts), world_mat, N, S,
-                                                                        normal_out, depth_hw_out);
+                                                                        normal_out, depth_hw_out, fa);
   COPE_CHECK_LAUNCH("eval_reduce");
   return 0;
 }

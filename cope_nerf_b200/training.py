@@ -8,7 +8,7 @@ import torch
 from .common import get_world_cameraOrigin_cameraRay, pixels_from_indices
 
 __all__ = ["near_far_from_sphere", "get_cos_anneal_ratio", "get_patch_indices", "process_data", "sample_rays", "eikonal_loss",
-           "rgb_l1_loss", "sdf_flow_loss", "neus_losses", "render_train_step", "build_networks", "DEFAULT_CFG"]
+           "rgb_l1_loss", "sdf_flow_loss", "neus_losses", "render_train_step", "build_networks", "DEFAULT_CFG", "render_image", "scene_flow_affine"]
 
 # configs/default.yaml:103-156
 DEFAULT_CFG = dict(
@@ -139,16 +139,39 @@ def render_train_step(renderer, pose, cam_id, pixels, camera_mat, scale_mat, rgb
     return loss.detach(), out, (o, d, dn)
 
 
-def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, depth_range, cos_anneal_ratio=1.0, it=1,
-                 chunk=8192, rays=None):
-    """Full-image evaluation render (model/training.py:157-283 render_visdata / eval.py:133-157 render_eval, the
-    rgb / depth / normal part) without the reference's 1024-ray chunks and per-chunk device -> host copies: the image is
-    rendered in `chunk`-ray launches, every result stays on the device.
+def scene_flow_affine(motion_network, time_step, next_time_step, n_sub):
+    """The scene-flow integration of model/training.py:202-207, 269-272 as ONE affine map F [3,4]: the reference moves every sample
+    point through n_sub Euler sub-steps p <- p + dt (w_t x p + v_t), w_t / v_t = motion_network at linspace(time_step,
+    next_time_step, n_sub + 1)[:-1], dt = (next_time_step - time_step) / n_sub.  Each sub-step is affine in p, so their composition is
+    M_{n-1} ... M_0 with M_t = [[I + dt [w_t]x, dt v_t], [0, 1]] - one batched network call + one chain launch (cope_pose_chain_fwd)."""
+    from .motion import _ChainFn
+    dev = motion_network.lin0.bias.device
+    ts = torch.linspace(float(time_step), float(next_time_step), int(n_sub) + 1)[:-1].view(-1, 1).to(dev)
+    ang, vel = motion_network(ts)
+    dt = (float(next_time_step) - float(time_step)) / int(n_sub)
+    z = torch.zeros_like(ang[:, 0])
+    skew = torch.stack([torch.stack([z, -ang[:, 2], ang[:, 1]], -1), torch.stack([ang[:, 2], z, -ang[:, 0]], -1),
+                        torch.stack([-ang[:, 1], ang[:, 0], z], -1)], dim=1)                  # [w]x, model/common.py:255-265 layout
+    M = torch.eye(4, dtype=torch.float32, device=dev).repeat(int(n_sub), 1, 1)
+    M[:, :3, :3] += dt * skew
+    M[:, :3, 3] = dt * vel
+    return _ChainFn.apply(M)[-1][:3].contiguous()
 
-    Returns a dict of device tensors over all h*w pixels (row-major):
+
+def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, depth_range, cos_anneal_ratio=1.0, it=1,
+                 chunk=None, rays=None, flow=None):
+    """Full-image evaluation render (model/training.py:157-283 render_visdata / eval.py:133-157 render_eval: rgb, depth, normal and
+    predicted-optical-flow maps) without the reference's 1024-ray chunk loop and its per-chunk device -> host copies.
+
+    chunk=None renders the whole pixel range in ONE pass (one launch per kernel of the pipeline) whenever its working set fits the
+    free device memory, and otherwise in the fewest equal passes that do (the inference path keeps ~7 kB per sample point);
+    an integer forces that many rays per pass.  Every result stays on the device.
+
+    Returns a dict of device tensors over the rendered pixels (row-major):
       rgb (HW,3), depth_pred (HW,1) [= sum w z / |d|, eval mode], weighted_z_vals (HW,1),
       depth_highest_weight (HW,) [-z of the arg-max-weight sample in the camera frame], normal (HW,3) [sum w n, rotated
-      into the camera frame by world_mat[:3,:3]].
+      into the camera frame by world_mat[:3,:3]], and with `flow` = (motion_network, time_step, next_time_step, n_sub) also
+      flow_pred (HW,2): the forward optical flow in pixels (:265-283, 296-297; n_sub = nb_sample_timestep * frame distance, :202).
     `rays` = (first, count) restricts the render to a contiguous pixel range (multi-GPU: one range per rank)."""
     from . import _lib as L
     from .common import get_world_cameraOrigin_cameraRay, pixels_from_indices
@@ -158,6 +181,19 @@ def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, de
                weighted_z_vals=torch.empty(count, 1, device=dev), depth_highest_weight=torch.empty(count, device=dev),
                normal=torch.empty(count, 3, device=dev))
     wm = world_mat.detach().contiguous().float()
+    F = KS = None
+    if flow is not None:
+        with torch.no_grad():
+            F = scene_flow_affine(*flow)
+            KS = (scale_mat.reshape(-1, 4, 4)[0, :3, :3] @ camera_mat.reshape(-1, 4, 4)[0, :3, :3]).contiguous().float()
+        out["flow_pred"] = torch.empty(count, 2, device=dev)
+    if chunk is None:
+        n_samples = renderer.n_samples + renderer.n_importance
+        per_ray = n_samples * 7168 + 4096                      # bytes per ray of the inference path (saved H stack + colour input + outputs)
+        free = torch.cuda.mem_get_info(dev)[0] if torch.cuda.is_available() else 0
+        budget = max(int(free * 0.6), per_ray * 1024)
+        passes = max(1, -(-count * per_ray // budget))
+        chunk = -(-count // passes)
     with torch.no_grad():
         for c0 in range(0, count, chunk):
             n = min(chunk, count - c0)
@@ -168,7 +204,9 @@ def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, de
             ro = renderer(o, d, dn, time_step, near, far, cos_anneal_ratio=cos_anneal_ratio, it=it, eval=True)
             S = ro['weights'].shape[1]
             L.call("cope_eval_reduce", L.ptr(ro['weights']), L.ptr(ro.grad4), L.ptr(ro.pts4), L.ptr(wm), n, S,
-                   L.ptr(out['normal'][c0:c0 + n]), L.ptr(out['depth_highest_weight'][c0:c0 + n]), L.stream())
+                   L.ptr(out['normal'][c0:c0 + n]), L.ptr(out['depth_highest_weight'][c0:c0 + n]),
+                   L.ptr(F), L.ptr(KS), L.ptr(pix.reshape(-1, 2).contiguous()) if F is not None else None, w / 2.0, h / 2.0,
+                   L.ptr(out['flow_pred'][c0:c0 + n]) if F is not None else None, L.stream())
             out['rgb'][c0:c0 + n] = ro['color_fine']
             out['depth_pred'][c0:c0 + n] = ro['depth_pred']
             out['weighted_z_vals'][c0:c0 + n] = ro['weighted_z_vals']

@@ -247,10 +247,15 @@ int cope_pose_integrate_bwd(const float* wv, const float* dt, int F, int n_sub, 
 int cope_pose_chain_fwd(const float* rel, int F, float* w2c, cope_stream_t s);
 int cope_pose_chain_bwd(const float* rel, const float* w2c, int F, const float* d_w2c, float* d_rel, cope_stream_t s);
 
-/* ---- per-ray image reductions of the evaluation render (model/training.py:236-262): normal[n] = R * sum_s w[n,s] * grad[n,s,:3]
- * and depth_hw[n] = -(world_mat @ [pts[n, argmax_s w], 1]).z, world_mat = device pointer to a row-major 4x4 (R = its 3x3). */
+/* ---- per-ray image reductions of the evaluation render (model/training.py:236-283): normal[n] = R * sum_s w[n,s] * grad[n,s,:3]
+ * and depth_hw[n] = -(world_mat @ [pts[n, argmax_s w], 1]).z, world_mat = device pointer to a row-major 4x4 (R = its 3x3).
+ * Optional (flow_affine != NULL): the predicted forward optical flow of :265-283, flow[n] = (proj(KS * F [sum_s w p; sum_s w]) -
+ * pix_norm[n]) * (flow_sx, flow_sy), where F [3 x 4] is the scene-flow integration of the sub-steps composed into one affine map
+ * (each Euler sub-step p <- p + dt (w x p + v) is affine in p), KS [3 x 3] = scale_mat[:3,:3] @ camera_mat[:3,:3], pix_norm
+ * [N x 2] the rays' normalised pixels and flow_sx / flow_sy = w / 2, h / 2 (:296-297). */
 int cope_eval_reduce(const float* weights, const float* grad, const float* pts, const float* world_mat, int64_t N, int S,
-                     float* normal_out, float* depth_hw_out, cope_stream_t s);
+                     float* normal_out, float* depth_hw_out, const float* flow_affine, const float* KS, const float* pix_norm,
+                     float flow_sx, float flow_sy, float* flow_out, cope_stream_t s);
 
 /* ---- loss reductions of the training step (SURVEY.md 8 a17 + 8f rank 2), one forward + one backward launch per group -------
  * cope_step_losses_*: rgb L1 (model/training.py:508), eikonal (train.py:526) and, when `motion` != NULL, the SDF-flow loss
@@ -293,6 +298,16 @@ int cope_patch_smooth_fwd(const float* depth, const float* rgb, int64_t n_patche
                           float w_smooth, float* losses, float* ws, cope_stream_t s);
 int cope_patch_smooth_bwd(const float* depth, const float* rgb, int64_t n_patches, int ps, float gamma, float w_edge,
                           float w_smooth, const float* g, float* d_depth, cope_stream_t s);
+
+/* ---- photometric relative-pose refinement (utils_poses/pose_refinement.py:34-61 compute_loss_and_warp_image) --------------
+ * images / next_images [B x 3 x H x W], depths [B x H x W] (of `images`), K [B x 3 x 3] (maps camera xyz to the normalised
+ * [-1,1] pixel grid of pose_refinement.py:88-96), poses [B x 4 x 4] relative camera poses.  loss[0] = sum |warp(next_images) -
+ * images| valid / sum valid; warped [B x 3 x H x W] may be NULL; ws: 4 floats, kept for the backward.  The backward ACCUMULATES
+ * g[0] * d loss / d poses into d_poses [B x 4 x 4] (rows 0..2; the caller zero-fills). */
+int cope_pose_refine_fwd(const float* images, const float* next_images, const float* depths, const float* K, const float* poses,
+                         int B, int H, int W, float* warped, float* loss, float* ws, cope_stream_t s);
+int cope_pose_refine_bwd(const float* images, const float* next_images, const float* depths, const float* K, const float* poses,
+                         int B, int H, int W, const float* ws, const float* g, float* d_poses, cope_stream_t s);
 
 /* ---- training-pixel selection (process_data, model/training.py:413-471; arange_pixels, model/common.py:12-39) ----------
  * n_patches patch_size x patch_size patches of an h x w frame -> N = n_patches * patch_size^2 rays, row-major inside each patch:

@@ -26,7 +26,7 @@ __all__ = [
     "MOTION_CFG", "init_motion_params", "motion_forward", "euler_xyz_to_matrix", "consecutive_relative_pose",
     "relative_camera_pose", "w2c_mappings",
     "warp_pixel", "flow_forward_prediction", "flow_rgb_loss", "sdf_consistency_loss", "stage1_losses",
-    "smoothness_loss", "edge_smoothness_loss", "stage1_step",
+    "smoothness_loss", "edge_smoothness_loss", "stage1_step", "refine_uv", "compute_loss_and_warp_image",
 ]
 
 # configs/default.yaml:103-156 (no scene config overrides any of these shapes)
@@ -453,13 +453,21 @@ def train_step(P, pose, pixels, camera_mat, scale_mat, rgb_gt, t, depth_range, c
     return loss, dict(out=out, rays_o=o, rays_d=d, rays_d_norm=dn, loss_rgb=l_rgb, loss_eikonal=l_eik)
 
 
-def render_image(P, world_mat, camera_mat, scale_mat, h, w, t, depth_range, cos_anneal=1.0, chunk=1024, cfg=None):
-    """Evaluation image render, restating model/training.py:210-283 (render_visdata: the rgb / depth / weighted-z /
-    depth_highest_weight / normal part; the optical-flow part belongs to the MotionNetwork and is out of scope).
+def render_image(P, world_mat, camera_mat, scale_mat, h, w, t, depth_range, cos_anneal=1.0, chunk=1024, cfg=None, flow=None):
+    """Evaluation image render, restating model/training.py:210-283 (render_visdata: rgb / depth / weighted-z /
+    depth_highest_weight / normal maps and, with flow = (motion_params, time_step, next_time_step, n_sub), the predicted forward
+    optical flow of :203-208, 265-283, 296-297).
     1024-ray chunks as the reference (:210); each chunk: rays (:213), near/far (:217), renderer(eval=True) (:220),
-    arg-max-weight depth (:236-243), normal = sum_s normals * weights (:256-262)."""
+    arg-max-weight depth (:236-243), normal = sum_s normals * weights (:256-262), scene-flow integration of every sample point
+    over the sub-steps (:269-272), weight average (:273-275), projection and flow (:277-280)."""
     _, sc = pixel_grid(h, w)
-    rgb, depth, wz, dhw, nrm = [], [], [], [], []
+    rgb, depth, wz, dhw, nrm, flw = [], [], [], [], [], []
+    ang_list, vel_list = [], []
+    if flow is not None:
+        mp, t0, t1, n_sub = flow
+        for tt in torch.linspace(float(t0), float(t1), int(n_sub) + 1)[:-1]:          # :205-208
+            a_t, v_t = motion_forward(mp, tt.view(-1, 1))
+            ang_list.append(a_t); vel_list.append(v_t)
     with torch.no_grad():
         for i in range(0, h * w, chunk):
             pix = sc[:, i:i + chunk]
@@ -477,8 +485,22 @@ def render_image(P, world_mat, camera_mat, scale_mat, h, w, t, depth_range, cos_
             nn_ = (out["normals"] * wts[:, :, None]).sum(dim=1)
             nrm.append((world_mat[:3, :3] @ nn_.T).T)
             rgb.append(out["color_fine"]); depth.append(out["depth_pred"]); wz.append(out["weighted_z_vals"])
-    return dict(rgb=torch.cat(rgb), depth_pred=torch.cat(depth), weighted_z_vals=torch.cat(wz),
-                depth_highest_weight=torch.cat(dhw), normal=torch.cat(nrm))
+            if flow is not None:
+                pts_sf = torch.clone(pts)
+                interval = (float(t1) - float(t0)) / int(n_sub)
+                for k in range(int(n_sub)):
+                    sf = torch.linalg.cross(ang_list[k].expand_as(pts_sf), pts_sf) + vel_list[k]
+                    pts_sf = pts_sf + interval * sf
+                pts_sf = torch.sum(wts.view(n, -1, 1) * pts_sf.view(n, -1, 3), dim=1)
+                pm = (scale_mat[0, :3, :3] @ camera_mat[0, :3, :3] @ pts_sf.T).T
+                pm = pm[:, :2] / pm[:, 2:]
+                fl = pm - pix[0]
+                flw.append(torch.stack([fl[:, 0] * (w / 2), fl[:, 1] * (h / 2)], dim=-1))     # :296-297
+    res = dict(rgb=torch.cat(rgb), depth_pred=torch.cat(depth), weighted_z_vals=torch.cat(wz),
+               depth_highest_weight=torch.cat(dhw), normal=torch.cat(nrm))
+    if flow is not None:
+        res["flow_pred"] = torch.cat(flw)
+    return res
 
 
 # --------------------------------------------------------------------------- continuous pose model (MotionNetwork)
@@ -725,3 +747,25 @@ def stage1_step(P, motion_params, rays_o, rays_d, rays_d_norm, near, far, rgb_gt
     loss = sum(weights[k] * parts[k] for k in parts)                              # model/training.py:525-531
     parts["flow_fw_pred"] = aux["flow_fw_pred"]
     return loss, parts, out
+
+
+# --------------------------------------------------------------------------- pose refinement
+def refine_uv(h, w):
+    """utils_poses/pose_refinement.py:88-96: [3, H, W] = (col, row, 1) with col, row normalised to [-1, 1]."""
+    rows, cols = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    return torch.stack([cols / ((w - 1) / 2) - 1, rows / ((h - 1) / 2) - 1, torch.ones_like(rows)])
+
+
+def compute_loss_and_warp_image(images, next_images, depths, K_batch, uv_batch, relative_poses):
+    """utils_poses/pose_refinement.py:34-61 with warp_pixel_fn = train.py:235-244 (normalize_pix=False)."""
+    n = len(images)
+    xyz = torch.inverse(K_batch) @ ((uv_batch * depths).view(n, 3, -1))
+    txyz = relative_poses[:, :3, :3] @ xyz + relative_poses[:, :3, 3:]
+    tuv = K_batch @ txyz
+    tdepth = tuv[:, 2:3]
+    tuv = (tuv[:, :2] / tdepth).view(uv_batch[:, :2].shape)
+    valid = ((tuv[:, 0] >= -1) & (tuv[:, 0] <= 1) & (tuv[:, 1] >= -1) & (tuv[:, 1] <= 1)).float().unsqueeze(1)
+    coord = torch.stack([tuv[:, 0], tuv[:, 1]], dim=-1)
+    warped = F.grid_sample(next_images, coord, mode="bilinear", padding_mode="border", align_corners=True)
+    loss = torch.sum(torch.abs(warped - images) * valid) / torch.sum(valid)
+    return loss, warped

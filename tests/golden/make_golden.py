@@ -654,6 +654,88 @@ def main():
     pre.update({f"param.{k}": v for k, v in sd_pre.items()})
     G["pretrained_sdf"] = npd(pre)
 
+
+    # ---------------------------------------------------------------- pose refinement (utils_poses/pose_refinement.py:34-61, 117-126)
+    # compute_loss_and_warp_image is executed from the mounted source (the module itself imports tqdm / `from model import
+    # PoseRetriever`, which the shimmed package does not export); warp_pixel is train.py:235-244; the symmetric loss and the
+    # PoseRetriever gradients follow lines 117-126 with the imported reference PoseRetriever.
+    psrc = open(os.path.join(REF, "utils_poses", "pose_refinement.py")).read().split("\n")
+    pns = {"torch": torch, "np": np}
+    exec("\n".join(psrc[33:61]), pns)
+    Bp, Hp, Wp = 3, 20, 28
+    yy, xx = torch.meshgrid(torch.arange(Hp).float(), torch.arange(Wp).float(), indexing="ij")
+    wavep = lambda a, b, c: 0.5 + 0.4 * torch.sin(a * xx + b * yy + c)
+    frames = torch.stack([torch.stack([wavep(0.3 + 0.05 * k, 0.2 + 0.04 * c, 0.7 * k + c) for c in range(3)]) for k in range(Bp + 1)])
+    images_p, next_p = frames[:-1].clone(), frames[1:].clone()
+    torch.manual_seed(71)
+    depths_p = 2.0 + 0.3 * torch.sin(0.2 * xx + 0.1 * yy)[None, None].repeat(Bp, 1, 1, 1) + 0.05 * torch.rand(Bp, 1, Hp, Wp)
+    next_depths_p = depths_p + 0.02 * torch.rand(Bp, 1, Hp, Wp)
+    K_p = torch.tensor([[1.6, 0.0, 0.05], [0.0, 2.1, -0.03], [0.0, 0.0, 1.0]]).repeat(Bp, 1, 1) * torch.tensor([1.0, 1.02, 0.98]).view(Bp, 1, 1)
+    K_p[:, 2, 2] = 1.0
+    uv_p = O.refine_uv(Hp, Wp)
+    uv_b = uv_p.unsqueeze(0).repeat(Bp, 1, 1, 1)
+    rp = R.poses.PoseRetriever(Bp)
+    with torch.no_grad():
+        rp.r.copy_(torch.randn(Bp, 3) * 0.04); rp.t.copy_(torch.randn(Bp, 3) * 0.08)
+    fake_w = types.SimpleNamespace()
+    warp_fn = types.MethodType(ns["warp_pixel"], fake_w)
+    rel_p = torch.stack([rp(i) for i in range(Bp)])
+    lp, wp_img = pns["compute_loss_and_warp_image"](images_p, next_p, depths_p, K_p, uv_b, rel_p, warp_fn)
+    ln, wn_img = pns["compute_loss_and_warp_image"](next_p, images_p, next_depths_p, K_p, uv_b, torch.inverse(rel_p), warp_fn)
+    ((lp + ln) / 2).backward()
+    pose_o = {k: v.detach().clone() for k, v in rp.state_dict().items()}
+    pose_o["r"].requires_grad_(True); pose_o["t"].requires_grad_(True)
+    rel_o = torch.stack([O.pose_forward(pose_o, i) for i in range(Bp)])
+    olp, owp = O.compute_loss_and_warp_image(images_p, next_p, depths_p, K_p, uv_b, rel_o)
+    oln, own = O.compute_loss_and_warp_image(next_p, images_p, next_depths_p, K_p, uv_b, torch.inverse(rel_o))
+    ((olp + oln) / 2).backward()
+    close(olp, lp, 1e-6, "refine loss pos"); close(oln, ln, 1e-6, "refine loss neg"); close(owp, wp_img, 1e-6, "refine warped")
+    close(pose_o["r"].grad, rp.r.grad, 1e-5, "refine dr"); close(pose_o["t"].grad, rp.t.grad, 1e-5, "refine dt")
+    G["pose_refine_small"] = npd(dict(images=images_p, next_images=next_p, depths=depths_p, next_depths=next_depths_p, K=K_p, r=rp.r.detach(),
+                                      t=rp.t.detach(), rel=rel_p, loss_pos=lp, loss_neg=ln, warped_pos=wp_img, warped_neg=wn_img,
+                                      dr=rp.r.grad, dt=rp.t.grad))
+    print("pose refine: loss", float(lp), float(ln), "valid frac", float(((wp_img - images_p).abs().sum() > 0)))
+
+
+    # ---------------------------------------------------------------- predicted optical flow of the evaluation render
+    # model/training.py:203-208 (motion samples), :269-280 (per-point scene-flow integration, weight average, projection) and
+    # :296-297 (pixel units), executed from the mounted source on the renderer outputs of the small networks.
+    tsrc = open(os.path.join(REF, "model", "training.py")).read().split("\n")
+    fns = {"torch": torch, "np": np}
+    exec("def flow_block(pts, weights, rgb_pred_i, angular_velocity_list, velocity_list, next_time_step, time_step, nb_sample_timestep,\n"
+         "               scale_mat, camera_mat, pixels_i):\n" + textwrap.indent(textwrap.dedent("\n".join(tsrc[268:280])), "    ")
+         + "\n    return flow_fw_pred_i[0]\n", fns)
+    Hf, Wf = 10, 14
+    Kf = O.camera_matrix(0.8 * Wf, 0.8 * Wf, Wf, Hf).unsqueeze(0)
+    wf = torch.eye(4); wf[2, 3] = -2.0
+    _, pix_f = R.common.arange_pixels((Hf, Wf), 1)
+    t0f, t1f, nsub_f = torch.tensor([0.1]), torch.tensor([0.5]), 6
+    angs, vels = [], []
+    for tt_ in torch.linspace(t0f.item(), t1f.item(), nsub_f + 1)[:-1]:
+        a_t, v_t = f_mot(tt_.view(-1, 1))
+        angs.append(a_t.detach()); vels.append(v_t.detach())
+    flows_ref = []
+    with torch.no_grad():
+        o_f, d_f, dn_f = TT.get_world_cameraOrigin_cameraRay(None, pix_f, Kf, wf, Sc2)
+        nr_f, fr_f = TT.near_far_from_sphere(types.SimpleNamespace(depth_range=[0.5, 3.5]), o_f, d_f)
+        ro_f = f_rnd(o_f, d_f, dn_f, t0f, nr_f, fr_f, background_rgb=None, cos_anneal_ratio=1.0, it=1, eval=True)
+        fl_ref = fns["flow_block"](ro_f["sampled_points"].view(-1, 3), ro_f["weights"], ro_f["color_fine"], angs, vels, t1f, t0f, nsub_f,
+                                   Sc2, Kf, pix_f)
+        fl_ref = torch.stack([fl_ref[:, 0] * (Wf / 2), fl_ref[:, 1] * (Hf / 2)], dim=-1)
+    Pf = {tag: {k: v.detach().clone() for k, v in m.state_dict().items()} for tag, m in (("sdf", f_sdf), ("color", f_col), ("variance", f_var))}
+    mpf = {k: v.detach().clone() for k, v in f_mot.state_dict().items()}
+    of = O.render_image(Pf, wf, Kf, Sc2, Hf, Wf, t0f, [0.5, 3.5], cos_anneal=1.0, chunk=64, flow=(mpf, t0f, t1f, nsub_f))
+    # rays that miss the surface carry weights ~1e-5 per sample: their weight-averaged point is a ratio of two tiny sums and
+    # amplifies the 2e-5 renderer tolerance; the comparison is relative to the largest flow of the frame
+    print("eval flow map: max |oracle - reference|", float((of["flow_pred"] - fl_ref).abs().max()), "px of", float(fl_ref.abs().max()))
+    close(of["flow_pred"], fl_ref, 5e-4, "eval flow map")
+    close(of["rgb"], ro_f["color_fine"], 5e-4, "eval flow rgb")      # rays that graze the surface: 64 * 2^i up-sampling sharpness
+    print("eval flow map: |flow| mean", float(fl_ref.abs().mean()), "px")
+    fm = dict(H=Hf, W=Wf, K=Kf, world=wf, t0=t0f, t1=t1f, n_sub=nsub_f, flow_pred=fl_ref, rgb=ro_f["color_fine"])
+    for tag, d_ in (("sdf", Pf["sdf"]), ("color", Pf["color"]), ("variance", Pf["variance"]), ("motion", mpf)):
+        fm.update({f"param.{tag}.{k}": v for k, v in d_.items()})
+    G["eval_flow_small"] = npd(fm)
+
     only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     for name, d in G.items():
         if only and name not in only:

@@ -346,3 +346,67 @@ def test_composite_vector_path_matches_scalar_path_and_oracle(eval_mode, monkeyp
     assert rel_err(vec["weights"], w) < 1e-4 and rel_err(vec["color"], color) < 1e-4 and rel_err(vec["depth"], depth) < 1e-4
     assert rel_err(vec["d_sdf"], lv["sdf"].grad) < 1e-3 and rel_err(vec["d_grad"], lv["grad"].grad) < 1e-3
     assert rel_err(vec["d_rgb"], lv["rgb"].grad) < 1e-4 and rel_err(vec["d_var"], lv["var"].grad.reshape(1)) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rank 4 + rest of rank 3
+def test_pose_refinement_golden():
+    """Photometric relative-pose refinement (utils_poses/pose_refinement.py:34-61, 117-126): loss, warped frames and the
+    PoseRetriever gradients of both directions against the fixture of the reference's own lines; then a few Adam steps of
+    `perform_pose_refinement` must lower the loss."""
+    from cope_nerf_b200 import pose_refinement as PR
+    g = load_golden("pose_refine_small")
+    B, _, H, W = g["images"].shape
+    pr = C.PoseRetriever(B).to(DEV)
+    with torch.no_grad():
+        pr.r.copy_(g["r"]); pr.t.copy_(g["t"])
+    rel = torch.stack([pr(i) for i in range(B)])
+    assert_close(rel, g["rel"], 1e-6, "relative poses")
+    uv = PR.make_uv((H, W), DEV)
+    assert_close(uv, O.refine_uv(H, W), 1e-7, "uv grid")
+    lp, wp = PR.compute_loss_and_warp_image(cu(g["images"]), cu(g["next_images"]), cu(g["depths"]), cu(g["K"]), None, rel)
+    inv = torch.stack([C.losses.rigid_inverse(p) for p in rel])
+    ln, wn = PR.compute_loss_and_warp_image(cu(g["next_images"]), cu(g["images"]), cu(g["next_depths"]), cu(g["K"]), None, inv)
+    assert rel_err(lp, g["loss_pos"]) < 1e-5 and rel_err(ln, g["loss_neg"]) < 1e-5, (float(lp), float(ln))
+    assert_close(wp, g["warped_pos"], 1e-5, "warped pos"); assert_close(wn, g["warped_neg"], 1e-5, "warped neg")
+    ((lp + ln) / 2).backward()
+    e_r, e_t = rel_err(pr.r.grad, g["dr"]), rel_err(pr.t.grad, g["dt"])
+    assert e_r < 1e-3 and e_t < 1e-3, (e_r, e_t)
+    # the symmetric loss through the module-level helper == the two calls above
+    pr.zero_grad()
+    l2 = PR.refinement_losses(pr, range(B), cu(g["images"]), cu(g["next_images"]), cu(g["depths"]), cu(g["next_depths"]), cu(g["K"]))
+    assert rel_err(l2, (g["loss_pos"] + g["loss_neg"]) / 2) < 1e-5
+    # optimisation loop (pose_refinement.py:104-150): the loss goes down
+    opt = torch.optim.Adam(pr.parameters(), lr=2e-3)
+    batch = (torch.arange(B), torch.arange(B) + 1, g["images"], g["next_images"], g["depths"][:, 0], g["next_depths"][:, 0], g["K"], g["K"])
+    hist = PR.perform_pose_refinement(pr, opt, [batch], epochs=25, resolution=(H, W))
+    assert hist[-1] < hist[0] * 0.98, hist
+
+
+def test_eval_flow_map_golden():
+    """render_image(flow=...): the predicted optical-flow map of model/training.py:265-283 as ONE affine map per frame and four
+    numbers per ray, against the fixture of the reference's per-point integration."""
+    g = load_golden("eval_flow_small")
+    P = {t: unflatten(g, f"param.{t}.") for t in ("sdf", "color", "variance")}
+    r = renderer_from(P, SMALL_CFG)
+    mot = C.MotionNetwork(d_out=6, d_in=1, d_hidden=64, n_layers=4, skip_in=[2], multires=6, bias=0.5, scale=1.0, geometric_init=False,
+                          weight_norm=True).to(DEV)
+    mot.load_state_dict(unflatten(g, "param.motion."))
+    H, W = int(g["H"]), int(g["W"])
+    args = (r, cu(g["world"]), cu(g["K"]), torch.eye(4, device=DEV).unsqueeze(0), H, W, cu(g["t0"]), (0.5, 3.5))
+    flow = (mot, float(g["t0"]), float(g["t1"]), int(g["n_sub"]))
+    out = C.training.render_image(*args, flow=flow)                          # one pass
+    assert_close(out["rgb"], g["rgb"], 1e-3, "rgb")
+    e = (out["flow_pred"].cpu() - g["flow_pred"]).abs().max() / g["flow_pred"].abs().max()
+    assert e < 1e-3, e
+    out2 = C.training.render_image(*args, flow=flow, chunk=37)              # ragged passes: identical
+    assert torch.equal(out["flow_pred"], out2["flow_pred"]) and torch.equal(out["rgb"], out2["rgb"])
+    # the affine map itself against the oracle's sub-step loop on random points
+    F = C.training.scene_flow_affine(*flow).cpu()
+    mp = unflatten(g, "param.motion.")
+    pts = torch.randn(50, 3)
+    q = pts.clone()
+    dt = (float(g["t1"]) - float(g["t0"])) / int(g["n_sub"])
+    for tt in torch.linspace(float(g["t0"]), float(g["t1"]), int(g["n_sub"]) + 1)[:-1]:
+        a, v = O.motion_forward(mp, tt.view(-1, 1))
+        q = q + dt * (torch.linalg.cross(a.expand_as(q), q) + v)
+    assert_close(pts @ F[:, :3].T + F[:, 3], q, 1e-5, "scene-flow affine map")

@@ -269,3 +269,29 @@ def test_pretrained_sdf_weights_fixture():
         assert abs(float(v.grad.double().norm()) - float(g[f"gnorm.{k}"])) <= 1e-3 * float(g[f"gnorm.{k}"]) + 1e-9, k
         if f"grad.{k}" in g:
             assert rel_err(v.grad, g[f"grad.{k}"]) < 1e-3, k
+
+
+def test_pose_refinement_warp():
+    """utils_poses/pose_refinement.py:34-61 + :117-126 (fixture: the reference's own lines with its PoseRetriever)."""
+    g = load_golden("pose_refine_small")
+    B, _, H, W = g["images"].shape
+    pose = dict(r=g["r"].clone().requires_grad_(True), t=g["t"].clone().requires_grad_(True), init_c2w=torch.eye(4).repeat(B, 1, 1))
+    rel = torch.stack([O.pose_forward(pose, i) for i in range(B)])
+    assert_close(rel, g["rel"], 1e-6, "relative poses")
+    uv = O.refine_uv(H, W).unsqueeze(0).repeat(B, 1, 1, 1)
+    lp, wp = O.compute_loss_and_warp_image(g["images"], g["next_images"], g["depths"], g["K"], uv, rel)
+    ln, wn = O.compute_loss_and_warp_image(g["next_images"], g["images"], g["next_depths"], g["K"], uv, torch.inverse(rel))
+    assert_close(lp, g["loss_pos"], 1e-6, "loss pos"); assert_close(ln, g["loss_neg"], 1e-6, "loss neg")
+    assert_close(wp, g["warped_pos"], 1e-6, "warped pos"); assert_close(wn, g["warped_neg"], 1e-6, "warped neg")
+    ((lp + ln) / 2).backward()
+    assert_close(pose["r"].grad, g["dr"], 1e-5, "dr"); assert_close(pose["t"].grad, g["dt"], 1e-5, "dt")
+
+
+def test_eval_flow_map():
+    """model/training.py:203-208, 265-283, 296-297: predicted forward optical flow of the evaluation render."""
+    g = load_golden("eval_flow_small")
+    P = {t: unflatten(g, f"param.{t}.") for t in ("sdf", "color", "variance")}
+    out = O.render_image(P, g["world"], g["K"], torch.eye(4).unsqueeze(0), int(g["H"]), int(g["W"]), g["t0"], [0.5, 3.5],
+                         cos_anneal=1.0, chunk=50, flow=(unflatten(g, "param.motion."), g["t0"], g["t1"], int(g["n_sub"])))
+    assert_close(out["rgb"], g["rgb"], 5e-4, "rgb")
+    assert (out["flow_pred"] - g["flow_pred"]).abs().max() <= 5e-4 * g["flow_pred"].abs().max()
