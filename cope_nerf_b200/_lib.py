@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcope_b200.so")
 MAX_LIN = 12
 PREC_FP32, PREC_BF16 = 0, 1
 WS_HOLDS_PACK = 0x100      # cope_sdf_query: the scratch head still holds this network's packed weights
+FLAT_HAS_PACK = 0x200      # any bf16 MLP entry point: the packed weights follow the flat parameters (cope_mlp_pack)
 ACT_SOFTPLUS100, ACT_LEAKY_RELU = 0, 1
 
 _f = C.c_void_p      # device pointers travel as integers
@@ -40,6 +41,9 @@ _SIGS = {
     "cope_last_error": (C.c_char_p, []),
     "cope_launch_count": (C.c_uint64, []),
     "cope_mlp_flat_floats": (_l, [_D]),
+    "cope_mlp_pack_offset": (_l, [_D]),
+    "cope_mlp_pack_floats": (_l, [_D, _i, _i]),
+    "cope_mlp_pack": (_i, [_D, _i, _i, _f, _f]),
     "cope_weightnorm_fwd": (_i, [_f, _f, _f, _i, _i, _f]),
     "cope_weightnorm_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _f]),
     "cope_flat_weights_fwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f]),

@@ -411,15 +411,16 @@ static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, c
 }
 
 int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s,
-                   bool ws_holds_pack) {
+                   bool ws_holds_pack, const bf16* wpx) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   if (P <= 0) return 0;
-  bf16* wp = reinterpret_cast<bf16*>(ws);
-  bf16* pe = wp + b.w_total;
+  bf16* wp_ws = reinterpret_cast<bf16*>(ws);
+  const bf16* wp = wpx ? wpx : wp_ws;       // wpx: weights packed once per step behind the flat parameters (COPE_FLAT_HAS_PACK)
+  bf16* pe = wp_ws + b.w_total;
   bf16* bufs[3] = {pe + P * 64, pe + P * 64 + P * b.LD, pe + P * 64 + 2 * P * b.LD};
-  if (!ws_holds_pack)      // the caller vouches that an earlier query on this stream left the same weights' pack at the head of ws
-    if (int rc = pack_sdf(m, b, Wflat, wp, true, false, s)) return rc;
+  if (!ws_holds_pack && !wpx)   // ws_holds_pack: the caller vouches that an earlier query on this stream left the pack at the head of ws
+    if (int rc = pack_sdf(m, b, Wflat, wp_ws, true, false, s)) return rc;
   if (sdf_chain_supported(m) && !getenv("COPE_NO_CHAIN")) {
     uint32_t offs[COPE_MAX_LIN];
     for (int l = 0; l < m.n_lin; ++l) offs[l] = (uint32_t)b.wf_off[l];
@@ -433,15 +434,18 @@ int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_
 }
 
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
-                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, bf16* feat_b16, int feat_b16_ld, bool infer) {
+                 int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, bf16* feat_b16, int feat_b16_ld, bool infer,
+                 const bf16* wpx) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   if (P <= 0) return 0;
   SdfSavedB sv = sdf_saved_b(b, P, saved);
-  bf16* wp = reinterpret_cast<bf16*>(ws);
-  float* ge0 = reinterpret_cast<float*>(wp + b.w_total);
+  bf16* wp_ws = reinterpret_cast<bf16*>(ws);
+  const bf16* wp = wpx ? wpx : wp_ws;
+  float* ge0 = reinterpret_cast<float*>(wp_ws + b.w_total);
   float* ge1 = ge0 + P * 64;
-  if (int rc = pack_sdf(m, b, Wflat, wp, true, grad != nullptr, s)) return rc;
+  if (!wpx)
+    if (int rc = pack_sdf(m, b, Wflat, wp_ws, true, grad != nullptr, s)) return rc;
   if (grad && !feat && fused_enabled(m, b, "fwd")) {
     if (int rc = sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, feat_b16, feat_b16_ld, ge0, ge1, s, infer)) return rc;
     pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, ge0, 64, b.skip > 0 ? ge1 : nullptr, 64, grad, m.d_in, 0);
@@ -527,7 +531,7 @@ bf16* sdf_bwd_dfeat_slot(const MlpShape& m, int64_t P, float* ws, int* ld) {
 // ------------------------------------------------------------------------------------------- SDF backward
 int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, const float* saved, const float* d_sdf,
                  int d_sdf_ld, const float* d_feat, int d_feat_ld, const float* dgrad, float* dWflat, float* dx,
-                 int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws) {
+                 int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws, const bf16* wpx) {
   SdfB b;
   if (make_sdfb(m, &b)) return -1;
   const bool have_dy = d_sdf || d_feat || d_feat_in_ws;
@@ -537,8 +541,9 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   }
   SdfSavedB sv = sdf_saved_b(b, P, const_cast<float*>(saved));
   const int top = b.top, LD = b.LD;
-  bf16* wp = reinterpret_cast<bf16*>(ws);
-  bf16* T = wp + b.w_total;                               // T_l, l = 1..top   -> T + (l-1) P LD
+  bf16* wp_ws = reinterpret_cast<bf16*>(ws);
+  const bf16* wp = wpx ? wpx : wp_ws;
+  bf16* T = wp_ws + b.w_total;                            // T_l, l = 1..top   -> T + (l-1) P LD
   bf16* ZB2 = T + (int64_t)top * P * LD;                  // zb2_l, l = 0..top-1
   bf16* ZBall = ZB2 + (int64_t)top * P * LD;              // zb_l, l = 0..top-1 (fused chain); the layer-by-layer path
   bf16* ZB[2] = {ZBall, ZBall + (int64_t)P * LD};         // ping-pongs between the first two
@@ -550,7 +555,8 @@ int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   auto Tl = [&](int l) { return l == 0 ? t0 : T + (int64_t)(l - 1) * P * LD; };
   auto ldT = [&](int l) { return l == 0 ? 64 : LD; };
   auto zb2 = [&](int l) { return ZB2 + (int64_t)l * P * LD; };
-  if (int rc = pack_sdf(m, b, Wflat, wp, dgrad != nullptr, true, s)) return rc;
+  if (!wpx)
+    if (int rc = pack_sdf(m, b, Wflat, wp_ws, dgrad != nullptr, true, s)) return rc;
   const int featW = m.d_out - 1;
 
   const uint64_t LDu = (uint64_t)LD, Pu = (uint64_t)P;
@@ -960,14 +966,16 @@ static void cz_job(CzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a,
 
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
                    const float* normals, const float* feat, int feat_ld, int64_t P, float* rgb, float* saved, float* ws,
-                   cudaStream_t s, bool feat_in_cin, bool infer) {
+                   cudaStream_t s, bool feat_in_cin, bool infer, const bf16* wpx) {
   ColB c;
   if (make_colb(m, Lv, &c)) return -1;
   COPE_REQUIRE(m.skip < 0, "bf16 colour path: skip connections are not supported");
   if (P <= 0) return 0;
   ColSavedB sv = col_saved_b(c, P, saved);
-  bf16* wp = reinterpret_cast<bf16*>(ws);
-  if (int rc = pack_color(m, c, Wflat, wp, true, false, s)) return rc;
+  bf16* wp_ws = reinterpret_cast<bf16*>(ws);
+  const bf16* wp = wpx ? wpx : wp_ws;
+  if (!wpx)
+    if (int rc = pack_color(m, c, Wflat, wp_ws, true, false, s)) return rc;
   if (feat_in_cin && color_fused_enabled(m, c)) {
     // ---- fused chain: tail of the input built in the kernel, 4 ReLU layers + sigmoid, h_l TMA-stored for the backward
     CzArgs a{};
@@ -1002,18 +1010,20 @@ int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const 
 
 int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int dirs_group, int Lv, int64_t P,
                    const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs, float* dnormals,
-                   float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, bf16* dfeat_b16, int dfeat_b16_ld) {
+                   float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, bf16* dfeat_b16, int dfeat_b16_ld, const bf16* wpx) {
   ColB c;
   if (make_colb(m, Lv, &c)) return -1;
   if (P <= 0) return 0;
   ColSavedB sv = col_saved_b(c, P, const_cast<float*>(saved));
-  bf16* wp = reinterpret_cast<bf16*>(ws);
-  bf16* DZ = wp + c.w_total;                                   // dz_l, l = 0..top-1 (fused chain); the layer-by-layer
+  bf16* wp_ws = reinterpret_cast<bf16*>(ws);
+  const bf16* wp = wpx ? wpx : wp_ws;
+  bf16* DZ = wp_ws + c.w_total;                                // dz_l, l = 0..top-1 (fused chain); the layer-by-layer
   bf16* B[2] = {DZ, DZ + (int64_t)P * c.LD};                   // path ping-pongs between the first two
   bf16* dzt = DZ + (int64_t)c.top * P * c.LD;                  // [P x 128]
   float* rest = reinterpret_cast<float*>(dzt + (int64_t)P * 128);
   float* part = rest + P * 64;
-  if (int rc = pack_color(m, c, Wflat, wp, false, true, s)) return rc;
+  if (!wpx)
+    if (int rc = pack_color(m, c, Wflat, wp_ws, false, true, s)) return rc;
   if (!dfeat && color_fused_enabled(m, c)) {
     // ---- fused adjoint chain (stores every dz_l), then the weight gradients from the stored tiles
     const int F = c.d_feat, R = c.rest, top = c.top;
@@ -1109,6 +1119,18 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
     }
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------- weights packed once per step
+// The packed bf16 operands of a network (forward AND transposed blocks, in the layout every bf16 entry point expects at `wp`)
+// written behind its flat fp32 parameters: the five per-call re-packs of a training step become one launch per network.
+int64_t mlp_pack_elems_bf16(const MlpShape& m, int is_color, int Lv) {
+  if (is_color) { ColB c; if (make_colb(m, Lv, &c)) return -1; return (int64_t)c.w_total; }
+  SdfB b; if (make_sdfb(m, &b)) return -1; return (int64_t)b.w_total;
+}
+int mlp_pack_bf16(const MlpShape& m, int is_color, int Lv, const float* Wflat, bf16* wp, cudaStream_t s) {
+  if (is_color) { ColB c; if (make_colb(m, Lv, &c)) return -1; return pack_color(m, c, Wflat, wp, true, true, s); }
+  SdfB b; if (make_sdfb(m, &b)) return -1; return pack_sdf(m, b, Wflat, wp, true, true, s);
 }
 
 }  // namespace cope

@@ -211,8 +211,8 @@ int cope_sdf_query(const cope_mlp_desc* d, const float* Wflat, const float* x, i
                    int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  if ((prec & ~COPE_WS_HOLDS_PACK) == COPE_PREC_BF16)
-    return sdf_query_bf16(m, Wflat, x, P, sdf_out, ws, as_stream(s_), (prec & COPE_WS_HOLDS_PACK) != 0);
+  if ((prec & 0xFF) == COPE_PREC_BF16)
+    return sdf_query_bf16(m, Wflat, x, P, sdf_out, ws, as_stream(s_), (prec & COPE_WS_HOLDS_PACK) != 0, flat_pack_ptr(m, Wflat, prec));
   COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_query: unknown precision %d", prec);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
@@ -242,7 +242,9 @@ int cope_sdf_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
                  float* feat, int feat_ld, float* grad, float* saved, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  if (prec == COPE_PREC_BF16) return sdf_fwd_bf16(m, Wflat, x, P, sdf, sdf_ld, feat, feat_ld, grad, saved, ws, as_stream(s_));
+  if ((prec & 0xFF) == COPE_PREC_BF16)
+    return sdf_fwd_bf16(m, Wflat, x, P, sdf, sdf_ld, feat, feat_ld, grad, saved, ws, as_stream(s_), nullptr, 0, false,
+                        flat_pack_ptr(m, Wflat, prec));
   COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_fwd: unknown precision %d", prec);
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
@@ -296,9 +298,9 @@ int cope_sdf_bwd(const cope_mlp_desc* d, const float* Wflat, const float* x, int
   if (make_shape(d, &m)) return -1;
   COPE_REQUIRE(m.act == COPE_ACT_SOFTPLUS100 || (dgrad == nullptr && prec == COPE_PREC_FP32),
                "sdf_bwd: activation %d has no second-order / tensor-core path", m.act);
-  if (prec == COPE_PREC_BF16)
+  if ((prec & 0xFF) == COPE_PREC_BF16)
     return sdf_bwd_bf16(m, Wflat, x, P, saved, d_sdf, d_sdf_ld, d_feat, d_feat_ld, dgrad, dWflat, dx, dx_accumulate, ws,
-                        as_stream(s_));
+                        as_stream(s_), false, flat_pack_ptr(m, Wflat, prec));
   COPE_REQUIRE(prec == COPE_PREC_FP32, "sdf_bwd: unknown precision %d", prec);
   const bool have_dy = d_sdf || d_feat;
   if (P <= 0 || (!have_dy && !dgrad)) {
@@ -490,8 +492,9 @@ int cope_color_fwd(const cope_mlp_desc* d, const float* Wflat, const float* x, c
                    int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  if (prec == COPE_PREC_BF16)
-    return color_fwd_bf16(m, Wflat, x, dirs, dirs_group, Lv, normals, feat, feat_ld, P, rgb, saved, ws, as_stream(s_));
+  if ((prec & 0xFF) == COPE_PREC_BF16)
+    return color_fwd_bf16(m, Wflat, x, dirs, dirs_group, Lv, normals, feat, feat_ld, P, rgb, saved, ws, as_stream(s_), false, false,
+                          flat_pack_ptr(m, Wflat, prec));
   COPE_REQUIRE(prec == COPE_PREC_FP32, "color_fwd: unknown precision %d", prec);
   const int d_feat = m.in[0] - (4 + 3 * (1 + 2 * Lv) + 4);
   COPE_REQUIRE(d_feat > 0 && m.skip < 0, "color_fwd: layer-0 width %d does not match idr input", m.in[0]);
@@ -519,9 +522,9 @@ int cope_color_bwd(const cope_mlp_desc* d, const float* Wflat, const float* dirs
                    float* dfeat, int dfeat_ld, float* ws, int prec, cope_stream_t s_) {
   MlpShape m;
   if (make_shape(d, &m)) return -1;
-  if (prec == COPE_PREC_BF16)
+  if ((prec & 0xFF) == COPE_PREC_BF16)
     return color_bwd_bf16(m, Wflat, dirs, dirs_group, Lv, P, saved, d_rgb, dWflat, dx, ddirs, dnormals, dfeat, dfeat_ld, ws,
-                          as_stream(s_));
+                          as_stream(s_), nullptr, 0, flat_pack_ptr(m, Wflat, prec));
   COPE_REQUIRE(prec == COPE_PREC_FP32, "color_bwd: unknown precision %d", prec);
   const int d_feat = m.in[0] - (4 + 3 * (1 + 2 * Lv) + 4);
   if (P <= 0) return 0;
@@ -547,6 +550,25 @@ int cope_color_bwd(const cope_mlp_desc* d, const float* Wflat, const float* dirs
                                                                 dnormals, dfeat, dfeat_ld);
   COPE_CHECK_LAUNCH("color_unpack");
   return 0;
+}
+
+/* ---- weights packed once per step (bf16 path) */
+int64_t cope_mlp_pack_offset(const cope_mlp_desc* d) {
+  MlpShape m;
+  if (make_shape(d, &m)) return -1;
+  return (m.n_flat + 63) / 64 * 64;
+}
+int64_t cope_mlp_pack_floats(const cope_mlp_desc* d, int is_color, int Lv) {
+  MlpShape m;
+  if (make_shape(d, &m)) return -1;
+  const int64_t e = mlp_pack_elems_bf16(m, is_color, Lv);
+  return e < 0 ? -1 : (e + 1) / 2 + 64;
+}
+int cope_mlp_pack(const cope_mlp_desc* d, int is_color, int Lv, float* flat_with_tail, cope_stream_t s) {
+  MlpShape m;
+  if (make_shape(d, &m)) return -1;
+  return mlp_pack_bf16(m, is_color, Lv, flat_with_tail, reinterpret_cast<__nv_bfloat16*>(flat_with_tail + (m.n_flat + 63) / 64 * 64),
+                       as_stream(s));
 }
 
 }  // extern "C"

@@ -48,24 +48,30 @@ int64_t sdf_ws_floats_bf16(const MlpShape& m, int64_t P);
 bool sdf_infer_compact_bf16(const MlpShape& m);
 int64_t sdf_query_ws_floats_bf16(const MlpShape& m, int64_t P);
 int sdf_query_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf_out, float* ws, cudaStream_t s,
-                   bool ws_holds_pack = false);
+                   bool ws_holds_pack = false, const __nv_bfloat16* wpx = nullptr);
 int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, float* sdf, int sdf_ld, float* feat,
                  int feat_ld, float* grad, float* saved, float* ws, cudaStream_t s, __nv_bfloat16* feat_b16 = nullptr,
-                 int feat_b16_ld = 0, bool infer = false);
+                 int feat_b16_ld = 0, bool infer = false, const __nv_bfloat16* wpx = nullptr);
 int sdf_bwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t P, const float* saved, const float* d_sdf,
                  int d_sdf_ld, const float* d_feat, int d_feat_ld, const float* dgrad, float* dWflat, float* dx,
-                 int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws = false);
+                 int dx_accumulate, float* ws, cudaStream_t s, bool d_feat_in_ws = false, const __nv_bfloat16* wpx = nullptr);
 __nv_bfloat16* sdf_bwd_dfeat_slot(const MlpShape& m, int64_t P, float* ws, int* ld);
 __nv_bfloat16* color_cin_slot(const MlpShape& m, int Lv, int64_t P, float* saved, int* ld);
 int64_t color_saved_floats_bf16(const MlpShape& m, int64_t P);
 int64_t color_ws_floats_bf16(const MlpShape& m, int64_t P);
 int color_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, const float* dirs, int dirs_group, int Lv,
                    const float* normals, const float* feat, int feat_ld, int64_t P, float* rgb, float* saved, float* ws,
-                   cudaStream_t s, bool feat_in_cin = false, bool infer = false);
+                   cudaStream_t s, bool feat_in_cin = false, bool infer = false, const __nv_bfloat16* wpx = nullptr);
 int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int dirs_group, int Lv, int64_t P,
                    const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs, float* dnormals,
                    float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, __nv_bfloat16* dfeat_b16 = nullptr,
-                   int dfeat_b16_ld = 0);
+                   int dfeat_b16_ld = 0, const __nv_bfloat16* wpx = nullptr);
+int64_t mlp_pack_elems_bf16(const MlpShape& m, int is_color, int Lv);
+int mlp_pack_bf16(const MlpShape& m, int is_color, int Lv, const float* Wflat, __nv_bfloat16* wp, cudaStream_t s);
+// COPE_FLAT_HAS_PACK: the packed bf16 weights follow the flat fp32 parameters (64-float aligned); nullptr when the flag is off
+inline const __nv_bfloat16* flat_pack_ptr(const MlpShape& m, const float* Wflat, int prec) {
+  return (prec & COPE_FLAT_HAS_PACK) ? reinterpret_cast<const __nv_bfloat16*>(Wflat + (m.n_flat + 63) / 64 * 64) : nullptr;
+}
 
 // small fp32 kernels of mlp_f32.cu that the bf16 path reuses
 __global__ void pe_vjp_kernel(const float* __restrict__ x, int64_t P, int d, int L, const float* __restrict__ ge0, int ld0,

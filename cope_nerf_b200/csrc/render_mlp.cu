@@ -31,12 +31,14 @@ int cope_render_mlp_fwd(const cope_mlp_desc* sd, const float* sdfW, const cope_m
   if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
-  if (prec == COPE_PREC_BF16) {
+  if ((prec & 0xFF) == COPE_PREC_BF16) {
     int ld = 0;
     __nv_bfloat16* cin = color_cin_slot(mc, Lv, P, col_saved, &ld);
     COPE_REQUIRE(cin != nullptr, "render_mlp_fwd: colour network shape not supported on the bf16 path");
-    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld)) return rc;
-    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true);
+    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld, false, flat_pack_ptr(ms, sdfW, prec)))
+      return rc;
+    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true, false,
+                          flat_pack_ptr(mc, colW, prec));
   }
   const int F = ms.d_out - 1;
   float* feat = ws;
@@ -56,6 +58,7 @@ static int64_t infer_sdf_saved_floats(const cope_mlp_desc* sd, int64_t P, int pr
 }
 
 int64_t cope_render_mlp_infer_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
+  prec &= 0xFF;
   const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
   const int64_t a = infer_sdf_saved_floats(sd, P, prec), b = cope_color_saved_floats(cd, P, prec);
   if (w < 0 || a < 0 || b < 0) return -1;
@@ -68,6 +71,8 @@ int cope_render_mlp_infer(const cope_mlp_desc* sd, const float* sdfW, const cope
   MlpShape ms, mc;
   if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
   if (P <= 0) return 0;
+  const int flags = prec;
+  prec &= 0xFF;
   const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
   const int64_t a = infer_sdf_saved_floats(sd, P, prec);
   COPE_REQUIRE(w >= 0 && a >= 0, "render_mlp_infer: unsupported network shape");
@@ -78,8 +83,10 @@ int cope_render_mlp_infer(const cope_mlp_desc* sd, const float* sdfW, const cope
     int ld = 0;
     __nv_bfloat16* cin = color_cin_slot(mc, Lv, P, col_saved, &ld);
     COPE_REQUIRE(cin != nullptr, "render_mlp_infer: colour network shape not supported on the bf16 path");
-    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld, true)) return rc;
-    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true, true);
+    if (int rc = sdf_fwd_bf16(ms, sdfW, x, P, sdf, 1, nullptr, 0, grad, sdf_saved, ws, s, cin, ld, true, flat_pack_ptr(ms, sdfW, flags)))
+      return rc;
+    return color_fwd_bf16(mc, colW, x, dirs, dirs_group, Lv, grad, nullptr, 0, P, rgb, col_saved, ws, s, true, true,
+                          flat_pack_ptr(mc, colW, flags));
   }
   return cope_render_mlp_fwd(sd, sdfW, cd, colW, x, dirs, dirs_group, Lv, P, sdf, grad, rgb, sdf_saved, col_saved, ws, prec, s_);
 }
@@ -92,6 +99,8 @@ int cope_render_mlp_bwd(const cope_mlp_desc* sd, const float* sdfW, const cope_m
   if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
   if (P <= 0) return 0;
   cudaStream_t s = as_stream(s_);
+  const int flags = prec;
+  prec &= 0xFF;
   const int64_t col_ws = cope_color_ws_floats(cd, P, prec);
   if (prec == COPE_PREC_BF16) {
     float* ws_sdf = ws + col_ws;
@@ -99,9 +108,10 @@ int cope_render_mlp_bwd(const cope_mlp_desc* sd, const float* sdfW, const cope_m
     __nv_bfloat16* slot = sdf_bwd_dfeat_slot(ms, P, ws_sdf, &ld);
     COPE_REQUIRE(slot != nullptr, "render_mlp_bwd: SDF network shape not supported on the bf16 path");
     if (int rc = color_bwd_bf16(mc, colW, dirs, dirs_group, Lv, P, col_saved, d_rgb, dW_col, dx, ddirs_pp, d_grad, nullptr, 0, ws, s,
-                                slot, ld))
+                                slot, ld, flat_pack_ptr(mc, colW, flags)))
       return rc;
-    return sdf_bwd_bf16(ms, sdfW, x, P, sdf_saved, d_sdf, 1, nullptr, 0, d_grad, dW_sdf, dx, 1, ws_sdf, s, true);
+    return sdf_bwd_bf16(ms, sdfW, x, P, sdf_saved, d_sdf, 1, nullptr, 0, d_grad, dW_sdf, dx, 1, ws_sdf, s, true,
+                        flat_pack_ptr(ms, sdfW, flags));
   }
   const int F = ms.d_out - 1;
   float* dfeat = ws;

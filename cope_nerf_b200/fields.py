@@ -53,15 +53,20 @@ class _FlatWeights(torch.autograd.Function):
     (cope_flat_weights_fwd / _bwd)."""
 
     @staticmethod
-    def forward(ctx, offsets, *params):
+    def forward(ctx, offsets, pack, *params):
         n = len(params) // 3
         params = tuple(p.contiguous() for p in params)
         vs, gs, bs = params[0::3], params[1::3], params[2::3]
-        flat = torch.empty(offsets[-1], dtype=torch.float32, device=params[0].device)
+        # pack = (desc, is_color, Lv, tail offset, tail floats): the bf16 operands of the tensor-core path are written ONCE per
+        # step behind the fp32 parameters (cope_mlp_pack); every entry point that gets this buffer skips its own re-pack
+        n_total = offsets[-1] if pack is None else pack[3] + pack[4]
+        flat = torch.empty(n_total, dtype=torch.float32, device=params[0].device)
         meta = dict(rows=(C.c_int * n)(*[v.shape[0] for v in vs]), cols=(C.c_int * n)(*[v.shape[1] for v in vs]),
                     w_off=(C.c_int64 * n)(*offsets[0:2 * n:2]), b_off=(C.c_int64 * n)(*offsets[1:2 * n:2]))
         L.call("cope_flat_weights_fwd", n, _ptr_array(vs), _ptr_array(gs), _ptr_array(bs), meta["rows"], meta["cols"],
                meta["w_off"], meta["b_off"], flat, L.stream())
+        if pack is not None:
+            L.call("cope_mlp_pack", pack[0], pack[1], pack[2], flat, L.stream())
         ctx.meta, ctx.n = meta, n
         ctx.save_for_backward(*params)
         return flat
@@ -80,7 +85,7 @@ class _FlatWeights(torch.autograd.Function):
         grads = []
         for dv, dg, db in zip(dvs, dgs, dbs):
             grads += [dv, dg, db]
-        return (None, *grads)
+        return (None, None, *grads)
 
 
 class _MlpBase(nn.Module):
@@ -100,14 +105,37 @@ class _MlpBase(nn.Module):
     def _lins(self):
         return [getattr(self, f"lin{l}") for l in range(len(self._dims_in))]
 
+    def _pack_spec(self):
+        """(desc, is_color, Lv, tail offset, tail floats) of the once-per-step bf16 weight pack, or None (strict fp32 path, or a
+        shape the tensor-core path does not take)."""
+        if getattr(self, "precision", L.PREC_FP32) != L.PREC_BF16:
+            return None
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        if "spec" not in cache:
+            is_color = 1 if hasattr(self, "multires_view") else 0
+            Lv = int(getattr(self, "multires_view", 0))
+            try:
+                n = L.query("cope_mlp_pack_floats", self.desc, is_color, Lv)
+                cache["spec"] = (self.desc, is_color, Lv, L.query("cope_mlp_pack_offset", self.desc), n)
+            except L.CopeError:
+                cache["spec"] = None
+        return cache["spec"]
+
+    def call_prec(self, flat):
+        """`prec` argument of a kernel call that receives `flat`: the precision, plus COPE_FLAT_HAS_PACK when `flat` carries the
+        packed operands behind the parameters."""
+        prec = getattr(self, "precision", L.PREC_FP32)
+        return prec | (L.FLAT_HAS_PACK if (prec == L.PREC_BF16 and flat.numel() > self.n_flat) else 0)
+
     def flat_weights(self):
-        """Effective (weight-normalised) parameters as one differentiable flat tensor."""
+        """Effective (weight-normalised) parameters as one differentiable flat tensor (followed, on the tensor-core path, by the
+        packed bf16 operands: see _pack_spec)."""
         lins = self._lins()
         if all(m.weight_norm for m in lins):
             ps = []
             for m in lins:
                 ps += [m.weight_v, m.weight_g, m.bias]
-            return _FlatWeights.apply(self._offsets, *ps)
+            return _FlatWeights.apply(self._offsets, self._pack_spec(), *ps)
         parts = []
         for m in lins:   # plain nn.Linear parameterisation (weight_norm=False): nothing to normalise
             w = m.weight_v * (m.weight_g / m.weight_v.norm(dim=1, keepdim=True)) if m.weight_norm else m.weight
@@ -127,9 +155,9 @@ class _SdfFn(torch.autograd.Function):
         x = x.contiguous().float()
         y = torch.empty(P, d_out, dtype=torch.float32, device=dev)
         grad = torch.empty(P, net.desc.d_in, dtype=torch.float32, device=dev) if want_grad else None
-        saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, int(want_grad), prec), dtype=torch.float32,
+        saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, int(want_grad), prec & 0xFF), dtype=torch.float32,
                             device=dev)
-        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, prec), dev)
+        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, prec & 0xFF), dev)
         L.call("cope_sdf_fwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(y), d_out, y.data_ptr() + 4, d_out,
                L.ptr(grad), L.ptr(saved), L.ptr(ws), prec, L.stream())
         ctx.net, ctx.prec, ctx.want_grad = net, prec, want_grad
@@ -146,7 +174,7 @@ class _SdfFn(torch.autograd.Function):
         dgrad = dgrad.contiguous() if (dgrad is not None and ctx.want_grad) else None
         dflat = torch.zeros_like(flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
-        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, prec), dev)
+        ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, prec & 0xFF), dev)
         L.call("cope_sdf_bwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(saved),
                L.ptr(dy), d_out, (dy.data_ptr() + 4) if dy is not None else None, d_out, L.ptr(dgrad),
                L.ptr(dflat), L.ptr(dx), 0, L.ptr(ws), prec, L.stream())
@@ -167,7 +195,7 @@ class _SdfValueFn(torch.autograd.Function):
         saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, 1, L.PREC_BF16), dtype=torch.float32, device=dev)
         ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, L.PREC_BF16), dev)
         L.call("cope_sdf_fwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(sdf), 1, None, 0, L.ptr(grad), L.ptr(saved), L.ptr(ws),
-               L.PREC_BF16, L.stream())
+               net.call_prec(flat), L.stream())
         ctx.net = net
         ctx.save_for_backward(flat, x, saved)
         return sdf
@@ -181,7 +209,7 @@ class _SdfValueFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
         ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, L.PREC_BF16), dev)
         L.call("cope_sdf_bwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(saved), L.ptr(d_sdf.contiguous()), 1, None, 0, None,
-               L.ptr(dflat), L.ptr(dx), 0, L.ptr(ws), L.PREC_BF16, L.stream())
+               L.ptr(dflat), L.ptr(dx), 0, L.ptr(ws), net.call_prec(flat), L.stream())
         return None, dflat, dx
 
 
@@ -234,7 +262,7 @@ class SDFNetwork(_MlpBase):
     def apply_flat(self, flat, x, want_grad):
         if self.scale != 1:
             raise NotImplementedError("scale != 1 is not wired into the fused kernels (reference default is 1.0)")
-        return _SdfFn.apply(self, flat, x, want_grad, self.precision)
+        return _SdfFn.apply(self, flat, x, want_grad, self.call_prec(flat))
 
     def query_flat(self, flat, x, pack_token=None):
         """sdf only, no autograd state (cope_sdf_query).  `pack_token`: a mutable list shared by consecutive queries with the SAME
@@ -244,8 +272,8 @@ class SDFNetwork(_MlpBase):
         x = x.contiguous().float()
         out = torch.empty(P, 1, dtype=torch.float32, device=x.device)
         ws = L.scratch(L.query("cope_sdf_query_ws_floats", self.desc, P, self.precision), x.device)
-        prec = self.precision
-        if pack_token is not None and prec == L.PREC_BF16:
+        prec = self.call_prec(flat)
+        if pack_token is not None and prec == L.PREC_BF16:      # no once-per-step pack in `flat`: share one pack between the queries
             key = (ws.data_ptr(), flat.data_ptr(), flat._version, L.stream())
             if pack_token and pack_token[0] == key:
                 prec |= L.WS_HOLDS_PACK
@@ -281,8 +309,8 @@ class _ColorFn(torch.autograd.Function):
         points, normals, view_dirs = points.contiguous().float(), normals.contiguous().float(), view_dirs.contiguous().float()
         feats = feats.contiguous().float()       # y[:, 1:] views arrive with row stride 257: densify
         rgb = torch.empty(P, net._dims_out[-1], dtype=torch.float32, device=dev)
-        saved = torch.empty(L.query("cope_color_saved_floats", net.desc, P, prec), dtype=torch.float32, device=dev)
-        ws = L.scratch(L.query("cope_color_ws_floats", net.desc, P, prec), dev)
+        saved = torch.empty(L.query("cope_color_saved_floats", net.desc, P, prec & 0xFF), dtype=torch.float32, device=dev)
+        ws = L.scratch(L.query("cope_color_ws_floats", net.desc, P, prec & 0xFF), dev)
         L.call("cope_color_fwd", net.desc, L.ptr(flat), L.ptr(points), L.ptr(view_dirs), dirs_group, net.multires_view,
                L.ptr(normals), L.ptr(feats), feats.stride(0), P, L.ptr(rgb), L.ptr(saved), L.ptr(ws), prec, L.stream())
         ctx.net, ctx.prec, ctx.dirs_group = net, prec, dirs_group
@@ -301,7 +329,7 @@ class _ColorFn(torch.autograd.Function):
         dn = torch.zeros(P, 4, dtype=torch.float32, device=dev) if need[3] else None
         dd = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[4] else None
         df = torch.empty(ctx.feat_shape, dtype=torch.float32, device=dev) if need[5] else None
-        ws = L.scratch(L.query("cope_color_ws_floats", net.desc, P, prec), dev)
+        ws = L.scratch(L.query("cope_color_ws_floats", net.desc, P, prec & 0xFF), dev)
         L.call("cope_color_bwd", net.desc, L.ptr(flat), L.ptr(view_dirs), ctx.dirs_group, net.multires_view, P,
                L.ptr(saved), L.ptr(d_rgb.contiguous()), L.ptr(dflat), L.ptr(dx), L.ptr(dd), L.ptr(dn), L.ptr(df),
                df.shape[1] if df is not None else 0, L.ptr(ws), prec, L.stream())
@@ -335,7 +363,7 @@ class RenderingNetwork(_MlpBase):
         self._finish(dims[:-1], dims[1:], 4, 0, -1)
 
     def apply_flat(self, flat, points, normals, view_dirs, feature_vectors, dirs_group=1):
-        return _ColorFn.apply(self, flat, points, normals, view_dirs, feature_vectors, dirs_group, self.precision)
+        return _ColorFn.apply(self, flat, points, normals, view_dirs, feature_vectors, dirs_group, self.call_prec(flat))
 
     def forward(self, points, normals, view_dirs, feature_vectors):
         return self.apply_flat(self.flat_weights(), points, normals, view_dirs, feature_vectors, 1)

@@ -39,6 +39,12 @@ def sample_cdf(cdf, bins, n_samples, return_inds=False):
     return (out, inds) if return_inds else out
 
 
+def _call_prec(sdf_net, sdf_flat, col_net, col_flat):
+    """`prec` of a render-MLP call: COPE_FLAT_HAS_PACK only when BOTH flat buffers carry their once-per-step weight pack."""
+    a, b = sdf_net.call_prec(sdf_flat), col_net.call_prec(col_flat)
+    return a if a == b else sdf_net.precision
+
+
 def _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm, time_step, z, near, far, n_coarse,
                   cos_anneal, eval_mode):
     """render_core forward (model/neus_renderer.py:307-450): points -> fused SDF + colour MLPs -> compositing.
@@ -69,7 +75,7 @@ def _core_forward(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d_norm
     ws = L.scratch(L.query("cope_render_mlp_ws_floats", sdf_net.desc, col_net.desc, P, prec_s), dev)
     L.call("cope_render_mlp_fwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
            col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(ws),
-           prec_s, s)
+           _call_prec(sdf_net, sdf_flat, col_net, col_flat), s)
 
     weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
     color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
@@ -115,7 +121,8 @@ def _core_backward(rnd, cfg, saved, need_rays, need_var, d_color, d_depth, d_gra
         d_pts = None
     L.call("cope_render_mlp_bwd", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
            col_net.multires_view, P, L.ptr(sdf_saved), L.ptr(col_saved), L.ptr(d_sdf), L.ptr(d_grad), L.ptr(d_rgb),
-           L.ptr(d_sdf_flat), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(ws), prec_s, s)
+           L.ptr(d_sdf_flat), L.ptr(d_col_flat), L.ptr(d_pts), L.ptr(d_dirs_pp), L.ptr(ws),
+           _call_prec(sdf_net, sdf_flat, col_net, col_flat), s)
     d_rays_o = None
     if need_rays:
         d_rays_o = _f32(N, 3, device=dev)
@@ -253,7 +260,7 @@ def _render_core_infer(rnd, sdf_flat, col_flat, variance, rays_o, rays_d, rays_d
     sdf, grad, rgb = _f32(P, 1, device=dev), _f32(P, 4, device=dev), _f32(P, 3, device=dev)
     ws = L.scratch(L.query("cope_render_mlp_infer_ws_floats", sdf_net.desc, col_net.desc, P, prec), dev)
     L.call("cope_render_mlp_infer", sdf_net.desc, L.ptr(sdf_flat), col_net.desc, L.ptr(col_flat), L.ptr(pts), L.ptr(rays_d), S,
-           col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(ws), prec, s)
+           col_net.multires_view, P, L.ptr(sdf), L.ptr(grad), L.ptr(rgb), L.ptr(ws), _call_prec(sdf_net, sdf_flat, col_net, col_flat), s)
     weights, cdf = _f32(N, S, device=dev), _f32(N, S, device=dev)
     color, depth, wz = _f32(N, 3, device=dev), _f32(N, 1, device=dev), _f32(N, 1, device=dev)
     wsum, wmax, inv_s = _f32(N, 1, device=dev), _f32(N, 1, device=dev), _f32(1, device=dev)

@@ -35,6 +35,10 @@ typedef void* cope_stream_t;
 /* OR-ed into `prec` of cope_sdf_query: the head of `ws` still holds the packed bf16 weights that an earlier cope_sdf_query left there
  * on the same stream for the same Wflat contents (the four sampling queries of one NeuSRenderer.forward): skip the re-pack launch */
 #define COPE_WS_HOLDS_PACK 0x100
+/* OR-ed into `prec` of any bf16 MLP entry point: the flat parameter buffer passed as Wflat is followed, at float offset
+ * cope_mlp_pack_offset(desc), by the packed bf16 operands that cope_mlp_pack wrote there (cope_mlp_pack_floats floats).
+ * The entry point then skips its own re-pack: one pack launch per network and step instead of five. */
+#define COPE_FLAT_HAS_PACK 0x200
 
 /* Shape of a weight-normalised MLP (SDFNetwork / RenderingNetwork, model/neus_fields.py:205-374).
  * Flat parameter layout (floats): for l in 0..n_lin-1: W_l [dims_out[l] x dims_in[l]] row-major, then
@@ -288,6 +292,13 @@ int cope_flow_rgb_fwd(const float* wp, const float* w2c, const float* KS, const 
 int cope_flow_rgb_bwd(const float* wp, const float* w2c, const float* KS, const float* norm_pix, const float* pix,
                       const float* ref_imgs, const float* rgb_gt, int64_t N, int T, int H, int W, const float* ws, const float* g,
                       float* d_wp, float* d_w2c, cope_stream_t s);
+
+/* ---- weights packed once per step (bf16 path; see COPE_FLAT_HAS_PACK).  is_color: 0 = SDF network layout (forward + transposed
+ * blocks + the sdf row), 1 = colour network layout (Lv = multires_view).  flat_with_tail: the flat fp32 parameters [W_l | b_l]*
+ * with cope_mlp_pack_floats extra floats allocated from offset cope_mlp_pack_offset on. */
+int64_t cope_mlp_pack_offset(const cope_mlp_desc* d);
+int64_t cope_mlp_pack_floats(const cope_mlp_desc* d, int is_color, int Lv);
+int cope_mlp_pack(const cope_mlp_desc* d, int is_color, int Lv, float* flat_with_tail, cope_stream_t s);
 
 /* ---- depth-patch smoothness (model/losses.py:7-18 SmoothnessLoss, :20-38 EdgePreservingSmoothnessLoss; called on
  * depth_pred.view(-1, ps, ps, 1) and rgb_gt.view(-1, ps, ps, 3) at train.py:519-525) ------------------------------------
