@@ -225,19 +225,20 @@ def mlp_traffic_from_profile():
         return None, None
 
 
-def stage1_step_ms(C, dev, prec, n_rays, steps, warmup):
+def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True):
     """The reference's WHOLE stage-1 iteration (train.py:407-532) on one GPU: on-device patch sampling + rays (process_data),
     fused render + rgb / eikonal / SDF-flow node, flow-RGB over the valid reference frames, SDF-consistency re-query (another
     131 072-point SDF forward + backward), depth-patch smoothness, backward into SDF / colour / variance / MotionNetwork, both
     Adam steps.  Synthetic 100-frame sequence, query frame 40, reference frames 41-43, world frame 50, 10 sub-steps per pair
-    (configs/default.yaml).  Eager launches (frame-dependent shapes: the pose chain length changes with the frame index)."""
+    (configs/default.yaml).  The frame-dependent pieces go through losses.Stage1Static (frame indices as device tensors, one
+    global pose chain), so the iteration is ONE CUDA graph that is valid for every frame.  Returns (ms per step, launch note)."""
     from cope_nerf_b200 import losses as CL
     torch.manual_seed(678)
     rnd = C.training.build_networks(device=dev, precision=prec)
     mot = C.MotionNetwork(d_out=6, d_in=1, d_hidden=256, n_layers=4, skip_in=[2], multires=6, bias=0.5, scale=1.0, geometric_init=False,
                           weight_norm=True).to(dev)
-    opt = torch.optim.Adam(list(rnd.parameters()), lr=1e-3, fused=True)
-    mopt = torch.optim.Adam(list(mot.parameters()), lr=5e-4, fused=True)
+    opt = torch.optim.Adam(list(rnd.parameters()), lr=1e-3, fused=True, capturable=True)
+    mopt = torch.optim.Adam(list(mot.parameters()), lr=5e-4, fused=True, capturable=True)
     g = torch.Generator().manual_seed(5)
     img = torch.rand(1, 3, H, W, generator=g).to(dev)
     refs = torch.rand(3, 3, H, W, generator=g).to(dev)
@@ -245,34 +246,67 @@ def stage1_step_ms(C, dev, prec, n_rays, steps, warmup):
     Kr = Kc.repeat(3, 1, 1)
     world = torch.eye(4, device=dev)
     n_img, idx, ref_idx, world_idx, n_sub = 100, 40, [41, 42, 43], 50, 10
-    qts = torch.tensor([idx / (n_img - 1) * 2 - 1], device=dev)
+    st = CL.Stage1Static(mot, n_img, n_sub, world_idx, -1.0 + 2.0 * world_idx / (n_img - 1))
     w = dict(rgb=1.0, eik=0.1, sdf=0.1, frgb=7.5, cons=1.0, edge=1.0, smooth=1e-4)
+    n_corner = (H - 3) * (W - 3)
+    static = dict(corners=torch.zeros(n_rays // 16, dtype=torch.int64, device=dev), t_rand=torch.zeros(n_rays, 64, device=dev),
+                  qts=torch.tensor([idx / (n_img - 1) * 2 - 1], device=dev), idx=torch.tensor([idx], device=dev),
+                  ref=torch.tensor(ref_idx, device=dev), valid=torch.ones(3, device=dev), cons_on=torch.ones(1, device=dev))
+    from cope_nerf_b200.dist import FlatGradBucket
+    bucket = FlatGradBucket(list(rnd.parameters()) + list(mot.parameters()))      # one fill launch clears every gradient
 
-    def step(i):
-        opt.zero_grad(set_to_none=True); mopt.zero_grad(set_to_none=True)
-        pix, npix, o, d, dn, rgb_gt, _ = C.training.process_data(img, Kc, world, Sc, n_rays, patch_size=4, seed=i)
+    def new_inputs():
+        static["corners"].copy_(torch.randint(0, n_corner, (n_rays // 16,), device=dev))
+        static["t_rand"].copy_(torch.rand(n_rays, 64, device=dev))
+
+    def iteration():
+        bucket.zero_()
+        pix, npix, o, d, dn, rgb_gt, _ = C.training.process_data(img, Kc, world, Sc, n_rays, patch_size=4, corners=static["corners"])
         near, far = C.training.near_far_from_sphere(o, d, DEPTH_RANGE)
-        rnd.t_rand_override = torch.rand(n_rays, 64, device=dev)
-        ang, vel = mot(qts.view(-1, 1))
-        loss, out = rnd.forward_losses(o, d, dn, qts, near, far, rgb_gt, cos_anneal_ratio=0.5, it=1, rgb_weight=w["rgb"],
+        rnd.t_rand_override = static["t_rand"]
+        ang, vel = mot(static["qts"].view(-1, 1))
+        loss, out = rnd.forward_losses(o, d, dn, static["qts"], near, far, rgb_gt, cos_anneal_ratio=0.5, it=1, rgb_weight=w["rgb"],
                                        eikonal_weight=w["eik"], sdf_weight=w["sdf"], motion=torch.cat([ang, vel], 1))
-        aux = CL.stage1_losses(out, rgb_gt, mot, rnd.sdf_network, float(idx / (n_img - 1) * 2 - 1), idx, ref_idx, 3, n_img, n_sub, Kr, Sc,
-                               npix, pix, refs, world_idx, -1.0 + 2.0 * world_idx / (n_img - 1), consistency_pose_grad=False,
-                               include_sdf_loss=False)
+        aux = st.losses(out, rgb_gt, rnd.sdf_network, static["idx"], static["ref"], static["valid"], static["cons_on"], Kr, Sc, npix, pix,
+                        refs, consistency_pose_grad=False)
         sm, _ = CL.depth_smoothness_losses(out["depth_pred"], rgb_gt, 4, edge_weight=w["edge"], smooth_weight=w["smooth"])
-        (loss + w["frgb"] * aux["flow_rgb_loss"] + w["cons"] * aux["sdf_consistency_loss"] + sm).backward()
+        total = loss + w["frgb"] * aux["flow_rgb_loss"] + w["cons"] * aux["sdf_consistency_loss"] + sm
+        total.backward()
         opt.step(); mopt.step()
+        return total.detach()
 
-    for i in range(warmup):
-        step(i)
+    graph, note = None, "eager launches"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            new_inputs(); iteration()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration()
+            note = "one CUDA graph per stage-1 iteration (valid for every frame: indices are device tensors)"
+        except Exception as e:      # pragma: no cover
+            graph, note = None, f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:100]})"
+            torch.cuda.synchronize()
+
+    def step():
+        new_inputs()
+        graph.replay() if graph is not None else iteration()
+
+    for _ in range(warmup):
+        step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(steps):
-        step(warmup + i)
+    for _ in range(steps):
+        step()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    return e0.elapsed_time(e1) / steps, note
 
 
 class Runner:
@@ -549,8 +583,8 @@ def main():
                                               f"nets/losses/Adam, oracle port of the reference's PyTorch CPU path"}
         if world == 1 and not args.no_extras:
             try:
-                ms1 = stage1_step_ms(C, dev, prec, 1024, 10, 3)
-                line["stage1"] = {"ms_per_step": ms1, "value": 1024 / (ms1 * 1e-3), "unit": "rays/s", "launch": "eager",
+                ms1, note1 = stage1_step_ms(C, dev, prec, 1024, 10, 3)
+                line["stage1"] = {"ms_per_step": ms1, "value": 1024 / (ms1 * 1e-3), "unit": "rays/s", "launch": note1,
                                   "note": "the reference's whole stage-1 iteration (train.py:407-532): render + rgb / eikonal / SDF-flow + flow-RGB (3 "
                                           "reference frames) + SDF-consistency re-query + depth-patch smoothness + MotionNetwork, both Adam steps"}
             except Exception as e:      # pragma: no cover

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["step_losses", "packed_outputs", "weighted_points", "flow_rgb_loss", "sdf_consistency_loss", "projection_matrices", "rigid_inverse",
-           "stage1_losses", "depth_smoothness_losses", "SmoothnessLoss", "EdgePreservingSmoothnessLoss"]
+           "stage1_losses", "depth_smoothness_losses", "SmoothnessLoss", "EdgePreservingSmoothnessLoss", "Stage1Static"]
 
 
 def _f32(*shape, device):
@@ -287,3 +287,65 @@ def stage1_losses(out, rgb_gt, motion_network, sdf_network, query_time_step, ima
             res["flow_rgb_loss"], res["flow_fw_pred"] = flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs[:nb_valid], rgb_gt,
                                                                       return_flow=True)
     return res
+
+
+# ------------------------------------------------------------------------------------------------ shape-static stage-1 terms
+class Stage1Static:
+    """The flow-RGB and SDF-consistency terms of train.py:480-517 in a form whose tensor shapes do NOT depend on the frame index,
+    so that the whole stage-1 iteration (render, losses, backward, both optimisers) can be captured in ONE CUDA graph and replayed
+    for every frame; `stage1_losses` above follows the reference's control flow (pose chains whose length changes with the frame)
+    and is the parity reference of this class (tests/test_gpu_round2.py).
+
+    The reference chains the relative poses rel_a .. rel_{b-1} for every pair (a, b) it needs (query frame -> each reference frame,
+    world frame <-> query frame).  Here ONE chain over all consecutive pairs of the sequence is evaluated per step,
+    G_k = rel_{k-1} ... rel_0 (one batched MotionNetwork call on the (N - 1) * n_sub fixed time samples, one integration launch,
+    one chain launch), and every map the losses need is G_b G_a^-1 with the rigid inverse: the same matrix as the reference's
+    product up to fp32 rounding.  In particular cw2 = G_world G_idx^-1 covers both branches of train.py:501 (the inverse when the
+    world frame precedes the query frame, the plain product otherwise).  Frame indices arrive as DEVICE tensors:
+        idx_t [1] int64, ref_idx_t [T] int64 (clamped to N - 1), ref_valid_t [T] float (1 = the frame exists and counts),
+        cons_on_t [1] float (0 when the query frame is the world frame, train.py:496)."""
+
+    def __init__(self, motion_network, total_nb_images, nb_sample_timestep, world_cam_idx, world_time_step):
+        from .motion import MotionNetwork
+        dev = motion_network.lin0.bias.device
+        self.motion, self.n_img, self.n_sub = motion_network, int(total_nb_images), int(nb_sample_timestep)
+        self.world_idx = torch.tensor([int(world_cam_idx)], dtype=torch.int64, device=dev)
+        self.world_time_step = float(world_time_step)
+        ts, dts = [], []
+        for cam in range(self.n_img - 1):
+            lst, dt = MotionNetwork._pair_times(cam, self.n_img, self.n_sub)
+            ts.append(lst); dts.append(dt)
+        self.ts = torch.cat(ts).view(-1, 1).to(dev)
+        self.dts = torch.stack(dts).to(dev)
+        far = torch.zeros(4, 4, dtype=torch.float32, device=dev)        # an invalid reference frame: every projection lands far outside
+        far[0, 3] = far[1, 3] = 1e8
+        far[2, 3] = far[3, 3] = 1.0
+        self.far = far
+
+    def global_chain(self):
+        from .motion import _ChainFn, _IntegrateFn
+        ang, vel = self.motion(self.ts)
+        rel = _IntegrateFn.apply(torch.cat([ang, vel], dim=1), self.dts, self.n_img - 1, self.n_sub)
+        return _ChainFn.apply(rel)                                  # [N, 4, 4], G_0 = I
+
+    def losses(self, out, rgb_gt, sdf_network, idx_t, ref_idx_t, ref_valid_t, cons_on_t, ref_camera_mats, scale_mat, norm_pix, pix,
+               ref_imgs, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True):
+        """Returns dict(flow_rgb_loss, sdf_consistency_loss, flow_fw_pred [T,N,2]); `out` from NeuSRenderer.forward / forward_losses."""
+        G = self.global_chain()
+        inv_i = rigid_inverse(G.index_select(0, idx_t)[0])
+        zero = torch.zeros((), dtype=torch.float32, device=G.device)
+        res = dict(flow_rgb_loss=zero, sdf_consistency_loss=zero, flow_fw_pred=None)
+        pts4 = packed_outputs(out)[1]
+        if use_consistency:
+            cw2 = G.index_select(0, self.world_idx)[0] @ inv_i
+            if not (consistency_pose_grad and torch.is_grad_enabled()):
+                cw2 = cw2.detach()
+            res["sdf_consistency_loss"] = cons_on_t.reshape(()) * sdf_consistency_loss(sdf_network, pts4[:, :3], out["sdf"], cw2,
+                                                                                       self.world_time_step)
+        if use_flow_rgb:
+            w2c = G.index_select(0, ref_idx_t) @ inv_i
+            w2c = torch.where(ref_valid_t.view(-1, 1, 1) > 0, w2c, self.far)
+            wp = weighted_points(out["weights"], pts4)
+            KS = projection_matrices(scale_mat, ref_camera_mats)
+            res["flow_rgb_loss"], res["flow_fw_pred"] = flow_rgb_loss(wp, w2c, KS, norm_pix, pix, ref_imgs, rgb_gt, return_flow=True)
+        return res
