@@ -264,11 +264,11 @@ def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True):
         pix, npix, o, d, dn, rgb_gt, _ = C.training.process_data(img, Kc, world, Sc, n_rays, patch_size=4, corners=static["corners"])
         near, far = C.training.near_far_from_sphere(o, d, DEPTH_RANGE)
         rnd.t_rand_override = static["t_rand"]
-        ang, vel = mot(static["qts"].view(-1, 1))
+        G, motion = st.global_chain(static["qts"])          # ONE MotionNetwork call: pose chain of the sequence + the query-time motion
         loss, out = rnd.forward_losses(o, d, dn, static["qts"], near, far, rgb_gt, cos_anneal_ratio=0.5, it=1, rgb_weight=w["rgb"],
-                                       eikonal_weight=w["eik"], sdf_weight=w["sdf"], motion=torch.cat([ang, vel], 1))
+                                       eikonal_weight=w["eik"], sdf_weight=w["sdf"], motion=motion)
         aux = st.losses(out, rgb_gt, rnd.sdf_network, static["idx"], static["ref"], static["valid"], static["cons_on"], Kr, Sc, npix, pix,
-                        refs, consistency_pose_grad=False)
+                        refs, consistency_pose_grad=False, G=G)
         sm, _ = CL.depth_smoothness_losses(out["depth_pred"], rgb_gt, 4, edge_weight=w["edge"], smooth_weight=w["smooth"])
         total = loss + w["frgb"] * aux["flow_rgb_loss"] + w["cons"] * aux["sdf_consistency_loss"] + sm
         total.backward()

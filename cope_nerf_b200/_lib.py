@@ -47,7 +47,7 @@ _SIGS = {
     "cope_weightnorm_fwd": (_i, [_f, _f, _f, _i, _i, _f]),
     "cope_weightnorm_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _f]),
     "cope_flat_weights_fwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
-    "cope_flat_weights_bwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "cope_flat_weights_bwd": (_i, [_i, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _f]),
     "cope_embed_fwd": (_i, [_f, _l, _i, _i, _f, _f]),
     "cope_sdf_saved_floats": (_l, [_D, _l, _i, _i]),
     "cope_sdf_ws_floats": (_l, [_D, _l, _i]),

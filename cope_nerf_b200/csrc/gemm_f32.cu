@@ -152,10 +152,83 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmArgs a) {
   }
 }
 
+// Small-problem variant: 32 x 64 x 16 tiles, 256 threads, 2 x 4 outputs per thread.  The MotionNetwork runs on ~1000 time samples
+// (M ~ 990, N = K = 256): the 128 x 128 kernel covers that with 16 CTAs on 148 SMs and ~60 us of exposed latency per GEMM; this one
+// launches 124.  Same operand conventions and epilogues.
+constexpr int SM_ = 32, SN_ = 64, SK_ = 16;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_small_kernel(const GemmArgs a) {
+  __shared__ float As[SK_][SM_ + 1];
+  __shared__ float Bs[SK_][SN_ + 1];
+  const int m0 = blockIdx.y * SM_, n0 = blockIdx.x * SN_;
+  int kbeg = 0, kend = a.K;
+  if (a.split_k > 1) {
+    int chunk = (int)(((int64_t)a.K + a.split_k - 1) / a.split_k);
+    chunk = (chunk + SK_ - 1) / SK_ * SK_;
+    kbeg = blockIdx.z * chunk;
+    kend = min(a.K, kbeg + chunk);
+    if (kbeg >= kend) return;
+  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+  for (int k0 = kbeg; k0 < kend; k0 += SK_) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                       // A tile: 32 x 16
+      const int idx = threadIdx.x + 256 * i;
+      const int mm = TA ? (idx % SM_) : (idx / SK_), kk = TA ? (idx / SM_) : (idx % SK_);
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.0f;
+      if (m < a.M && k < kend) v = TA ? a.A[(int64_t)k * a.lda + m] : a.A[(int64_t)m * a.lda + k];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // B tile: 16 x 64
+      const int idx = threadIdx.x + 256 * i;
+      const int nn = TB ? (idx / SK_) : (idx % SN_), kk = TB ? (idx % SK_) : (idx / SN_);
+      const int n = n0 + nn, k = k0 + kk;
+      float v = 0.0f;
+      if (n < a.N && k < kend) v = TB ? a.B[(int64_t)n * a.ldb + k] : a.B[(int64_t)k * a.ldb + n];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SK_; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b = Bs[k][tx * 4 + j];
+        acc[0][j] = fmaf(a0, b, acc[0][j]);
+        acc[1][j] = fmaf(a1, b, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < a.N) epilogue(a, m, n, acc[i][j]);
+    }
+  }
+}
+
 int launch_gemm(bool transA, bool transB, const GemmArgs& a, cudaStream_t s) {
   if (a.M <= 0 || a.N <= 0) return 0;
   COPE_REQUIRE(a.K > 0, "gemm: K must be positive (M=%d N=%d K=%d)", a.M, a.N, a.K);
   COPE_REQUIRE(a.split_k == 1 || a.epi == EPI_ATOMIC, "gemm: split-K needs the atomic epilogue");
+  const int64_t big_ctas = (int64_t)((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM) * a.split_k;
+  if (big_ctas < 74) {               // less than half a wave of the 128 x 128 tiles: the small-tile kernel fills the machine
+    dim3 grid((a.N + SN_ - 1) / SN_, (a.M + SM_ - 1) / SM_, a.split_k);
+    if (!transA && transB) sgemm_small_kernel<false, true><<<grid, 256, 0, s>>>(a);
+    else if (!transA && !transB) sgemm_small_kernel<false, false><<<grid, 256, 0, s>>>(a);
+    else if (transA && !transB) sgemm_small_kernel<true, false><<<grid, 256, 0, s>>>(a);
+    else sgemm_small_kernel<true, true><<<grid, 256, 0, s>>>(a);
+    COPE_CHECK_LAUNCH("sgemm_small");
+    return 0;
+  }
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.split_k);
   if (!transA && transB) sgemm_kernel<false, true><<<grid, NT, 0, s>>>(a);
   else if (!transA && !transB) sgemm_kernel<false, false><<<grid, NT, 0, s>>>(a);

@@ -378,23 +378,25 @@ static void fz_job(FzArgs* a, size_t w_off, int Np, int Kp, int acc, int wait_a,
 // ge0 / ge1 (gradient w.r.t. the PE)
 static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, const bf16* wp, const float* x, int64_t P,
                          const SdfSavedB& sv, float* sdf, int sdf_ld, bf16* feat_b16, int feat_b16_ld, float* ge0, float* ge1,
-                         cudaStream_t s, bool infer) {
+                         cudaStream_t s, bool infer, bool value_only = false) {
   FzArgs a{};
   fz_common(m, b, Wflat, wp, x, P, &a);
   const int top = b.top;
   for (int l = 0; l < top; ++l) fz_job(&a, b.wf_off[l], b.Np[l], b.Kp[l], l & 1, 1, (l & 1) + 1);
   fz_job(&a, b.wf_off[top], b.featN, b.Kp[top], top & 1, 1, 0);
   fz_job(&a, b.wtop_sdf_off, 16, b.Kp[top], (top & 1) ^ 1, 0, (top & 1) + 1);
-  for (int l = top - 1; l >= 0; --l) {
-    const int st = top + 1 + (top - 1 - l);
-    fz_job(&a, b.wt_off[l], l == 0 ? 64 : r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
-  }
+  if (!value_only)
+    for (int l = top - 1; l >= 0; --l) {
+      const int st = top + 1 + (top - 1 - l);
+      fz_job(&a, b.wt_off[l], l == 0 ? 64 : r16(m.in[l]), r64(m.out[l]), st & 1, 1, (st & 1) + 1);
+    }
   a.sdf = sdf; a.sdf_ld = sdf_ld; a.has_feat = feat_b16 != nullptr; a.ge0 = ge0; a.ge1 = ge1; a.infer = infer;
+  a.value_only = value_only;
   FzMaps maps{};
   const uint64_t LD = (uint64_t)b.LD, Pu = (uint64_t)P;
   if (int rc = make_tmap3(sv.pe, 64, Pu, 1, 64, Pu * 64, &maps.in0)) return rc;
   if (int rc = make_tmap3(sv.H, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.H)) return rc;
-  if (infer) maps.D = maps.H;      // never stored: the saved block has no delta stack in inference
+  if (infer || value_only) maps.D = maps.H;      // never stored: the saved block has no delta stack in inference / value-only mode
   else if (int rc = make_tmap3(sv.D, LD, Pu, (uint64_t)top, LD, Pu * LD, &maps.D)) return rc;
   if (feat_b16) {
     if (int rc = make_tmap3(feat_b16, (uint64_t)b.featN, Pu, 1, (uint64_t)feat_b16_ld, Pu * (uint64_t)feat_b16_ld, &maps.out)) return rc;
@@ -446,6 +448,11 @@ int sdf_fwd_bf16(const MlpShape& m, const float* Wflat, const float* x, int64_t 
   float* ge1 = ge0 + P * 64;
   if (!wpx)
     if (int rc = pack_sdf(m, b, Wflat, wp_ws, true, grad != nullptr, s)) return rc;
+  if (!grad && !feat && !feat_b16 && sdf && fused_enabled(m, b, "fwd") && fused_enabled(m, b, "val")) {
+    // value pass only (SDFNetwork.sdf with gradients, the SDF-consistency re-query of train.py:504): the chain stores H_1..H_top
+    // for the value-only backward and stops before the reverse sweep
+    return sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, nullptr, 0, ge0, ge1, s, false, true);
+  }
   if (grad && !feat && fused_enabled(m, b, "fwd")) {
     if (int rc = sdf_fwd_fused(m, b, Wflat, wp, x, P, sv, sdf, sdf_ld, feat_b16, feat_b16_ld, ge0, ge1, s, infer)) return rc;
     pe_vjp_kernel<<<g1(P * m.d_in), 256, 0, s>>>(x, P, m.d_in, m.L, ge0, 64, b.skip > 0 ? ge1 : nullptr, 64, grad, m.d_in, 0);

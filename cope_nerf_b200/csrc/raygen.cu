@@ -62,7 +62,7 @@ __global__ void flat_weights_fwd_kernel(const __grid_constant__ WnBatch B, float
   for (int c = lane; c < cols; c += 32) W[c] = vr[c] * sc;
   if (lane == 0) flat[B.b_off[l] + row] = B.b[l][row];
 }
-__global__ void flat_weights_bwd_kernel(const __grid_constant__ WnBatch B, const float* __restrict__ dflat) {
+__global__ void flat_weights_bwd_kernel(const __grid_constant__ WnBatch B, const float* __restrict__ dflat, int accumulate) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B.total_rows) return;
   int l = 0;
@@ -77,8 +77,15 @@ __global__ void flat_weights_bwd_kernel(const __grid_constant__ WnBatch B, const
   const float nrm = sqrtf(ss), gi = B.g[l][row];
   const float a = gi / nrm, b = gi * dot / (nrm * ss);
   float* dv = B.dv[l] + (int64_t)row * cols;
-  for (int c = lane; c < cols; c += 32) dv[c] = a * dr[c] - b * vr[c];
-  if (lane == 0) { B.dg[l][row] = dot / nrm; B.db[l][row] = dflat[B.b_off[l] + row]; }
+  // accumulate: dv / dg / db ARE the parameters' .grad buffers (views of one flat bucket): add in place instead of handing
+  // ~80 temporaries to autograd, which would launch one elementwise add per parameter tensor
+  if (accumulate) {
+    for (int c = lane; c < cols; c += 32) dv[c] += a * dr[c] - b * vr[c];
+    if (lane == 0) { B.dg[l][row] += dot / nrm; B.db[l][row] += dflat[B.b_off[l] + row]; }
+  } else {
+    for (int c = lane; c < cols; c += 32) dv[c] = a * dr[c] - b * vr[c];
+    if (lane == 0) { B.dg[l][row] = dot / nrm; B.db[l][row] = dflat[B.b_off[l] + row]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------ 4x4 helpers (fp64)
@@ -336,11 +343,11 @@ int cope_flat_weights_fwd(int n, const void* const* v, const void* const* g, con
 }
 int cope_flat_weights_bwd(int n, const void* const* v, const void* const* g, const int* rows, const int* cols,
                           const int64_t* w_off, const int64_t* b_off, const float* dflat, void* const* dv, void* const* dg,
-                          void* const* db, cope_stream_t s) {
+                          void* const* db, int accumulate, cope_stream_t s) {
   WnBatch B{};
   if (int rc = fill_wn(B, n, v, g, g, rows, cols, w_off, b_off)) return rc;
   for (int l = 0; l < n; ++l) { B.dv[l] = (float*)dv[l]; B.dg[l] = (float*)dg[l]; B.db[l] = (float*)db[l]; }
-  flat_weights_bwd_kernel<<<(B.total_rows + 3) / 4, 128, 0, as_stream(s)>>>(B, dflat);
+  flat_weights_bwd_kernel<<<(B.total_rows + 3) / 4, 128, 0, as_stream(s)>>>(B, dflat, accumulate);
   COPE_CHECK_LAUNCH("flat_weights_bwd");
   return 0;
 }

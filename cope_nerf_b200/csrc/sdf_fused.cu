@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
           }
           if (a.has_feat)
             for (int j = 0; j < 4; ++j) store_stg(&tm.out, j * 64, row0, 0);      // feature -> colour input slot
-          for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, !a.infer); // delta_l
+          if (!a.value_only)
+            for (int l = top - 1; l >= 0; --l) store_tile(&tm.D, row0, l, 4, !a.infer); // delta_l
         } else if (MODE == FZ_TAN) {
           store_tile(&tm.in0, row0, 0, 1, true);                                  // T_0
           for (int l = 0; l < top; ++l) {
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
       for (int tile = tile_first; tile < ntiles; tile += tile_step, ++t_local) {
         const int row0 = tile * 128;
         if (MODE == FZ_FWD) {
+          if (a.value_only) continue;                                             // no reverse sweep: nothing to load back
           mbar_wait_park(B.h_stored, t_local & 1);
           for (int l = top - 1; l >= 1; --l)
             for (int j = 0; j < 4; ++j) load_aux(&tm.H, j, row0, l - 1);          // H_l
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
           }
           tc_fence_before();
         }
+        if (a.value_only) continue;       // value pass only: the next tile (all 16 epilogue warps take this branch together)
         // ---------------- top of the reverse sweep, in place: delta_{top-1} = w0 * sp(H_top)
         E.begin_event();
         {

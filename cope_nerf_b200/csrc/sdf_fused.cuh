@@ -42,6 +42,7 @@ struct FzArgs {
   float* sdf; int sdf_ld; int has_feat;
   __nv_bfloat16* feat_ptr; int feat_ld;   // FWD (two-tile kernel): the feature block of the colour input, written with plain stores
   int infer;                 // FWD: no backward will follow: the reverse-sweep deltas are not stored
+  int value_only;            // FWD: value pass only (SDFNetwork.sdf with gradients): no reverse sweep, no delta / ge0 / ge1
   float* ge0; float* ge1;    // [P x 64] fp32 gradients w.r.t. the PE (layer 0 / skip layer)
   // ADJ
   const float* d_sdf; int d_sdf_ld;

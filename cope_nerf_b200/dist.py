@@ -51,7 +51,12 @@ class FlatGradBucket:
     `optimizer.zero_grad(set_to_none=False)`) — NOT with the default `optimizer.zero_grad()`: set_to_none=True drops the
     views, autograd then allocates fresh `.grad` tensors outside the bucket and the all-reduce would exchange a stale
     buffer.  `allreduce_()` checks this and re-attaches (copying the stray gradients in) rather than exchanging garbage.
-    Gradients that already exist at construction are copied into the bucket, not discarded."""
+    Gradients that already exist at construction are copied into the bucket, not discarded.
+
+    Parameters of a bucket are marked `_cope_grad_in_place`: the weight-norm backward of the network modules
+    (fields._FlatWeights) then ACCUMULATES into the bucket's views inside its own kernel and reports no gradient to autograd,
+    which would otherwise launch one elementwise add per parameter tensor (~80 per step).  Consequence: for such parameters use
+    `loss.backward()` (not `torch.autograd.grad`, which would find no gradient), and gradient hooks on them do not fire."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -81,6 +86,8 @@ class FlatGradBucket:
                     view.zero_()
             p.grad = view
             moved += 1
+        for p in self.params:
+            p._cope_grad_in_place = True      # fields._FlatWeights.backward adds straight into these views (no per-tensor add launch)
         return moved
 
     def zero_(self):

@@ -68,6 +68,7 @@ class _FlatWeights(torch.autograd.Function):
         if pack is not None:
             L.call("cope_mlp_pack", pack[0], pack[1], pack[2], flat, L.stream())
         ctx.meta, ctx.n = meta, n
+        ctx.param_refs = params          # the Parameter objects themselves (their .grad / bucket mark are read in backward)
         ctx.save_for_backward(*params)
         return flat
 
@@ -77,11 +78,21 @@ class _FlatWeights(torch.autograd.Function):
         n, meta = ctx.n, ctx.meta
         vs, gs, bs = params[0::3], params[1::3], params[2::3]
         dflat = dflat.contiguous()
-        dvs = [torch.empty_like(v) for v in vs]
-        dgs = [torch.empty_like(g) for g in gs]
-        dbs = [torch.empty_like(b) for b in bs]
+        # Parameters whose .grad lives in a dist.FlatGradBucket (marked by it) receive their gradient IN PLACE: the kernel adds into
+        # the bucket's views, and autograd gets None - instead of ~80 temporaries and one elementwise add launch per tensor.
+        refs = ctx.param_refs
+        in_place = all(getattr(p, "_cope_grad_in_place", False) and p.grad is not None and p.grad.is_contiguous()
+                       and p.grad.dtype == torch.float32 and p.grad.shape == p.shape for p in refs)
+        if in_place:
+            dvs, dgs, dbs = [p.grad for p in refs[0::3]], [p.grad for p in refs[1::3]], [p.grad for p in refs[2::3]]
+        else:
+            dvs = [torch.empty_like(v) for v in vs]
+            dgs = [torch.empty_like(g) for g in gs]
+            dbs = [torch.empty_like(b) for b in bs]
         L.call("cope_flat_weights_bwd", n, _ptr_array(vs), _ptr_array(gs), meta["rows"], meta["cols"], meta["w_off"],
-               meta["b_off"], dflat, _ptr_array(dvs), _ptr_array(dgs), _ptr_array(dbs), L.stream())
+               meta["b_off"], dflat, _ptr_array(dvs), _ptr_array(dgs), _ptr_array(dbs), int(in_place), L.stream())
+        if in_place:
+            return (None, None) + (None,) * len(params)
         grads = []
         for dv, dg, db in zip(dvs, dgs, dbs):
             grads += [dv, dg, db]
@@ -183,18 +194,17 @@ class _SdfFn(torch.autograd.Function):
 
 class _SdfValueFn(torch.autograd.Function):
     """sdf = SDFNetwork.sdf(x) with gradients on the tensor-core path (the SDF-consistency re-query, train.py:504): the forward
-    is the fused value + sweep chain (its analytic gradient is computed and dropped: still 3x faster than nine separate GEMM
-    launches with an fp32 [P,257] output), the backward one fused adjoint sweep + one batched weight-gradient launch."""
+    is the fused chain in its value-only form (stores H_1..H_top, no reverse sweep), the backward one fused adjoint sweep + one
+    batched weight-gradient launch."""
 
     @staticmethod
     def forward(ctx, net, flat, x):
         P, dev = x.shape[0], x.device
         x = x.contiguous().float()
         sdf = torch.empty(P, 1, dtype=torch.float32, device=dev)
-        grad = torch.empty(P, net.desc.d_in, dtype=torch.float32, device=dev)
-        saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, 1, L.PREC_BF16), dtype=torch.float32, device=dev)
+        saved = torch.empty(L.query("cope_sdf_saved_floats", net.desc, P, 0, L.PREC_BF16), dtype=torch.float32, device=dev)
         ws = L.scratch(L.query("cope_sdf_ws_floats", net.desc, P, L.PREC_BF16), dev)
-        L.call("cope_sdf_fwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(sdf), 1, None, 0, L.ptr(grad), L.ptr(saved), L.ptr(ws),
+        L.call("cope_sdf_fwd", net.desc, L.ptr(flat), L.ptr(x), P, L.ptr(sdf), 1, None, 0, None, L.ptr(saved), L.ptr(ws),
                net.call_prec(flat), L.stream())
         ctx.net = net
         ctx.save_for_backward(flat, x, saved)

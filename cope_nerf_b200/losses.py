@@ -322,16 +322,27 @@ class Stage1Static:
         far[2, 3] = far[3, 3] = 1.0
         self.far = far
 
-    def global_chain(self):
+    def global_chain(self, query_time_step=None):
+        """G [N, 4, 4] (G_0 = I).  With `query_time_step` ([1] device tensor) the MotionNetwork is evaluated on the chain's time
+        samples AND the query time in ONE batched call; returns (G, motion [1, 6] = angular velocity | velocity at the query
+        time, the SDF-flow term's input, train.py:472)."""
         from .motion import _ChainFn, _IntegrateFn
-        ang, vel = self.motion(self.ts)
-        rel = _IntegrateFn.apply(torch.cat([ang, vel], dim=1), self.dts, self.n_img - 1, self.n_sub)
-        return _ChainFn.apply(rel)                                  # [N, 4, 4], G_0 = I
+        if query_time_step is None:
+            ang, vel = self.motion(self.ts)
+            wv, mq = torch.cat([ang, vel], dim=1), None
+        else:
+            ang, vel = self.motion(torch.cat([self.ts, query_time_step.reshape(1, 1).float()], dim=0))
+            all_wv = torch.cat([ang, vel], dim=1)
+            wv, mq = all_wv[:-1], all_wv[-1:]
+        G = _ChainFn.apply(_IntegrateFn.apply(wv, self.dts, self.n_img - 1, self.n_sub))
+        return G if query_time_step is None else (G, mq)
 
     def losses(self, out, rgb_gt, sdf_network, idx_t, ref_idx_t, ref_valid_t, cons_on_t, ref_camera_mats, scale_mat, norm_pix, pix,
-               ref_imgs, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True):
-        """Returns dict(flow_rgb_loss, sdf_consistency_loss, flow_fw_pred [T,N,2]); `out` from NeuSRenderer.forward / forward_losses."""
-        G = self.global_chain()
+               ref_imgs, use_flow_rgb=True, use_consistency=True, consistency_pose_grad=True, G=None):
+        """Returns dict(flow_rgb_loss, sdf_consistency_loss, flow_fw_pred [T,N,2]); `out` from NeuSRenderer.forward / forward_losses.
+        `G`: the chain of `global_chain` when the caller already evaluated it (together with the query-time motion)."""
+        if G is None:
+            G = self.global_chain()
         inv_i = rigid_inverse(G.index_select(0, idx_t)[0])
         zero = torch.zeros((), dtype=torch.float32, device=G.device)
         res = dict(flow_rgb_loss=zero, sdf_consistency_loss=zero, flow_fw_pred=None)

@@ -73,12 +73,13 @@ int cope_weightnorm_bwd(const float* v, const float* g, const float* dW, float* 
 
 /* All n layers of one network in one launch (host arrays of device pointers / sizes): flat = [W_l | b_l]* with
  * W_l = g_l * v_l / ||v_l||_row at float offset w_off[l] and the bias copied to b_off[l]; the backward writes
- * dv_l, dg_l, db_l (OVERWRITTEN) from dflat.  n <= 16. */
+ * dv_l, dg_l, db_l from dflat: OVERWRITTEN, or with accumulate != 0 ADDED to (the buffers then are the parameters' gradient
+ * buffers themselves, e.g. views of one flat all-reduce bucket).  n <= 16. */
 int cope_flat_weights_fwd(int n, const void* const* v, const void* const* g, const void* const* b, const int* rows,
                           const int* cols, const int64_t* w_off, const int64_t* b_off, float* flat, cope_stream_t s);
 int cope_flat_weights_bwd(int n, const void* const* v, const void* const* g, const int* rows, const int* cols,
                           const int64_t* w_off, const int64_t* b_off, const float* dflat, void* const* dv, void* const* dg,
-                          void* const* db, cope_stream_t s);
+                          void* const* db, int accumulate, cope_stream_t s);
 
 /* ---- positional encoding (model/neus_embedder.py:6-51): out [P x d*(1+2L)] */
 int cope_embed_fwd(const float* x, int64_t P, int d, int L, float* out, cope_stream_t s);
