@@ -404,11 +404,6 @@ static int sdf_fwd_fused(const MlpShape& m, const SdfB& b, const float* Wflat, c
     maps.out = maps.H;
   }
   maps.Z2 = maps.H;
-  a.feat_ptr = feat_b16; a.feat_ld = feat_b16_ld;
-  // opt-in (COPE_FWD_PAIR=1): two tiles in flight per CTA.  Correct but slower than the one-tile kernel on the training shapes
-  // (559 vs 498 us at 131 072 points, see sdf_fwd_pair.cu), so it is not the default
-  const char* pe = getenv("COPE_FWD_PAIR");
-  if (pe && atoi(pe) != 0 && !getenv("COPE_FZ_TIMELINE") && sdf_fwd_pair_supported(a)) return launch_sdf_fwd_pair(a, maps, s);
   return launch_sdf_fused(FZ_FWD, a, maps, s);
 }
 

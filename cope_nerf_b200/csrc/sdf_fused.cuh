@@ -40,7 +40,6 @@ struct FzArgs {
   int64_t w_top_off;         // float offset of row 0 of the last layer inside Wflat
   // FWD
   float* sdf; int sdf_ld; int has_feat;
-  __nv_bfloat16* feat_ptr; int feat_ld;   // FWD (two-tile kernel): the feature block of the colour input, written with plain stores
   int infer;                 // FWD: no backward will follow: the reverse-sweep deltas are not stored
   int value_only;            // FWD: value pass only (SDFNetwork.sdf with gradients): no reverse sweep, no delta / ge0 / ge1
   float* ge0; float* ge1;    // [P x 64] fp32 gradients w.r.t. the PE (layer 0 / skip layer)
@@ -65,9 +64,6 @@ int make_tmap3(const __nv_bfloat16* ptr, uint64_t cols, uint64_t rows, uint64_t 
                CUtensorMap* out);
 bool sdf_fused_supported(const MlpShape& m);
 int launch_sdf_fused(int mode, const FzArgs& a, const FzMaps& maps, cudaStream_t s);
-// FZ_FWD with two tiles in flight per CTA (sdf_fwd_pair.cu): launches with more tiles than SMs
-bool sdf_fwd_pair_supported(const FzArgs& a);
-int launch_sdf_fwd_pair(const FzArgs& a, const FzMaps& maps, cudaStream_t s);
 
 }  // namespace cope
 

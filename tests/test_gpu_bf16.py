@@ -299,28 +299,6 @@ def _render_mlp_fwd_bwd(r, x, dirs, S, seed):
     return dict(sdf=o_sdf, grad=o_grad, rgb=o_rgb, dWs=dWs, dWc=dWc, dx=dx)
 
 
-def test_fwd_pair_kernel_matches_one_tile_kernel(monkeypatch):
-    """sdf_fwd_pair_kernel (two tiles in flight per CTA; launches with more than 148 tiles) against sdf_fused_kernel<FWD>: same
-    sdf / gradient / colour, and - through the saved H and delta stacks - the same parameter gradients from the backward."""
-    P0 = full_params(perturb=0.02)
-    r = bf16_renderer(P0, C.training.DEFAULT_CFG)
-    for n_rays in (149, 300, 1024):          # 149 tiles (one CTA with a pair), pairs + singles, 6-7 tiles per CTA
-        S = 128
-        torch.manual_seed(n_rays)
-        x = torch.cat([torch.randn(n_rays * S, 3, device=DEV) * 0.6, torch.full((n_rays * S, 1), 0.2, device=DEV)], -1)
-        dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
-        monkeypatch.setenv("COPE_FWD_PAIR", "0")
-        one = _render_mlp_fwd_bwd(r, x, dirs, S, 5)
-        monkeypatch.setenv("COPE_FWD_PAIR", "1")
-        two = _render_mlp_fwd_bwd(r, x, dirs, S, 5)
-        monkeypatch.delenv("COPE_FWD_PAIR")
-        for k in ("sdf", "grad", "rgb"):
-            assert torch.isfinite(two[k]).all()
-            assert rel_err(two[k], one[k]) < 2e-3, (n_rays, k, rel_err(two[k], one[k]))
-        for k in ("dWs", "dWc", "dx"):
-            assert cos_sim(two[k], one[k]) > 0.9999 and rel_err(two[k], one[k]) < 1e-2, (n_rays, k, rel_err(two[k], one[k]))
-
-
 @pytest.mark.parametrize("n", [3000, 128 * 150 + 5])
 def test_bf16_value_only_backward_fused_vs_layered_and_oracle(monkeypatch, n):
     """SDFNetwork.forward / .sdf with gradients (the SDF-consistency re-query, train.py:504): the backward runs as one fused

@@ -1,4 +1,4 @@
-"""Decode the clock64 timeline of a two-tiles-in-flight chain kernel (COPE_Q2_TIMELINE=<file> / COPE_FWD_PAIR_TIMELINE=<file>):
+"""Decode the clock64 timeline of a two-tiles-in-flight chain kernel (COPE_Q2_TIMELINE=<file>):
     python tools/pair_timeline.py <file> [max_events]"""
 import sys, numpy as np
 d = np.fromfile(sys.argv[1], dtype=np.int64).reshape(2, 4096)
