@@ -21,17 +21,21 @@ def bf16_renderer(P, cfg):
 
 
 def check_grads(named, ref, tag, floor=1e-7, bias_cos=COS, cos=COS):
-    worst = 1.0
+    worst, worst_b = 1.0, 1.0
     for k, p in named:
         g, w = p.grad, ref[k]
         if w.norm() < floor:
             assert g.norm() < 1e-4, (tag, k, g.norm())
             continue
         c = cos_sim(g, w)
-        worst = min(worst, c)
+        if k.endswith("bias"):
+            worst_b = min(worst_b, c)
+        else:
+            worst = min(worst, c)
         assert c > (bias_cos if k.endswith("bias") else cos), (tag, k, c, rel_err(g, w))
         assert 0.9 < (g.norm() / w.norm()).item() < 1.1, (tag, k)
-    return worst
+    print(f"[measured] {tag}: min cos weights {worst:.5f} (asserted > {cos}), biases {worst_b:.5f} (asserted > {bias_cos})")
+    return min(worst, worst_b)
 
 
 @pytest.mark.parametrize("which", ["small", "full"])
@@ -117,7 +121,9 @@ def test_bf16_full_size_step_vs_oracle_and_fp32():
     assert cos_sim(out["depth_pred"], aux["out"]["depth_pred"]) > COS
     for tag, net in (("sdf", r.sdf_network), ("color", r.color_network), ("variance", r.deviation_network)):
         check_grads(net.named_parameters(), {k: v.grad for k, v in Pg[tag].items()}, tag)
-    assert cos_sim(pose.r.grad, po["r"].grad) > 0.99 and cos_sim(pose.t.grad, po["t"].grad) > 0.99
+    c_r, c_t = cos_sim(pose.r.grad, po["r"].grad), cos_sim(pose.t.grad, po["t"].grad)
+    print(f"[measured] pose gradient cos: r {c_r:.5f}, t {c_t:.5f} (asserted > 0.999)")
+    assert c_r > 0.999 and c_t > 0.999
 
 
 def test_fused_query_chain_matches_layered_path(monkeypatch):

@@ -198,7 +198,15 @@ def test_up_sample_and_merge(small_params):
     for S, inv_s in ((64, 64), (80, 128), (96, 256), (112, 512)):
         nz, cdf, inds = r.up_sample(ro, rd, cu(u[f"z{S}"]), cu(u[f"sdf{S}"]), 16, inv_s, return_aux=True)
         assert_close(cdf, u[f"cdf{S}"], 2e-6, f"cdf{S}")
-        assert (inds.cpu() != u[f"inds{S}"]).float().mean() < 0.02, "indices may only differ at 1-ulp CDF ties"
+        # the contract is "bit-exact WHEN FED THE REFERENCE'S CDF" (test_sample_cdf_bit_exact above: torch.equal); here the kernel
+        # builds its own CDF (within 2e-6), so an index may differ only where u sits within that distance of a CDF entry
+        mism = (inds.cpu() != u[f"inds{S}"])
+        print(f"[measured] up_sample S={S}: {int(mism.sum())} of {mism.numel()} indices differ from the reference's (own CDF)")
+        assert mism.float().mean() < 0.02, "indices may only differ at 1-ulp CDF ties"
+        if mism.any():
+            uu = torch.linspace(0.5 / 16, 1 - 0.5 / 16, 16).expand_as(mism)
+            gap = (u[f"cdf{S}"].unsqueeze(1) - uu.unsqueeze(-1)).abs().min(dim=-1)[0]
+            assert float(gap[mism].max()) < 4e-6, "an index differs although u is not within the CDF tolerance of an entry"
         assert_close(nz, u[f"new_z{S}"], 2e-5, f"new_z{S}")
     z2, s2 = r.cat_z_vals(ro, rd, cu(u["t"]), cu(u["z64"]), cu(u["new_z64"]), cu(u["sdf64"]), last=False)
     assert torch.equal(z2.cpu(), u["cat_z"])
