@@ -67,3 +67,28 @@ def test_two_rank_flat_allreduce_equals_single_rank():
     for rank, flat, w in got:
         assert torch.allclose(flat, ref, atol=1e-6), rank
         assert w == 64.0
+
+
+def test_flat_grad_bucket_keeps_and_reattaches_gradients():
+    """ADVICE (round 1): building the bucket must not discard gradients that already exist, and gradients that autograd
+    allocated outside the bucket (optimizer.zero_grad(set_to_none=True) dropped the views) must be pulled back in by
+    allreduce_() instead of a stale buffer being exchanged."""
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Tanh(), torch.nn.Linear(6, 2))
+    x = torch.randn(10, 4)
+    net(x).pow(2).sum().backward()
+    ref = torch.cat([p.grad.reshape(-1).clone() for p in net.parameters()])
+    bucket = FlatGradBucket(net.parameters())                  # after backward(): the gradients are copied in, not zeroed
+    assert torch.allclose(bucket.flat, ref)
+    for p in net.parameters():
+        assert p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    opt.zero_grad()                                            # set_to_none=True: the views are gone
+    assert all(p.grad is None for p in net.parameters())
+    net(x).pow(2).sum().backward()                             # fresh .grad tensors outside the bucket
+    bucket.allreduce_()                                        # single rank: no exchange, but the re-attach must happen
+    assert torch.allclose(bucket.flat, ref)
+    bucket.zero_()
+    assert float(bucket.flat.abs().max()) == 0.0 and all(float(p.grad.abs().max()) == 0.0 for p in net.parameters())
+    net(x).pow(2).sum().backward()                             # accumulates into the views again
+    assert torch.allclose(bucket.flat, ref)
