@@ -79,8 +79,10 @@ def test_bf16_fields_backward_full_size():
     # (bias gradients, and weight_g = a second reduction over a row of dW) are almost pure cancellation: their
     # relative error is ~ sqrt(P) * 2^-9 * rms / |sum|.  Real losses (the full-step tests below) do not have that
     # structure and hold 0.999 on every tensor.
-    check_grads(r.sdf_network.named_parameters(), {k: v.grad for k, v in Pg["sdf"].items()}, "sdf", bias_cos=0.98, cos=0.99)
-    check_grads(r.color_network.named_parameters(), {k: v.grad for k, v in Pg["color"].items()}, "color", bias_cos=0.98,
+    # Measured on the B200 (round 2): SDF 0.99956 / 0.99941 (weights / biases), colour 0.99385 / 0.99223 - the colour net sees the
+    # cancellation twice (its own reductions and the upstream gradient of the SDF features), so it keeps the 0.99 floor here.
+    check_grads(r.sdf_network.named_parameters(), {k: v.grad for k, v in Pg["sdf"].items()}, "sdf", bias_cos=0.999, cos=0.999)
+    check_grads(r.color_network.named_parameters(), {k: v.grad for k, v in Pg["color"].items()}, "color", bias_cos=0.99,
                 cos=0.99)
     assert cos_sim(xc.grad, xo.grad) > COS
 
@@ -343,12 +345,12 @@ def test_bf16_value_only_backward_fused_vs_layered_and_oracle(monkeypatch, n):
         (torch.mean(torch.abs(yo[:, :1] - tgt)) + (yo * wy).mean()).backward()
         assert cos_sim(res["fused"]["y"], yo) > COS
         assert cos_sim(res["fused"]["dx"], xo.grad) > 0.99
-        check_grads(res_named(res["fused"]), {k: v.grad for k, v in Pg.items()}, "sdf value-only", bias_cos=0.98, cos=0.99)
+        check_grads(res_named(res["fused"]), {k: v.grad for k, v in Pg.items()}, "sdf value-only", bias_cos=0.999, cos=0.999)
         Ps = {k: v.clone().requires_grad_(True) for k, v in P["sdf"].items()}      # .sdf(): fused value + sweep forward, fused backward
         xs = x.clone().requires_grad_(True)
         torch.mean(torch.abs(O.sdf_value(Ps, xs) - tgt)).backward()
         assert cos_sim(res["fused_sdf"]["dx"], xs.grad) > 0.99
-        check_grads(res_named(res["fused_sdf"]), {k: v.grad for k, v in Ps.items()}, "sdf()", bias_cos=0.98, cos=0.99)
+        check_grads(res_named(res["fused_sdf"]), {k: v.grad for k, v in Ps.items()}, "sdf()", bias_cos=0.999, cos=0.999)
 
 
 def res_named(d):
