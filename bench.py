@@ -533,6 +533,12 @@ def main():
             torch.cuda.empty_cache()
         sweep = []
         for nr in (4096, 16384, 32768):
+            torch.cuda.empty_cache()
+            need = nr * 128 * 36 * 1024          # ~28 kB of saved stacks + workspace per sample point, 1.25x scratch slack
+            free = torch.cuda.mem_get_info(dev)[0]
+            if need > 0.9 * free:                # never walk into an out-of-memory condition on the box
+                sweep.append({"rays_per_gpu": nr, "skipped": f"needs ~{need / 2**30:.0f} GiB of saved activation stacks, {free / 2**30:.0f} GiB free"})
+                continue
             try:
                 rw = Runner(C, dev, prec, nr, world, rank, 5, 1.0 / world, "none")
                 ms = timed_region(rw.step, rw.resident, 3, 2)
