@@ -533,6 +533,7 @@ def main():
             torch.cuda.empty_cache()
         sweep = []
         for nr in (4096, 16384, 32768):
+            L._scratch.clear()                   # the grow-only per-stream scratch of the previous size
             torch.cuda.empty_cache()
             need = nr * 128 * 36 * 1024          # ~28 kB of saved stacks + workspace per sample point, 1.25x scratch slack
             free = torch.cuda.mem_get_info(dev)[0]
