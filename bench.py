@@ -543,7 +543,10 @@ def main():
             torch.cuda.empty_cache()
             need = nr * 128 * 36 * 1024          # ~28 kB of saved stacks + workspace per sample point, 1.25x scratch slack
             free = torch.cuda.mem_get_info(dev)[0]
-            if need > 0.9 * free:                # never walk into an out-of-memory condition on the box
+            fits = torch.tensor([1 if need <= 0.85 * free else 0], device=dev)
+            if world > 1:                        # ONE decision for all ranks: a rank that skipped would leave the others in a collective
+                dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+            if int(fits.item()) == 0:            # never walk into an out-of-memory condition on the box
                 sweep.append({"rays_per_gpu": nr, "skipped": f"needs ~{need / 2**30:.0f} GiB of saved activation stacks, {free / 2**30:.0f} GiB free"})
                 continue
             try:
