@@ -1123,6 +1123,19 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
   return 0;
 }
 
+// workspace of the FORWARD entry points alone (inference render): sdf_fwd_bf16 uses [packed weights | ge0 | ge1], color_fwd_bf16
+// only the packed weights - a quarter of the training workspace, which also holds the T / zb2 / zb stacks of the backward
+int64_t sdf_fwd_ws_floats_bf16(const MlpShape& m, int64_t P) {
+  SdfB b;
+  if (make_sdfb(m, &b)) return -1;
+  return ((int64_t)b.w_total + 1) / 2 + 2 * P * 64 + 64;
+}
+int64_t color_fwd_ws_floats_bf16(const MlpShape& m) {
+  ColB c;
+  if (make_colb(m, -1, &c)) return -1;
+  return ((int64_t)c.w_total + 1) / 2 + 64;
+}
+
 // ------------------------------------------------------------------------------------------- weights packed once per step
 // The packed bf16 operands of a network (forward AND transposed blocks, in the layout every bf16 entry point expects at `wp`)
 // written behind its flat fp32 parameters: the five per-call re-packs of a training step become one launch per network.

@@ -66,6 +66,8 @@ int color_bwd_bf16(const MlpShape& m, const float* Wflat, const float* dirs, int
                    const float* saved, const float* d_rgb, float* dWflat, float* dx, float* ddirs, float* dnormals,
                    float* dfeat, int dfeat_ld, float* ws, cudaStream_t s, __nv_bfloat16* dfeat_b16 = nullptr,
                    int dfeat_b16_ld = 0, const __nv_bfloat16* wpx = nullptr);
+int64_t sdf_fwd_ws_floats_bf16(const MlpShape& m, int64_t P);
+int64_t color_fwd_ws_floats_bf16(const MlpShape& m);
 int64_t mlp_pack_elems_bf16(const MlpShape& m, int is_color, int Lv);
 int mlp_pack_bf16(const MlpShape& m, int is_color, int Lv, const float* Wflat, __nv_bfloat16* wp, cudaStream_t s);
 // COPE_FLAT_HAS_PACK: the packed bf16 weights follow the flat fp32 parameters (64-float aligned); nullptr when the flag is off

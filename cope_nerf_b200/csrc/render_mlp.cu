@@ -57,9 +57,20 @@ static int64_t infer_sdf_saved_floats(const cope_mlp_desc* sd, int64_t P, int pr
   return cope_sdf_saved_floats(sd, P, compact ? 0 : 1, prec);
 }
 
+// forward-only workspace: on the tensor-core path the two forward entry points need the packed weights and the PE-gradient
+// buffers only (7.5 kB per point with the saved blocks instead of 26.6 kB with the training workspace)
+static int64_t infer_core_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
+  if (prec != COPE_PREC_BF16) return cope_render_mlp_ws_floats(sd, cd, P, prec);
+  MlpShape ms, mc;
+  if (make_shape(sd, &ms) || make_shape(cd, &mc)) return -1;
+  const int64_t a = sdf_fwd_ws_floats_bf16(ms, P), b = color_fwd_ws_floats_bf16(mc);
+  if (a < 0 || b < 0) return -1;
+  return (a > b ? a : b) + 1024;
+}
+
 int64_t cope_render_mlp_infer_ws_floats(const cope_mlp_desc* sd, const cope_mlp_desc* cd, int64_t P, int prec) {
   prec &= 0xFF;
-  const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
+  const int64_t w = infer_core_ws_floats(sd, cd, P, prec);
   const int64_t a = infer_sdf_saved_floats(sd, P, prec), b = cope_color_saved_floats(cd, P, prec);
   if (w < 0 || a < 0 || b < 0) return -1;
   return w + a + b + 256;
@@ -73,7 +84,7 @@ int cope_render_mlp_infer(const cope_mlp_desc* sd, const float* sdfW, const cope
   if (P <= 0) return 0;
   const int flags = prec;
   prec &= 0xFF;
-  const int64_t w = cope_render_mlp_ws_floats(sd, cd, P, prec);
+  const int64_t w = infer_core_ws_floats(sd, cd, P, prec);
   const int64_t a = infer_sdf_saved_floats(sd, P, prec);
   COPE_REQUIRE(w >= 0 && a >= 0, "render_mlp_infer: unsupported network shape");
   float* sdf_saved = ws + ((w + 63) / 64) * 64;

@@ -164,7 +164,7 @@ def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, de
     predicted-optical-flow maps) without the reference's 1024-ray chunk loop and its per-chunk device -> host copies.
 
     chunk=None renders the whole pixel range in ONE pass (one launch per kernel of the pipeline) whenever its working set fits the
-    free device memory, and otherwise in the fewest equal passes that do (the inference path keeps ~7 kB per sample point);
+    free device memory, and otherwise in the fewest equal passes that do (sized with cope_render_mlp_infer_ws_floats);
     an integer forces that many rays per pass.  Every result stays on the device.
 
     Returns a dict of device tensors over the rendered pixels (row-major):
@@ -188,8 +188,14 @@ def render_image(renderer, world_mat, camera_mat, scale_mat, h, w, time_step, de
             KS = (scale_mat.reshape(-1, 4, 4)[0, :3, :3] @ camera_mat.reshape(-1, 4, 4)[0, :3, :3]).contiguous().float()
         out["flow_pred"] = torch.empty(count, 2, device=dev)
     if chunk is None:
+        # bytes per ray of one pass, from the library's own size query (the inference workspace: packed weights, H stack, colour
+        # input, PE gradients, ... ~26 kB per sample point) x the 1.25 growth slack of the scratch buffer, plus the per-sample
+        # outputs and sampling intermediates
         n_samples = renderer.n_samples + renderer.n_importance
-        per_ray = n_samples * 7168 + 4096                      # bytes per ray of the inference path (saved H stack + colour input + outputs)
+        sn, cn = renderer.sdf_network, renderer.color_network
+        probe = 1024 * n_samples
+        ws = L.query("cope_render_mlp_infer_ws_floats", sn.desc, cn.desc, probe, sn.precision)
+        per_ray = int(ws * 4 * 1.25 / 1024) + n_samples * 160 + 4096
         free = torch.cuda.mem_get_info(dev)[0] if torch.cuda.is_available() else 0
         budget = max(int(free * 0.6), per_ray * 1024)
         passes = max(1, -(-count * per_ray // budget))
