@@ -51,7 +51,7 @@ def eval_image(rnd, pk, dev, h, w, chunk):
     nrank = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     first, last = rank * (h * w) // nrank, (rank + 1) * (h * w) // nrank
-    fn = lambda: C.training.render_image(rnd, world, K, S, h, w, t0, (0.01, 5.0), chunk=chunk, rays=(first, last - first))
+    fn = lambda: C.training.render_image(rnd, world, K, S, h, w, t0, (0.01, 5.0), chunk=(chunk or None), rays=(first, last - first))
     if nrank > 1:
         dist.barrier()
     t = timeit(fn, iters=3, warm=1)
@@ -135,7 +135,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, nargs="*", default=[4096, 16384, 65536, 262144])
     ap.add_argument("--eval-image", type=int, nargs=2, default=[484, 648], metavar=("H", "W"))
-    ap.add_argument("--eval-chunk", type=int, default=16384)
+    ap.add_argument("--eval-chunk", type=int, default=16384, help="rays per pass of the evaluation render; 0 = as few passes as fit the free memory")
     ap.add_argument("--eval-only", action="store_true", help="only the evaluation-image row (the one that runs under torchrun)")
     ap.add_argument("--hbm-only", action="store_true", help="only the HBM-bound kernels (sampling, compositing, losses): the ncu pass")
     ap.add_argument("--iters", type=int, default=0)
