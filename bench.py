@@ -69,25 +69,73 @@ def camera():
 
 
 class ClockSampler:
+    """SM clock + clock-event reasons of one GPU DURING a timed region.  In-process NVML thread (5 ms period: a 20-step region of
+    60 ms still yields ~10 samples); `nvidia-smi -lms` as the fallback when NVML cannot be loaded (its start-up alone can outlast a
+    short region, which is why it is only the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.path = gpu, None, None
+        self.nvml, self.handle, self.thread, self.samples, self.halt = None, None, None, [], None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:                 # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go through the UUID
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(gpu).uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv, h = self.nvml, self.handle
+        while not self.halt.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            self.halt.wait(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.samples, self.halt = [], threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            self.thread = None
+            sm = sorted(c for c, _ in self.samples)
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            if sm:
+                try:
+                    mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                except Exception:
+                    mx = max(sm)
+                out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(n for n, b in self.REASONS if bits & b),
+                           samples=len(sm), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -110,7 +158,7 @@ class ClockSampler:
             pass
         if sm:
             sm.sort()
-            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
@@ -406,6 +454,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=512, help="ray sample of the CPU baseline step (BASELINE.json configs[0]: 512 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / ray-sweep / eager-CUDA extras of the JSON line")
+    ap.add_argument("--no-sweep", action="store_true", help="skip only the 4K-32K ray sweep of the extras")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph-mode", default="auto", choices=["auto", "full", "compute", "none"],
                     help="auto: the whole step (incl. fused Adam) as one graph on one GPU; forward + backward as one graph with the NCCL "
@@ -460,16 +509,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(fn, batches, steps, warmup):
+    def timed_region(fn, batches, steps, warmup, sampler=None):
         for b in batches[:warmup]:
             fn(b)
         barrier()
+        if sampler is not None:      # clocks are sampled between the two barriers, i.e. while the timed steps run on the GPU
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for b in batches[warmup:warmup + steps]:
             fn(b)
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.result = sampler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -477,9 +530,8 @@ def main():
 
     # ---- value: device-resident inputs
     clocks = ClockSampler(local)
-    clocks.start()
-    ms_total = timed_region(run.step, run.resident, args.steps, args.warmup)
-    clk = clocks.stop()
+    ms_total = timed_region(run.step, run.resident, args.steps, args.warmup, sampler=clocks)
+    clk = clocks.result
     ms_per_step = ms_total / args.steps
     value = total_rays * args.steps / (ms_total * 1e-3)
     # launches of OUR kernels per step: kernels inside a replayed graph do not pass through the library's launch counter, so one
@@ -538,7 +590,7 @@ def main():
             del rs
             torch.cuda.empty_cache()
         sweep = []
-        for nr in (4096, 16384, 32768):
+        for nr in (() if args.no_sweep else (4096, 16384, 32768)):
             L._scratch.clear()                   # the grow-only per-stream scratch of the previous size
             torch.cuda.empty_cache()
             need = nr * 128 * 36 * 1024          # ~28 kB of saved stacks + workspace per sample point, 1.25x scratch slack
@@ -558,9 +610,10 @@ def main():
             except Exception as e:      # pragma: no cover - memory of the box
                 sweep.append({"rays_per_gpu": nr, "error": f"{type(e).__name__}: {str(e)[:80]}"})
             torch.cuda.empty_cache()
-        extras["sweep"] = {"unit": "rays/s (whole job)", "launch": "eager", "points": sweep,
-                           "note": "training steps at 4K-32K rays per GPU x 128 samples (configs[4]; 32K rays/GPU = 256K rays at 8 GPUs); "
-                                   "the fraction counts the WHOLE step against the MLP FLOPs, so it is a lower bound of the MLP group's own"}
+        if not args.no_sweep:
+            extras["sweep"] = {"unit": "rays/s (whole job)", "launch": "eager", "points": sweep,
+                               "note": "training steps at 4K-32K rays per GPU x 128 samples (configs[4]; 32K rays/GPU = 256K rays at 8 GPUs); "
+                                       "the fraction counts the WHOLE step against the MLP FLOPs, so it is a lower bound of the MLP group's own"}
 
     if rank == 0:
         pk = peaks()
