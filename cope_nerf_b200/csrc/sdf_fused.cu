@@ -36,9 +36,10 @@ template <int MODE> struct Cfg;
 template <> struct Cfg<FZ_FWD> { static constexpr int kW = 3, kAux = 2, kStg = 1, kBias = (COPE_MAX_LIN * 256 + 64) * 4; };
 template <> struct Cfg<FZ_TAN> { static constexpr int kW = 2, kAux = 5, kStg = 1, kBias = 0; };
 // ADJ (H + zb2 tiles streamed): measured kW / kAux = 2 / 6: 344 us, 3 / 4: 317 us, 4 / 2: 401 us.  TAN (H + delta): 2 / 5: 351 us, 3 / 3: 415 us
-template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 3, kAux = 4, kStg = 0, kBias = 0; };
+// kBias: 1 KB for row 0 of the last layer (d sdf / d H_top), read by every tile's top step
+template <> struct Cfg<FZ_ADJ> { static constexpr int kW = 3, kAux = 4, kStg = 0, kBias = 1024; };
 // value-path adjoint (no zb2 tiles to stream): the freed auxiliary slots go to the weight ring (2 / 6: 292 us, 3 / 3: 284 us, 4 / 2: 278 us)
-template <> struct Cfg<FZ_ADJ1> { static constexpr int kW = 4, kAux = 2, kStg = 0, kBias = 0; };
+template <> struct Cfg<FZ_ADJ1> { static constexpr int kW = 4, kAux = 2, kStg = 0, kBias = 1024; };
 constexpr bool is_adj(int mode) { return mode == FZ_ADJ || mode == FZ_ADJ1; }
 template <int MODE> using Lay = ChainLay<4, Cfg<MODE>::kW, Cfg<MODE>::kAux, Cfg<MODE>::kStg, Cfg<MODE>::kBias>;
 
@@ -99,6 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
     if (threadIdx.x == 0) sBias[a.n_lin * 256] = a.Wflat[a.b_off[a.n_lin - 1]];   // sdf bias (row 0)
     if (a.n_lin + 2 <= COPE_MAX_LIN)      // row 0 of the last layer (d sdf / d H_top), read by the top of the reverse sweep
       for (int i = threadIdx.x; i < 256; i += kThreads) sBias[(a.n_lin + 1) * 256 + i] = a.Wflat[a.w_top_off + i];
+  }
+  if (is_adj(MODE)) {
+    // with the shared-memory carve-out at its maximum there is no L1: 16 scalar __ldg per slab at the top step of every tile were
+    // 16 exposed L2 round trips (8.7 % of the value-path adjoint's stall samples, profiles/r02 source page)
+    for (int i = threadIdx.x; i < 256; i += kThreads) sBias[i] = a.Wflat[a.w_top_off + i];
   }
   if (warp == kMma) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -508,8 +514,11 @@ __global__ void __launch_bounds__(kThreads, 1) sdf_fused_kernel(const __grid_con
             float v[16];
             tmem_ld16(taddr + n0, v);
             if (l == top && a.d_sdf) {
+              float wz[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(dsdf, __ldg(w0 + n0 + i), v[i]);
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(wz + 4 * i) = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(dsdf, wz[i], v[i]);
             }
             if (n0 + 16 <= nsplit) {
               if (split) {
