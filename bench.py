@@ -205,9 +205,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.rays), "rays_per_gpu": args.rays, "rays_per_step_timed_here": n},
+        "config": workload_config(args.rays, args.gpus),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} rays x 64+64 samples per step, same nets/losses/Adam, oracle port of the "
+                         "sample": f"{n} of the {args.rays} rays x 64+64 samples per step, same nets/losses/Adam, oracle port of the "
                                    f"reference's PyTorch CPU path, torch threads = {cores}"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,6 +218,13 @@ def run_reference(args):
 def workload_name(rays):
     return (f"Co3D-skateboard NeuS train step: {rays} rays/GPU (4x4 patches of a {H}x{W} synthetic frame) x 64+64 "
             "samples, up_sample 4 iters, SDF 8x256 PE6 4-D, colour 4x256, rgb+eikonal+pose grads, Adam")
+
+
+def workload_config(rays, world):
+    """`config` of the JSON line: the WORKLOAD only, identical for both arms (how an arm runs it is in `implementation` / `cpu_baseline`)."""
+    return {"workload": workload_name(rays), "rays_per_gpu": rays,
+            "parallelism": f"dp{world} (rays sharded over the GPUs, one flat gradient all-reduce per step)",
+            "l2": "per-step working set (saved activations, >1 GB) exceeds the 126 MB L2; new ray batch every step"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -626,10 +633,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32" if prec == C.PREC_FP32 else "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(n), "rays_per_gpu": n, "parallelism": f"dp{world} (rays sharded, one flat-grad allreduce)",
-                       "precision": "fp32 SIMT (strict parity)" if prec == C.PREC_FP32 else "bf16 tcgen05, fp32 accumulate",
-                       "launch": graph_note,
-                       "l2": "per-step working set (saved activations, >1 GB) exceeds the 126 MB L2; new ray batch every step"},
+            "config": workload_config(n, world),
+            "implementation": {"precision": "fp32 SIMT (strict parity)" if prec == C.PREC_FP32 else "bf16 tcgen05, fp32 accumulate",
+                               "launch": graph_note},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

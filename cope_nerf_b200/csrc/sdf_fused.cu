@@ -10,8 +10,8 @@
 //   FZ_ADJ  adjoint sweep: zb_{l-1} = a (W_l^T zb_l) sp_l + zb2_{l-1}; eb0 / eb1 = gradient w.r.t. the PE
 //
 // Warp roles: 0-15 epilogue (4 per TMEM lane quarter; each owns a 16-column slab of every 64-column panel),
-// 16 weight producer (bulk TMA of 16 KB K=32 chunks into a 3-deep ring), 17 tcgen05.mma issuer + TMEM owner,
-// 18 TMA-store issuer, 19 auxiliary-tile producer (H / delta / zb2 panels into a 4-deep ring).
+// 16 weight producer (bulk TMA of 32 KB N = 256 x K = 64 chunks into a 2-4 deep ring, Cfg<MODE>), 17 tcgen05.mma issuer + TMEM
+// owner, 18 TMA-store issuer, 19 auxiliary-tile producer (16 KB H / delta / zb2 panels into a 2-5 deep ring).
 // The MMAs of layer l+1 start on K-panel j as soon as the epilogue of layer l has written panel j.
 #include "sdf_fused.cuh"
 
