@@ -280,7 +280,7 @@ def mlp_traffic_from_profile():
         return None, None
 
 
-def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True):
+def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True, optimizer="flat"):
     """The reference's WHOLE stage-1 iteration (train.py:407-532) on one GPU: on-device patch sampling + rays (process_data),
     fused render + rgb / eikonal / SDF-flow node, flow-RGB over the valid reference frames, SDF-consistency re-query (another
     131 072-point SDF forward + backward), depth-patch smoothness, backward into SDF / colour / variance / MotionNetwork, both
@@ -292,8 +292,6 @@ def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True):
     rnd = C.training.build_networks(device=dev, precision=prec)
     mot = C.MotionNetwork(d_out=6, d_in=1, d_hidden=256, n_layers=4, skip_in=[2], multires=6, bias=0.5, scale=1.0, geometric_init=False,
                           weight_norm=True).to(dev)
-    opt = torch.optim.Adam(list(rnd.parameters()), lr=1e-3, fused=True, capturable=True)
-    mopt = torch.optim.Adam(list(mot.parameters()), lr=5e-4, fused=True, capturable=True)
     g = torch.Generator().manual_seed(5)
     img = torch.rand(1, 3, H, W, generator=g).to(dev)
     refs = torch.rand(3, 3, H, W, generator=g).to(dev)
@@ -309,6 +307,12 @@ def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True):
                   ref=torch.tensor(ref_idx, device=dev), valid=torch.ones(3, device=dev), cons_on=torch.ones(1, device=dev))
     from cope_nerf_b200.dist import FlatGradBucket
     bucket = FlatGradBucket(list(rnd.parameters()) + list(mot.parameters()))      # one fill launch clears every gradient
+    if optimizer == "flat":          # train.py:59-60: one Adam for the NeuS networks, one for the MotionNetwork
+        opt = C.optim.FlatAdam(bucket, lr=1e-3, params=list(rnd.parameters()))
+        mopt = C.optim.FlatAdam(bucket, lr=5e-4, params=list(mot.parameters()))
+    else:
+        opt = torch.optim.Adam(list(rnd.parameters()), lr=1e-3, fused=True, capturable=True)
+        mopt = torch.optim.Adam(list(mot.parameters()), lr=5e-4, fused=True, capturable=True)
 
     def new_inputs():
         static["corners"].copy_(torch.randint(0, n_corner, (n_rays // 16,), device=dev))
@@ -368,7 +372,7 @@ class Runner:
     """One configuration of the training step on this rank: networks, optimiser, synthetic batches, and the step as ONE CUDA
     graph (pose -> rays -> sampling -> render -> loss -> backward -> gradient all-reduce -> fused Adam)."""
 
-    def __init__(self, C, dev, prec, n_rays, world, rank, n_batches, loss_scale, graph_mode):
+    def __init__(self, C, dev, prec, n_rays, world, rank, n_batches, loss_scale, graph_mode, optimizer="flat"):
         from cope_nerf_b200.dist import FlatGradBucket
         self.C, self.dev, self.n, self.world = C, dev, n_rays, world
         torch.manual_seed(678)
@@ -377,7 +381,10 @@ class Runner:
         with torch.no_grad():
             self.pose.r.copy_(torch.randn(1, 3) * 0.05); self.pose.t.copy_(torch.randn(1, 3) * 0.05)
         self.bucket = FlatGradBucket(list(self.rnd.parameters()) + [self.pose.r, self.pose.t])
-        self.opt = torch.optim.Adam(self.bucket.params, lr=1e-3, fused=True, capturable=True)
+        if optimizer == "flat":      # ONE elementwise launch over the flat parameter / gradient / moment buffers (cope_adam_step)
+            self.opt = C.optim.FlatAdam(self.bucket, lr=1e-3)
+        else:                        # torch's fused multi-tensor Adam: two ~50 us launches over the ~80 parameter tensors
+            self.opt = torch.optim.Adam(self.bucket.params, lr=1e-3, fused=True, capturable=True)
         self.Kc, self.Sc = camera().to(dev), torch.eye(4, device=dev).unsqueeze(0)
         self.tstep = torch.zeros(1, device=dev)
         host = synth_inputs(n_rays, n_batches, seed=678 + 1000 * rank)
@@ -461,6 +468,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=512, help="ray sample of the CPU baseline step (BASELINE.json configs[0]: 512 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / ray-sweep / eager-CUDA extras of the JSON line")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: optim.FlatAdam = one cope_adam_step launch over flat buffers; torch: torch.optim.Adam(fused=True, capturable=True)")
     ap.add_argument("--no-sweep", action="store_true", help="skip only the 4K-32K ray sweep of the extras")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph-mode", default="auto", choices=["auto", "full", "compute", "none"],
@@ -508,7 +517,7 @@ def main():
         args.graph_mode = "full" if world == 1 else "compute"
     total_rays = args.rays if (args.strong and world > 1) else n * world
     # rgb (sum/N) and eikonal (mean) are shard-linear: scale the local loss by this rank's share of the batch
-    run = Runner(C, dev, prec, n, world, rank, args.steps + args.warmup, n / total_rays, args.graph_mode)
+    run = Runner(C, dev, prec, n, world, rank, args.steps + args.warmup, n / total_rays, args.graph_mode, args.optimizer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -589,7 +598,7 @@ def main():
         torch.cuda.empty_cache()
         if world > 1:
             lo, hi = shard_range(1024, rank, world)
-            rs = Runner(C, dev, prec, hi - lo, world, rank, 13, (hi - lo) / 1024.0, args.graph_mode)
+            rs = Runner(C, dev, prec, hi - lo, world, rank, 13, (hi - lo) / 1024.0, args.graph_mode, args.optimizer)
             ms = timed_region(rs.step, rs.resident, 10, 3)
             extras["strong"] = {"rays_total": 1024, "rays_per_gpu": hi - lo, "ms_per_step": ms / 10, "value": 1024 * 10 / (ms * 1e-3),
                                 "unit": "rays/s", "launch": rs.note,
@@ -609,7 +618,7 @@ def main():
                 sweep.append({"rays_per_gpu": nr, "skipped": f"needs ~{need / 2**30:.0f} GiB of saved activation stacks, {free / 2**30:.0f} GiB free"})
                 continue
             try:
-                rw = Runner(C, dev, prec, nr, world, rank, 5, 1.0 / world, "none")
+                rw = Runner(C, dev, prec, nr, world, rank, 5, 1.0 / world, "none", args.optimizer)
                 ms = timed_region(rw.step, rw.resident, 3, 2)
                 sweep.append({"rays_per_gpu": nr, "ms_per_step": ms / 3, "value": nr * world * 3 / (ms * 1e-3),
                               "mlp_frac_of_sustained_bf16_upper_bound": nr * FLOP_PER_TRAIN_RAY / (ms / 3 * 1e-3) / 1e12 / peaks()["bf16_sustained"]})
@@ -635,7 +644,9 @@ def main():
             "vs_baseline": None, "dtype": "f32" if prec == C.PREC_FP32 else "bf16", "data": "synthetic",
             "config": workload_config(n, world),
             "implementation": {"precision": "fp32 SIMT (strict parity)" if prec == C.PREC_FP32 else "bf16 tcgen05, fp32 accumulate",
-                               "launch": graph_note},
+                               "launch": graph_note,
+                               "optimizer": "optim.FlatAdam (cope_adam_step, one launch over flat buffers)" if args.optimizer == "flat"
+                               else "torch.optim.Adam(fused=True, capturable=True)"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -658,7 +669,7 @@ def main():
                                               f"nets/losses/Adam, oracle port of the reference's PyTorch CPU path"}
         if world == 1 and not args.no_extras:
             try:
-                ms1, note1 = stage1_step_ms(C, dev, prec, 1024, 10, 3)
+                ms1, note1 = stage1_step_ms(C, dev, prec, 1024, 10, 3, optimizer=args.optimizer)
                 line["stage1"] = {"ms_per_step": ms1, "value": 1024 / (ms1 * 1e-3), "unit": "rays/s", "launch": note1,
                                   "note": "the reference's whole stage-1 iteration (train.py:407-532): render + rgb / eikonal / SDF-flow + flow-RGB (3 "
                                           "reference frames) + SDF-consistency re-query + depth-patch smoothness + MotionNetwork, both Adam steps"}

@@ -14,7 +14,7 @@ from .renderer import NeuSRenderer, sample_pdf
 from .motion import MotionNetwork
 from .common import (Exp, PoseRetriever, arange_pixels, convert3x4_4x4, get_world_cameraOrigin_cameraRay, make_c2w,
                      pixels_from_indices, vec2skew)
-from . import losses, pose_refinement, training
+from . import losses, optim, pose_refinement, training
 
 # precision bench.py / smoke use when none is requested: the tensor-core path (strict fp32 parity mode: PREC_FP32)
 DEFAULT_PRECISION = PREC_BF16
@@ -22,4 +22,4 @@ DEFAULT_PRECISION = PREC_BF16
 __all__ = ["CopeError", "PREC_BF16", "PREC_FP32", "load_library", "get_embedder", "RenderingNetwork", "SDFNetwork", "MotionNetwork",
            "SingleVarianceNetwork", "NeuSRenderer", "sample_pdf", "Exp", "PoseRetriever", "arange_pixels",
            "convert3x4_4x4", "get_world_cameraOrigin_cameraRay", "make_c2w", "pixels_from_indices", "vec2skew",
-           "training", "losses", "pose_refinement"]
+           "training", "losses", "pose_refinement", "optim"]

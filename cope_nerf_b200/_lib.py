@@ -97,6 +97,7 @@ _SIGS = {
     "cope_pose_refine_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
     "cope_pose_refine_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
     "cope_sample_pixels": (_i, [_f, C.c_uint64, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f]),
+    "cope_adam_step": (_i, [_f, _f, _f, _f, _l, _f, _fl, _fl, _fl, _fl, _fl, _f]),
     "cope_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _i, _f, _i, _f, _i, _i, _f]),
 }
 EXPORTS = tuple(_SIGS)

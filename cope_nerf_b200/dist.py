@@ -63,6 +63,7 @@ class FlatGradBucket:
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_params = None
         self._attach()
 
     def _views(self):
@@ -93,6 +94,36 @@ class FlatGradBucket:
     def zero_(self):
         self._attach()
         self.flat.zero_()
+
+    def flatten_params_(self):
+        """Move the PARAMETERS into one flat fp32 buffer laid out like the gradients (every `p.data` becomes a view of it, values
+        kept), so that an optimiser can update all of them with one elementwise launch (optim.FlatAdam).  Do this before a CUDA
+        graph of the step is captured: kernels captured earlier keep reading the old storage.  Idempotent."""
+        if self.flat_params is None:
+            fp = torch.empty_like(self.flat)
+            off = 0
+            with torch.no_grad():
+                for p in self.params:
+                    n = p.numel()
+                    view = fp[off:off + n].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view
+                    off += n
+            self.flat_params = fp
+        return self.flat_params
+
+    def param_range(self, params):
+        """[lo, hi) element range of `params` inside the flat buffers; they must be a contiguous run of the bucket's parameters,
+        in the bucket's order (one optimiser / learning rate per run, as train.py:59-60 builds one Adam per network group)."""
+        ids = [id(p) for p in self.params]
+        want = [id(p) for p in params if p.requires_grad]
+        if not want or want[0] not in ids:
+            raise ValueError("param_range: parameters are not in this bucket")
+        k = ids.index(want[0])
+        if ids[k:k + len(want)] != want:
+            raise ValueError("param_range: parameters are not a contiguous run of the bucket's parameters (same order)")
+        lo = sum(p.numel() for p in self.params[:k])
+        return lo, lo + sum(p.numel() for p in self.params[k:k + len(want)])
 
     def allreduce_(self, average=False):
         """Sum (or mean) over ranks, in place.  Local losses must already carry the 1/world factor of any

@@ -330,6 +330,15 @@ int cope_pose_refine_bwd(const float* images, const float* next_images, const fl
 int cope_sample_pixels(const int64_t* corners, uint64_t seed, int h, int w, int patch_size, int n_patches, const float* img,
                        int64_t* ray_idx, float* pix, float* norm_pix, float* rgb_gt, cope_stream_t s);
 
+/* ---- optimiser step (train.py:59-60 builds torch.optim.Adam, model/training.py:552-558 steps it) ------------------------
+ * torch.optim.Adam (no amsgrad) over ONE flat fp32 buffer of n elements: param, grad, exp_avg, exp_avg_sq [n].
+ *   exp_avg += (1 - beta1) (grad - exp_avg);  exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) grad^2;
+ *   param -= lr / (1 - beta1^t) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps)
+ * step [1] is the device-resident step count t >= 1 (the caller increments it before the call, so CUDA-graph replays advance
+ * it); weight_decay != 0 adds weight_decay * param to the gradient first (L2 penalty, as torch.optim.Adam). */
+int cope_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* step, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, cope_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

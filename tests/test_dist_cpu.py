@@ -92,3 +92,35 @@ def test_flat_grad_bucket_keeps_and_reattaches_gradients():
     assert float(bucket.flat.abs().max()) == 0.0 and all(float(p.grad.abs().max()) == 0.0 for p in net.parameters())
     net(x).pow(2).sum().backward()                             # accumulates into the views again
     assert torch.allclose(bucket.flat, ref)
+
+
+def test_flatten_params_and_param_range():
+    """FlatGradBucket.flatten_params_: every p.data becomes a view of ONE flat buffer laid out like the gradients (values kept,
+    forward unchanged, idempotent); param_range: contiguous runs only.  optim.FlatAdam has no CPU path."""
+    import cope_nerf_b200 as C
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    before = [p.detach().clone() for p in net.parameters()]
+    x = torch.randn(4, 5)
+    y0 = net(x).detach().clone()
+    bucket = FlatGradBucket(list(net.parameters()))
+    fp = bucket.flatten_params_()
+    assert bucket.flatten_params_() is fp and fp.numel() == bucket.flat.numel() == 66
+    off = 0
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p.detach(), b) and p.data_ptr() == fp.data_ptr() + 4 * off
+        off += p.numel()
+    assert torch.equal(net(x), y0)
+    net(x).sum().backward()                                  # gradients still land in the bucket's views
+    assert bucket.flat.abs().sum() > 0
+    fp.mul_(2.0)                                             # an update of the flat buffer IS an update of the module
+    assert torch.allclose(net[0].weight.detach(), before[0] * 2)
+    assert bucket.param_range(list(net[1].parameters())) == (42, 66)
+    assert bucket.param_range(list(net.parameters())) == (0, 66)
+    with pytest.raises(ValueError):
+        bucket.param_range([net[0].weight, net[1].weight])   # not a contiguous run
+    opt = C.optim.FlatAdam(bucket, lr=1e-3, params=list(net[1].parameters()))
+    assert opt.range == (42, 66) and isinstance(opt, torch.optim.Optimizer)
+    torch.optim.lr_scheduler.MultiStepLR(opt, [1], 0.1)      # schedulers attach (train.py:61-64)
+    with pytest.raises(C.CopeError):
+        opt.step()                                           # CPU tensors: no fallback

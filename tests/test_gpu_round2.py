@@ -460,3 +460,73 @@ def test_stage1_static_form_equals_reference_control_flow():
         assert worst < 2e-3, worst
         print(f"Stage1Static vs stage1_losses (world frame {world_idx}): flow-rgb {float(fb):.6f} / {float(fa):.6f}, "
               f"consistency {float(cb):.6f} / {float(ca):.6f}, worst gradient rel {worst:.2e}")
+
+
+# ------------------------------------------------------------------------------------------------ optimiser step (train.py:59-60)
+def test_flat_adam_matches_torch_adam():
+    """optim.FlatAdam (cope_adam_step over the flat parameter / gradient / moment buffers) against torch.optim.Adam on the real
+    networks' parameters: two optimisers with different learning rates over contiguous runs of ONE bucket (as train.py:59-60 builds
+    one Adam for the NeuS networks and one for the MotionNetwork), six steps of gradients spanning six decades, weight decay on one."""
+    torch.manual_seed(3)
+    rnd = C.training.build_networks(C.training.DEFAULT_CFG, device=DEV, precision=C.PREC_FP32)
+    pose = C.PoseRetriever(2).to(DEV)
+    pa, pb = list(rnd.parameters()), [pose.r, pose.t]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in pa + pb]
+    o_ref = [torch.optim.Adam(ref[:len(pa)], lr=1e-3), torch.optim.Adam(ref[len(pa):], lr=5e-4, weight_decay=0.01, betas=(0.8, 0.99))]
+    x = torch.rand(64, 4, device=DEV) - 0.5
+    with torch.no_grad():
+        y0 = rnd.sdf_network.sdf(x).clone()
+    bucket = FlatGradBucket(pa + pb)
+    o_a = C.optim.FlatAdam(bucket, lr=1e-3, params=pa)
+    o_b = C.optim.FlatAdam(bucket, lr=5e-4, weight_decay=0.01, betas=(0.8, 0.99), params=pb)
+    assert o_a.range == (0, sum(p.numel() for p in pa)) and o_b.range[1] == bucket.flat.numel()
+    with torch.no_grad():
+        assert torch.equal(rnd.sdf_network.sdf(x), y0), "flattening the parameters must not change the network"
+    start = [p.detach().clone() for p in ref]
+    for it in range(6):
+        bucket.zero_()
+        for p, q in zip(pa + pb, ref):
+            g = torch.randn_like(p) * 10.0 ** float(torch.randint(-5, 2, (1,)))
+            p.grad.copy_(g)                      # the bucket's views
+            q.grad = g.clone()
+        for o in o_ref:
+            o.step()
+        o_a.step(); o_b.step()
+    worst = 0.0
+    for p, q, s in zip(pa + pb, ref, start):
+        assert p.data_ptr() >= bucket.flat_params.data_ptr()
+        worst = max(worst, rel_err(p.detach() - s, q.detach() - s))        # error of the accumulated UPDATE, not of the parameter
+    print(f"[measured] FlatAdam vs torch.optim.Adam, six steps: worst relative error of the accumulated update {worst:.2e}")
+    assert worst < 1e-4
+    assert float(o_a.step_t) == 6.0
+    with torch.no_grad():
+        y1 = rnd.sdf_network.sdf(x)
+    assert (y1 - y0).abs().max() > 0, "the kernels read the updated flat parameters"
+
+
+def test_flat_adam_step_in_cuda_graph_advances():
+    """The step count lives on the device: replays of a captured step keep advancing the bias corrections (capturable Adam)."""
+    torch.manual_seed(4)
+    p = torch.nn.Parameter(torch.randn(1000, device=DEV))
+    q = torch.nn.Parameter(p.detach().clone())
+    bucket = FlatGradBucket([p])
+    opt, ref = C.optim.FlatAdam(bucket, lr=1e-2), torch.optim.Adam([q], lr=1e-2)
+    g = torch.randn(1000, device=DEV)
+    p.grad.copy_(g)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        opt.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    for _ in range(4):
+        q.grad = g.clone()
+        ref.step()
+    assert float(opt.step_t) == 4.0
+    assert_close(p.detach(), q.detach(), 1e-5, "four Adam steps (one eager + three replays)")
