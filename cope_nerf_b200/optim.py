@@ -41,6 +41,8 @@ class FlatAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if not self.flat_param.is_cuda:
+            raise L.CopeError("FlatAdam.step needs CUDA tensors (cope_adam_step; there is no CPU fallback)")
         self.bucket._attach()       # gradients that strayed outside the bucket (optimizer.zero_grad(set_to_none=True)) come back first
         g = self.param_groups[0]
         self.step_t.add_(1.0)
