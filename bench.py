@@ -370,7 +370,7 @@ def stage1_step_ms(C, dev, prec, n_rays, steps, warmup, use_graph=True, optimize
 
 class Runner:
     """One configuration of the training step on this rank: networks, optimiser, synthetic batches, and the step as ONE CUDA
-    graph (pose -> rays -> sampling -> render -> loss -> backward -> gradient all-reduce -> fused Adam)."""
+    graph (pose -> rays -> sampling -> render -> loss -> backward -> gradient all-reduce -> Adam step: optim.FlatAdam by default)."""
 
     def __init__(self, C, dev, prec, n_rays, world, rank, n_batches, loss_scale, graph_mode, optimizer="flat"):
         from cope_nerf_b200.dist import FlatGradBucket
@@ -414,7 +414,7 @@ class Runner:
         return loss
 
     def _capture(self, mode):
-        """mode 'full': the whole step incl. the gradient exchange and the (capturable) fused Adam in one graph - used on ONE GPU, where
+        """mode 'full': the whole step incl. the gradient exchange and the Adam step (device-resident step count) in one graph - used on ONE GPU, where
         the exchange is a no-op; mode 'compute' (N > 1): forward + backward as one graph, NCCL all-reduce and Adam launched eagerly
         behind the replay on the same stream.  Measured at 8 GPUs: 'compute' 2.92 ms per step; with the all-reduce captured inside the
         graph one run took 3.95 ms per step and the next one hung in the replayed collective, so NCCL is never captured by default."""
@@ -436,8 +436,8 @@ class Runner:
                     if attempt == "full":
                         self.exchange_and_update()
                 self.graph, self.static_loss, self.tail_eager = g, loss, attempt != "full"
-                self.note = ("one CUDA graph per step (fwd + bwd + gradient all-reduce + fused Adam)" if attempt == "full" else
-                             "one CUDA graph per step (fwd + bwd), eager all-reduce + fused Adam")
+                self.note = ("one CUDA graph per step (fwd + bwd + gradient all-reduce + Adam step)" if attempt == "full" else
+                             "one CUDA graph per step (fwd + bwd), eager all-reduce + Adam step")
                 return
             except Exception as e:      # pragma: no cover - depends on the box
                 self.graph = None
