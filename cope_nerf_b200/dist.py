@@ -100,6 +100,8 @@ class FlatGradBucket:
         kept), so that an optimiser can update all of them with one elementwise launch (optim.FlatAdam).  Do this before a CUDA
         graph of the step is captured: kernels captured earlier keep reading the old storage.  Idempotent."""
         if self.flat_params is None:
+            if any(p.dtype != torch.float32 for p in self.params):
+                raise ValueError("flatten_params_: the flat buffers are fp32; found a parameter of another dtype")
             fp = torch.empty_like(self.flat)
             off = 0
             with torch.no_grad():
@@ -111,6 +113,19 @@ class FlatGradBucket:
                     off += n
             self.flat_params = fp
         return self.flat_params
+
+    def params_attached(self):
+        """True while every parameter still is the view of the flat parameter buffer that flatten_params_ made it.  `module.half()`,
+        `module.to(other_device)` or `p.data = ...` re-allocate the storage: an optimiser that updates the flat buffer would then
+        silently stop training those parameters, so optim.FlatAdam checks this at every eager step."""
+        if self.flat_params is None:
+            return False
+        base, off = self.flat_params.data_ptr(), 0
+        for p in self.params:
+            if p.data_ptr() != base + 4 * off or p.dtype != torch.float32:
+                return False
+            off += p.numel()
+        return True
 
     def param_range(self, params):
         """[lo, hi) element range of `params` inside the flat buffers; they must be a contiguous run of the bucket's parameters,

@@ -43,6 +43,9 @@ class FlatAdam(torch.optim.Optimizer):
                 loss = closure()
         if not self.flat_param.is_cuda:
             raise L.CopeError("FlatAdam.step needs CUDA tensors (cope_adam_step; there is no CPU fallback)")
+        if not self.bucket.params_attached():
+            raise L.CopeError("FlatAdam.step: a parameter no longer lives in the bucket's flat buffer (module.half() / .to(device) / "
+                              "p.data = ... after the optimiser was built?); rebuild the bucket and the optimiser")
         self.bucket._attach()       # gradients that strayed outside the bucket (optimizer.zero_grad(set_to_none=True)) come back first
         g = self.param_groups[0]
         self.step_t.add_(1.0)

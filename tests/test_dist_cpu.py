@@ -119,8 +119,11 @@ def test_flatten_params_and_param_range():
     assert bucket.param_range(list(net.parameters())) == (0, 66)
     with pytest.raises(ValueError):
         bucket.param_range([net[0].weight, net[1].weight])   # not a contiguous run
+    assert bucket.params_attached()
     opt = C.optim.FlatAdam(bucket, lr=1e-3, params=list(net[1].parameters()))
     assert opt.range == (42, 66) and isinstance(opt, torch.optim.Optimizer)
     torch.optim.lr_scheduler.MultiStepLR(opt, [1], 0.1)      # schedulers attach (train.py:61-64)
     with pytest.raises(C.CopeError):
         opt.step()                                           # CPU tensors: no fallback
+    net[0].weight.data = net[0].weight.data.clone()          # what module.half().float() / .to(device) do to the storage
+    assert not bucket.params_attached()                      # ... FlatAdam.step refuses instead of updating a stale buffer
